@@ -1,0 +1,217 @@
+/* sdb200.h -- C-ABI of libsdb200.so: B200 (sm_100a) kernels for the sdanalysis per-frame dynamics
+ * hot path.  Plain C, no torch types.  Every pointer named d_* is a DEVICE pointer owned by the
+ * caller (the Python host keeps them in torch tensors); h_* are HOST pointers.  All calls enqueue
+ * work on the given stream (a cudaStream_t passed as void*) and return immediately unless stated
+ * otherwise.  Return value: 0 on success, negative SDB_E* code on failure; sdb_last_error() gives
+ * the message of the last failure on the calling thread.
+ *
+ * The reference (malramsay64/statdyn-analysis, sdanalysis v0.11.6) is pure Python: it has no FFI
+ * for this path.  Each entry point below therefore names the reference *Python* interface whose
+ * arithmetic it replaces (file:line relative to the reference checkout); INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ */
+#ifndef SDB200_H
+#define SDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_OK 0
+#define SDB_EINVAL (-1) /* bad argument */
+#define SDB_ECUDA (-2)  /* CUDA runtime error */
+
+#define SDB_MAX_TRACKERS 6 /* relaxations.py:67-81 -- the six default trackers */
+#define SDB_NO_STATUS 0xFFFFFFFFu /* relaxations.py:190,199 -- "not relaxed" = 2**32 - 1 */
+
+/* Number of fp64 sums produced per (frame, origin) by sdb_dyn_step, see enum below. */
+#define SDB_NSUM 16
+
+/* Index of each per-(frame, origin) sum in the output rows of sdb_dyn_step / sdb_dyn_finalize.
+ * The 15 quantities of Dynamics.compute_all (dynamics.py:49-65,328-394) are closed-form functions
+ * of these sums and of N (done on the host, dynamics.py:183-303). */
+enum {
+    SDB_S_DISP = 0,    /* sum |dr|                    -> mean_displacement   dynamics.py:357-359 */
+    SDB_S_DISP2 = 1,   /* sum |dr|^2                  -> msd                 dynamics.py:187-189 */
+    SDB_S_DISP4 = 2,   /* sum |dr|^4                  -> mfd, alpha          dynamics.py:191-211 */
+    SDB_S_COMSTRUCT = 3, /* count(|dr| < d)           -> com_struct          dynamics.py:410-428 */
+    SDB_S_ROT = 4,     /* sum |dtheta|                -> mean_rotation       dynamics.py:225-227 */
+    SDB_S_ROT2 = 5,    /* sum dtheta^2                -> msr                 dynamics.py:229-231 */
+    SDB_S_COS = 6,     /* sum cos|dtheta|             -> rot1                dynamics.py:237-247 */
+    SDB_S_COS2 = 7,    /* sum (2 cos^2|dtheta| - 1)   -> rot2                dynamics.py:249-259 */
+    SDB_S_ROT4 = 8,    /* sum dtheta^4                -> alpha_rot           dynamics.py:261-280 */
+    SDB_S_D2R2 = 9,    /* sum |dr|^2 dtheta^2         -> gamma               dynamics.py:282-303 */
+    SDB_S_STRUCT = 10, /* count of sites with |site displacement| < d (written by sdb_struct) */
+    SDB_S_OVERLAP = 11,/* |top-k(|dr|) & top-k(|dtheta|)| (written by sdb_overlap_*) */
+    SDB_S_BADQUAT = 12,/* count of quaternion quotients that are not unit (rowan raises ValueError)
+                          or not planar (x or y != 0) */
+    SDB_S_SPARE0 = 13,
+    SDB_S_SPARE1 = 14,
+    SDB_S_SPARE2 = 15
+};
+
+/* One first/last-passage tracker (relaxations.py:187-294,308-335), thresholds pre-digested by the
+ * host so that the device compares exactly like numpy compares an f32 array with a Python float:
+ *   translation trackers compare on the squared displacement with exact cut points
+ *      |dr| >  threshold  <=>  disp2 >= cut_gt     |dr| < threshold  <=>  disp2 < cut_lt
+ *   (|dr| = fl32(sqrt(disp2)) is monotone in disp2, the host finds the cut by bisection),
+ *   rotation trackers compare |dtheta| directly:  > thr_gt,  < thr_lt,  > irr_gt. */
+typedef struct {
+    int32_t is_rotation;  /* RelaxationType.rotation / translation          relaxations.py:35-37 */
+    int32_t is_last;      /* LastMolecularRelaxation (2 state bits) vs first passage (1 bit) */
+    int32_t bit;          /* first bit of this tracker inside the per-molecule flag byte */
+    float cut_gt;         /* value >= cut_gt  <=> distance >  threshold        (translation: disp2) */
+    float cut_lt;         /* value <  cut_lt  <=> distance <  threshold        (last passage only)  */
+    float cut_irr;        /* value >= cut_irr <=> distance >  irreversibility  (last passage only)  */
+} SdbTracker;
+
+/* Per-run constants of the fused dynamics step. */
+typedef struct {
+    int32_t n;            /* molecules */
+    int32_t stride;       /* elements per plane of every per-origin / per-frame array; a multiple
+                             of 4 that is >= n (16-byte vector accesses) */
+    float lx, ly, xy;     /* freud Box(Lx, Ly, xy, is2D=True)                util.py:178-193 */
+    float com_cut_lt;     /* disp2 < com_cut_lt <=> |dr| < d, d = pi/(2 wave_number) dynamics.py:399-403;
+                             set to -1 when wave_number is None (com_struct stays NaN) */
+    int32_t n_trackers;   /* 0..SDB_MAX_TRACKERS; 0 disables the relaxation update */
+    int32_t do_sums;      /* 0: skip the reductions (Relaxations.add alone) */
+    SdbTracker trackers[SDB_MAX_TRACKERS];
+} SdbDynParams;
+
+/* One active time-origin of the current frame (one "keyframe" of read/_read.py:134-141) and the
+ * device arrays holding its state.  Planes have `stride` elements (SdbDynParams.stride). */
+typedef struct {
+    float* d_delta;       /* float[3][stride]: accumulated dx, dy (_util.py:123,149) and rotation
+                             about z (_util.py:124,150-153), one plane each */
+    uint8_t* d_flags;     /* uint8[stride]: first-passage "fired" bits and last-passage states */
+    uint32_t* d_status;   /* uint32[n_trackers][stride]: passage times  relaxations.py:199,218,268-289 */
+    uint32_t timediff;    /* frame.timestep - origin.timestep   dynamics.py:213-215, relaxations.py:132 */
+    uint32_t flags;       /* SDB_ORIGIN_* */
+} SdbOrigin;
+#define SDB_ORIGIN_NEW 1u     /* created at this frame: state is initialised instead of read
+                                 (Dynamics.from_frame + first compute_all, read/_read.py:135-152) */
+#define SDB_ORIGIN_LITERAL 2u /* timediff is not larger than every earlier one of this origin: use
+                                 the literal read-modify-write of relaxations.py:215-218 */
+
+/* A run of active origins that share the same previous sample (TrackedMotion.previous_position /
+ * previous_orientation, _util.py:155-156).  The minimum-image step and the rotation increment are
+ * computed once per segment and molecule and applied to every origin of the segment. */
+typedef struct {
+    const void* d_prev;   /* float[4][stride] planes (x, y, qw, qz) of the previous sample; NULL means
+                             "previous sample == current frame" (origins created at this frame) */
+    int32_t first;        /* index of the first origin of the segment in the origin array */
+    int32_t count;        /* number of origins in the segment */
+    uint32_t flags;       /* SDB_SEG_* */
+    uint32_t reserved;
+} SdbSegment;
+#define SDB_SEG_NO_ROTATION 1u /* either sample has no orientation: skip the rotation update
+                                  (_util.py:150 "if previous_orientation is not None and ...") */
+#define SDB_SEG_ZERO_STEP 2u   /* no new sample: recompute the sums / trackers of the current state
+                                  (Dynamics.compute_msd() ... called between add()s); d_pos may be NULL */
+
+/* ---- fused per-frame dynamics + relaxation step (planar: 2D box, quaternions about z) ----------
+ * Replaces, for every active origin of one frame, Dynamics.compute_all (dynamics.py:328-394, minus
+ * `overlap` and `struct`, see below) and Relaxations.add (relaxations.py:135-162), i.e. the body of
+ * the hot loop read/_read.py:134-153.
+ *   d_pos  float[n][3], d_quat float[n][4] (may be NULL)  current frame in GSD layout (frame.py:162-184)
+ *   d_cur_compact  float[4][stride] out (may be NULL): planes (x, y, qw, qz) of the current frame; it
+ *                  becomes the previous sample of every origin updated here
+ *   d_origins / d_segments  device copies of the descriptor arrays (n_origins / n_segments entries)
+ *   d_partials double[n_origins][sdb_dyn_num_parts(n)][SDB_NSUM] scratch
+ *   d_sums  double[n_origins][SDB_NSUM] out, filled by the finalize kernel launched by this call
+ */
+int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
+                 float* d_cur_compact, const SdbOrigin* d_origins, int32_t n_origins,
+                 const SdbSegment* d_segments, int32_t n_segments, double* d_partials,
+                 double* d_sums, void* stream);
+/* |dr| and |dtheta| of every molecule of one origin (compute_displacement / compute_rotation,
+ * dynamics.py:179-181,217-219): d_disp, d_rot float[n] (either may be NULL). */
+int sdb_dyn_norms(const float* d_delta, int32_t n, int32_t stride, float* d_disp, float* d_rot,
+                  void* stream);
+int32_t sdb_dyn_num_parts(int32_t n);
+
+/* Pack a GSD-layout frame into the planar (x, y, qw, qz) form (frame.py:162-184 -> the
+ * TrackedMotion.previous_* sample of _util.py:121-131).  Also counts non-planar quaternions into
+ * *d_bad (uint32, may be NULL). */
+int sdb_pack_frame(const float* d_pos, const float* d_quat, int32_t n, int32_t stride,
+                   float* d_compact, uint32_t* d_bad, void* stream);
+
+/* ---- `struct` (dynamics.py:305-326 with _util.py:42-54) ----------------------------------------
+ * mode 0 = reference pairing (site-major rotation x molecule-major translation, rotation about x:
+ * parity traps T1/T2 of SURVEY.md), mode 1 = physical pairing (in-plane rotation of each molecule's
+ * own sites).  Adds the count of sites with displacement < dist into d_sums[o][SDB_S_STRUCT].
+ * sites: 3 x (x, y) of the molecule's sites as the f32 values of molecules.py:136-152. */
+int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride,
+               const float* h_sites_xy, int32_t n_sites, double dist, int32_t mode, double* d_sums,
+               void* stream);
+
+/* ---- `overlap` (dynamics.py:431-445) -----------------------------------------------------------
+ * Exact: the k largest |dr| and |dtheta| per origin (ties by larger molecule index first),
+ * intersection count into d_sums[o][SDB_S_OVERLAP].
+ * key_mode 0: keys are computed from the (dx, dy, dtheta) planes of each origin's d_delta exactly as the reference
+ * computes compute_displacement() / compute_rotation(); key_mode 1: plane 0 holds non-negative
+ * displacement keys and plane 2 rotation keys (abs applied) -- mobile_overlap() on caller arrays.
+ * d_scratch: sdb_overlap_scratch_bytes(n_origins, n) bytes. */
+int sdb_overlap(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride,
+                int32_t key_mode, int32_t k, void* d_scratch, double* d_sums, void* stream);
+size_t sdb_overlap_scratch_bytes(int32_t n_origins, int32_t n);
+
+/* ---- stand-alone trackers on caller-provided distances (API parity for
+ * MolecularRelaxation.add relaxations.py:209-218 and LastMolecularRelaxation.add :238-289).
+ * dist_is_f64: distances are double (numpy float64 input compares in f64) else float.
+ * d_status int64[n] (the reference keeps int64 status words), d_state uint8[n] (last passage). */
+int sdb_first_passage(const void* d_dist, int32_t dist_is_f64, int32_t n, double threshold,
+                      int64_t timediff, int64_t* d_status, void* stream);
+int sdb_last_passage(const void* d_dist, int32_t dist_is_f64, int32_t n, double threshold,
+                     double irreversibility, int64_t timediff, int64_t* d_status,
+                     uint8_t* d_state, void* stream);
+
+/* ---- general (3D box / arbitrary quaternion) tracked motion, TrackedMotion.add _util.py:133-156.
+ * Not the hot path: one origin per call, state in the reference's own (N,3) layout.
+ * h_box: Lx, Ly, Lz, xy, xz, yz; is2d as in freud (util.py:178-193).  d_prev_pos / d_prev_quat hold
+ * the previous sample and are overwritten with the current one.  d_quat may be NULL (no
+ * orientation given); rotate = 1 when both the previous and the current sample have an orientation
+ * (_util.py:150).  *d_bad (uint32, may be NULL) counts quotients rowan would reject. */
+int sdb_motion_general(const float* h_box, int32_t is2d, int32_t n, const float* d_pos,
+                       const float* d_quat, float* d_prev_pos, float* d_prev_quat, int32_t rotate,
+                       float* d_dtrans, float* d_drot, uint32_t* d_bad, void* stream);
+/* The SDB_S_* sums of Dynamics.compute_* (dynamics.py:179-303) from (N,3) accumulators; optionally
+ * also |dr| and |dtheta| per molecule (compute_displacement / compute_rotation).
+ * d_partials: double[sdb_sums_general_parts(n)][SDB_NSUM] scratch; d_sums: double[SDB_NSUM]. */
+int sdb_sums_general(int32_t n, const float* d_dtrans, const float* d_drot, float com_threshold,
+                     float* d_disp, float* d_rot, double* d_partials, double* d_sums, void* stream);
+int32_t sdb_sums_general_parts(int32_t n);
+
+/* ---- neighbours / orientational order (order.py:174-309) --------------------------------------
+ * k nearest neighbours within rmax (strict rsq < rmax^2, self excluded) in a periodic 2D box,
+ * sorted by (rsq, index), padded with 0xFFFFFFFF (nlist) / -1 (rsq).
+ * Outputs (any may be NULL): d_nlist uint32[n][k], d_rsq float[n][k], d_counts uint32[n],
+ * d_order double[n] = mean_k cos^2(2*intrinsic_distance) with missing neighbours -> self
+ * (order.py:54-65,85-86; needs d_quat float[n][4]).  k <= SDB_MAX_K. */
+#define SDB_MAX_K 16
+int sdb_neighbours(const float* h_box, int32_t n, const float* d_pos, const float* d_quat,
+                   float rmax, int32_t k, uint32_t* d_nlist, float* d_rsq, uint32_t* d_counts,
+                   double* d_order, void* d_scratch, size_t scratch_bytes, void* stream);
+size_t sdb_neighbours_scratch_bytes(const float* h_box, int32_t n, float rmax);
+/* order._orientational_order (order.py:68-86) and order._neighbour_relative_angle (order.py:28-65)
+ * on a caller-provided neighbour list: d_order double[n] and/or d_angles double[n][k]. */
+int sdb_orientational_order(const uint32_t* d_nlist, int32_t n, int32_t k, const float* d_quat,
+                            double* d_order, double* d_angles, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------------------*/
+const char* sdb_last_error(void);
+const char* sdb_version(void);
+/* Number of kernels launched by this library since load (used by bench.py's gpu_launches). */
+uint64_t sdb_launch_count(void);
+/* Host-side evaluation of the device arithmetic helpers (same source, compiled for the host) so
+ * the CPU test-suite can check them against the oracle without a GPU.  Test hooks only. */
+double sdb_test_rot_increment(float w, float z, float pw, float pz, int32_t* bad);
+void sdb_test_wrap2d(float lx, float ly, float xy, float vx, float vy, float* ox, float* oy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H */

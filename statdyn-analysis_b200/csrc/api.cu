@@ -1,0 +1,91 @@
+// api.cu -- library-wide plumbing of libsdb200.so: error reporting, launch counter, the atan table,
+// host-side test hooks.
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "sdb_internal.cuh"
+
+namespace {
+thread_local char g_error[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+SdbAtanTable g_host_table;
+std::once_flag g_host_table_once;
+__device__ SdbAtanTable g_dev_table;
+std::mutex g_dev_mutex;
+bool g_dev_ready[64] = {false};
+
+void build_host_table()
+{
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int i = 0; i < 1024; ++i) {
+        const double t = two_pi * (double)i / 1024.0;
+        g_host_table.cs[i][0] = cos(t);
+        g_host_table.cs[i][1] = sin(t);
+    }
+    // exact values on the axes
+    g_host_table.cs[0][0] = 1.0;    g_host_table.cs[0][1] = 0.0;
+    g_host_table.cs[256][0] = 0.0;  g_host_table.cs[256][1] = 1.0;
+    g_host_table.cs[512][0] = -1.0; g_host_table.cs[512][1] = 0.0;
+    g_host_table.cs[768][0] = 0.0;  g_host_table.cs[768][1] = -1.0;
+}
+}  // namespace
+
+void sdb_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int sdb_check_cuda(cudaError_t err, const char* what)
+{
+    if (err == cudaSuccess) return SDB_OK;
+    sdb_set_error("%s: %s", what, cudaGetErrorString(err));
+    return SDB_ECUDA;
+}
+
+void sdb_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+const double (*sdb_host_atan_table())[2]
+{
+    std::call_once(g_host_table_once, build_host_table);
+    return g_host_table.cs;
+}
+
+const double (*sdb_device_atan_table())[2]
+{
+    int dev = 0;
+    if (sdb_check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return nullptr;
+    void* sym = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        if (dev < 64 && !g_dev_ready[dev]) {
+            sdb_host_atan_table();
+            if (sdb_check_cuda(cudaMemcpyToSymbol(g_dev_table, &g_host_table, sizeof(SdbAtanTable)), "atan table upload"))
+                return nullptr;
+            g_dev_ready[dev] = true;
+        }
+    }
+    if (sdb_check_cuda(cudaGetSymbolAddress(&sym, g_dev_table), "cudaGetSymbolAddress")) return nullptr;
+    return reinterpret_cast<const double (*)[2]>(sym);
+}
+
+extern "C" const char* sdb_last_error(void) { return g_error; }
+extern "C" const char* sdb_version(void) { return "sdb200 0.1.0 (sm_100a)"; }
+extern "C" uint64_t sdb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" double sdb_test_rot_increment(float w, float z, float pw, float pz, int32_t* bad)
+{
+    int b = 0;
+    const double r = sdb_rot_increment(w, z, pw, pz, sdb_host_atan_table(), b);
+    if (bad) *bad = b;
+    return r;
+}
+
+extern "C" void sdb_test_wrap2d(float lx, float ly, float xy, float vx, float vy, float* ox, float* oy)
+{
+    sdb_wrap2d(lx, ly, xy, vx, vy, *ox, *oy);
+}

@@ -1,0 +1,195 @@
+"""ctypes binding of ``libsdb200.so`` (C-ABI declared in ``include/sdb200.h``).
+
+There is no CPU fallback: if the shared library is missing or a CUDA device is not available the
+functions here raise, loudly.  ``torch`` is used only as the owner of device memory and streams.
+"""
+
+import ctypes
+from ctypes import POINTER, c_double, c_float, c_int32, c_int64, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+from pathlib import Path
+
+LIB_NAME = "libsdb200.so"
+LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
+
+SDB_MAX_TRACKERS = 6
+SDB_NSUM = 16
+SDB_NO_STATUS = 0xFFFFFFFF
+SDB_MAX_K = 16
+
+S_DISP, S_DISP2, S_DISP4, S_COMSTRUCT, S_ROT, S_ROT2, S_COS, S_COS2, S_ROT4, S_D2R2 = range(10)
+S_STRUCT, S_OVERLAP, S_BADQUAT = 10, 11, 12
+
+ORIGIN_NEW, ORIGIN_LITERAL = 1, 2
+SEG_NO_ROTATION, SEG_ZERO_STEP = 1, 2
+
+# Every symbol include/sdb200.h declares; tests check that the library exports all of them.
+EXPORTS = (
+    "sdb_dyn_step",
+    "sdb_dyn_num_parts",
+    "sdb_dyn_norms",
+    "sdb_pack_frame",
+    "sdb_struct",
+    "sdb_overlap",
+    "sdb_overlap_scratch_bytes",
+    "sdb_first_passage",
+    "sdb_last_passage",
+    "sdb_motion_general",
+    "sdb_sums_general",
+    "sdb_sums_general_parts",
+    "sdb_neighbours",
+    "sdb_neighbours_scratch_bytes",
+    "sdb_orientational_order",
+    "sdb_last_error",
+    "sdb_version",
+    "sdb_launch_count",
+    "sdb_test_rot_increment",
+    "sdb_test_wrap2d",
+)
+
+
+class SdbTracker(ctypes.Structure):
+    _fields_ = [
+        ("is_rotation", c_int32),
+        ("is_last", c_int32),
+        ("bit", c_int32),
+        ("cut_gt", c_float),
+        ("cut_lt", c_float),
+        ("cut_irr", c_float),
+    ]
+
+
+class SdbDynParams(ctypes.Structure):
+    _fields_ = [
+        ("n", c_int32),
+        ("stride", c_int32),
+        ("lx", c_float),
+        ("ly", c_float),
+        ("xy", c_float),
+        ("com_cut_lt", c_float),
+        ("n_trackers", c_int32),
+        ("do_sums", c_int32),
+        ("trackers", SdbTracker * SDB_MAX_TRACKERS),
+    ]
+
+
+class SdbOrigin(ctypes.Structure):
+    _fields_ = [
+        ("d_delta", c_void_p),
+        ("d_flags", c_void_p),
+        ("d_status", c_void_p),
+        ("timediff", c_uint32),
+        ("flags", c_uint32),
+    ]
+
+
+class SdbSegment(ctypes.Structure):
+    _fields_ = [
+        ("d_prev", c_void_p),
+        ("first", c_int32),
+        ("count", c_int32),
+        ("flags", c_uint32),
+        ("reserved", c_uint32),
+    ]
+
+
+# numpy views of the two descriptor structs (filled vectorised by the engine)
+ORIGIN_DTYPE = [("d_delta", "<u8"), ("d_flags", "<u8"), ("d_status", "<u8"), ("timediff", "<u4"), ("flags", "<u4")]
+SEGMENT_DTYPE = [("d_prev", "<u8"), ("first", "<i4"), ("count", "<i4"), ("flags", "<u4"), ("reserved", "<u4")]
+
+_lib = None
+
+
+class SdbError(RuntimeError):
+    """A call into libsdb200.so failed."""
+
+
+def load():
+    """Load the CUDA library once; raise ImportError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root). "
+            "sdanalysis_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(str(LIB_PATH))
+    P = c_void_p
+    sig = {
+        "sdb_dyn_step": (c_int32, [POINTER(SdbDynParams), P, P, P, P, c_int32, P, c_int32, P, P, P]),
+        "sdb_dyn_num_parts": (c_int32, [c_int32]),
+        "sdb_dyn_norms": (c_int32, [P, c_int32, c_int32, P, P, P]),
+        "sdb_pack_frame": (c_int32, [P, P, c_int32, c_int32, P, P, P]),
+        "sdb_struct": (c_int32, [P, c_int32, c_int32, c_int32, POINTER(c_float), c_int32, c_double, c_int32, P, P]),
+        "sdb_overlap": (c_int32, [P, c_int32, c_int32, c_int32, c_int32, c_int32, P, P, P]),
+        "sdb_overlap_scratch_bytes": (c_size_t, [c_int32, c_int32]),
+        "sdb_first_passage": (c_int32, [P, c_int32, c_int32, c_double, c_int64, P, P]),
+        "sdb_last_passage": (c_int32, [P, c_int32, c_int32, c_double, c_double, c_int64, P, P, P]),
+        "sdb_motion_general": (c_int32, [POINTER(c_float), c_int32, c_int32, P, P, P, P, c_int32, P, P, P, P]),
+        "sdb_sums_general": (c_int32, [c_int32, P, P, c_float, P, P, P, P, P]),
+        "sdb_sums_general_parts": (c_int32, [c_int32]),
+        "sdb_neighbours": (c_int32, [POINTER(c_float), c_int32, P, P, c_float, c_int32, P, P, P, P, P, c_size_t, P]),
+        "sdb_neighbours_scratch_bytes": (c_size_t, [POINTER(c_float), c_int32, c_float]),
+        "sdb_orientational_order": (c_int32, [P, c_int32, c_int32, P, P, P, P]),
+        "sdb_last_error": (ctypes.c_char_p, []),
+        "sdb_version": (ctypes.c_char_p, []),
+        "sdb_launch_count": (c_uint64, []),
+        "sdb_test_rot_increment": (c_double, [c_float, c_float, c_float, c_float, POINTER(c_int32)]),
+        "sdb_test_wrap2d": (None, [c_float, c_float, c_float, c_float, c_float, POINTER(c_float), POINTER(c_float)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SdbError(f"libsdb200 error {rc}: {load().sdb_last_error().decode()}")
+
+
+def launch_count():
+    return int(load().sdb_launch_count())
+
+
+_torch = None
+
+
+def torch():
+    """Import torch lazily (the first import can take a minute on a fresh box)."""
+    global _torch
+    if _torch is None:
+        import torch as _t
+
+        _torch = _t
+    return _torch
+
+
+def require_cuda(device=None):
+    """Return a torch CUDA device or raise: there is no CPU path."""
+    t = torch()
+    if not t.cuda.is_available():
+        raise RuntimeError(
+            "sdanalysis_b200 needs a CUDA device (B200, sm_100a); torch.cuda.is_available() is False "
+            "and there is no CPU fallback."
+        )
+    load()
+    if device is None:
+        return t.device("cuda", t.cuda.current_device())
+    return t.device(device)
+
+
+def ptr(tensor):
+    return 0 if tensor is None else tensor.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch().cuda.current_stream(device).cuda_stream
+
+
+def float_array(values):
+    arr = (c_float * len(values))(*[float(v) for v in values])
+    return arr

@@ -1,0 +1,655 @@
+"""Batched multi-origin dynamics engine: the B200 replacement for the reference's hot loop.
+
+The reference keeps one ``(Dynamics, Relaxations)`` pair of Python objects per time-origin
+("keyframe") and, for every frame, calls ``compute_all`` + ``Relaxations.add`` on each active one
+(``read/_read.py:128-168``).  Here all origins of a rank live in HBM as planar arrays and one call to
+:meth:`DynamicsEngine.step` advances every active origin with the fused CUDA kernel
+(``csrc/dyn_step.cu``) plus the ``struct`` and ``overlap`` kernels.
+
+Per-origin state (N molecules, ``stride`` = N rounded up to 4):
+
+=============  ======================  =========================================================
+``delta``      ``float32[3][stride]``  accumulated dx, dy, rotation about z (``_util.py:123-124``)
+``flags``      ``uint8[stride]``       fired bits of the first-passage trackers + last-passage state
+``status``     ``uint32[T][stride]``   passage times (``relaxations.py:199``), written only
+=============  ======================  =========================================================
+
+Previous samples (``TrackedMotion.previous_*``, ``_util.py:155-156``) are shared, reference-counted
+planar frames ``float32[4][stride]`` = (x, y, qw, qz): after a frame is processed every origin that
+was active points at it, so in the dense (linear) schedule one frame is shared by all origins and in
+the exponential schedule at most one frame per origin is alive.
+"""
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+from ._lib import (
+    ORIGIN_DTYPE,
+    ORIGIN_LITERAL,
+    ORIGIN_NEW,
+    S_BADQUAT,
+    S_COMSTRUCT,
+    S_COS,
+    S_COS2,
+    S_D2R2,
+    S_DISP,
+    S_DISP2,
+    S_DISP4,
+    S_OVERLAP,
+    S_ROT,
+    S_ROT2,
+    S_ROT4,
+    S_STRUCT,
+    SDB_MAX_TRACKERS,
+    SDB_NSUM,
+    SEG_NO_ROTATION,
+    SEG_ZERO_STEP,
+    SEGMENT_DTYPE,
+    SdbDynParams,
+)
+
+F32 = np.float32
+MAX_STATUS = 2 ** 32 - 1
+
+ALL_QUANTITIES = (
+    "time",
+    "mean_displacement",
+    "msd",
+    "mfd",
+    "alpha",
+    "scattering_function",
+    "com_struct",
+    "mean_rotation",
+    "msr",
+    "rot1",
+    "rot2",
+    "alpha_rot",
+    "gamma",
+    "overlap",
+    "struct",
+)
+
+
+# ----------------------------------------------------------------------------------------------
+# threshold digestion (host): exact cut points for "f32 array <op> python float" comparisons
+# ----------------------------------------------------------------------------------------------
+def _cut_sqrt(threshold, strict_greater):
+    """Smallest f32 ``x`` with ``sqrt32(x) > thr`` (strict_greater) or ``sqrt32(x) >= thr``.
+
+    The reference compares ``np.linalg.norm(delta, axis=1)`` (= ``fl32(sqrt(disp2))``) with a Python
+    float, which numpy does in f32 (``relaxations.py:216``, ``dynamics.py:425``).  sqrt is monotone,
+    so the comparison is equivalent to a comparison of ``disp2`` with this cut.
+    """
+    thr = F32(threshold)
+    if np.isnan(thr):
+        return F32(np.inf)
+    ok = (lambda v: np.sqrt(v) > thr) if strict_greater else (lambda v: np.sqrt(v) >= thr)
+    x = F32(thr * thr) if thr > 0 else F32(0)
+    if not np.isfinite(x):
+        return F32(np.inf)
+    while x > 0 and ok(x):
+        x = np.nextafter(x, F32(0), dtype=F32)
+    while not ok(x):
+        nx = np.nextafter(x, F32(np.inf), dtype=F32)
+        if nx == x:
+            return F32(np.inf)
+        x = nx
+    return x
+
+
+def _cut_direct(threshold, strict_greater):
+    """Cut for quantities compared directly (|dtheta|): ``v > thr``  <=>  ``v >= nextafter(thr)``."""
+    thr = F32(threshold)
+    return np.nextafter(thr, F32(np.inf), dtype=F32) if strict_greater else thr
+
+
+def default_tracker_definitions(distance):
+    """The six default trackers of ``Relaxations.__init__`` (``relaxations.py:67-81``)."""
+    return [
+        {"name": "tau_D", "threshold": 3 * distance},
+        {"name": "tau_F", "threshold": distance},
+        {"name": "tau_L", "threshold": distance, "last_passage": True, "last_passage_cutoff": 3 * distance},
+        {"name": "tau_T2", "threshold": np.pi / 2, "type": "rotation"},
+        {"name": "tau_T3", "threshold": np.pi / 3, "type": "rotation"},
+        {"name": "tau_T4", "threshold": np.pi / 4, "type": "rotation"},
+    ]
+
+
+class TrackerSpec:
+    """Validated tracker definition (``Relaxations.set_mol_relax`` + ``create_mol_relaxations``,
+    ``relaxations.py:108-133,308-335``)."""
+
+    def __init__(self, item):
+        if item.get("name") is None:
+            raise ValueError("'name' is a required attribute")
+        if item.get("threshold") is None:
+            raise ValueError("'threshold' is a required attribute")
+        self.name = str(item["name"])
+        self.threshold = float(item["threshold"])
+        self.last_passage = bool(item.get("last_passage", False))
+        self.cutoff = float(item.get("last_passage_cutoff", 3.0 * self.threshold))
+        self.type = str(item.get("type", "translation"))
+        if self.type not in ("translation", "rotation"):
+            raise KeyError(self.type)
+        if self.threshold < 0:
+            raise ValueError(f"Threshold needs a positive value, got {self.threshold}")
+        if self.last_passage and self.cutoff < 0:
+            raise ValueError(
+                f"When using last passage a positive cutoff value is required, got {self.cutoff}, default is 1.0"
+            )
+
+
+def build_trackers(definitions):
+    specs = [TrackerSpec(item) for item in definitions]
+    if len(specs) > SDB_MAX_TRACKERS:
+        raise NotImplementedError(f"at most {SDB_MAX_TRACKERS} molecular relaxations are supported on the device")
+    bit = 0
+    for spec in specs:
+        spec.bit = bit
+        bit += 2 if spec.last_passage else 1
+    if bit > 8:
+        raise NotImplementedError("tracker state does not fit the per-molecule flag byte")
+    return specs
+
+
+def finalize_row(s, td, n, *, distance=None, overlap_k=None, n_sites=None, strict=True):
+    """The 15 quantities of ``Dynamics.compute_all`` from the SDB_S_* sums of one (frame, origin).
+
+    Closed forms of reference ``dynamics.py:183-303``; 0/0 gives NaN exactly like the reference under
+    its pinned numpy (SURVEY trap T3).  ``overlap_k`` / ``n_sites`` None leave the quantity NaN.
+    """
+    nan = float("nan")
+    n = float(n)
+    msd, mfd = s[S_DISP2] / n, s[S_DISP4] / n
+    msr, mfr = s[S_ROT2] / n, s[S_ROT4] / n
+    row = dict.fromkeys(ALL_QUANTITIES, nan)
+    row["time"] = td
+    row["mean_displacement"] = s[S_DISP] / n
+    row["msd"] = msd
+    row["mfd"] = mfd
+    row["alpha"] = mfd / (2 * msd * msd) - 1 if msd > 0 else nan
+    if distance is not None:
+        row["com_struct"] = s[S_COMSTRUCT] / n
+    row["mean_rotation"] = s[S_ROT] / n
+    row["msr"] = msr
+    row["rot1"] = s[S_COS] / n
+    row["rot2"] = s[S_COS2] / n
+    row["alpha_rot"] = mfr / (3 * msr * msr) - 1 if msr > 0 else nan
+    row["gamma"] = (s[S_D2R2] / n) / (msd * msr) - 1 if msd > 0 and msr > 0 else nan
+    if overlap_k is not None:
+        if overlap_k == 0:
+            if strict:
+                raise ZeroDivisionError("division by zero")  # dynamics.py:445 with N < 10
+        else:
+            row["overlap"] = s[S_OVERLAP] / overlap_k
+    if n_sites is not None:
+        row["struct"] = s[S_STRUCT] / (n * n_sites)
+    return row
+
+
+# ----------------------------------------------------------------------------------------------
+class _PoolFrame:
+    __slots__ = ("planes", "refs", "has_orientation")
+
+    def __init__(self, planes):
+        self.planes = planes
+        self.refs = 0
+        self.has_orientation = True
+
+
+class _Origin:
+    __slots__ = ("key", "timestep", "delta", "flags", "status", "prev", "max_timediff", "updates")
+
+    def __init__(self, key, timestep):
+        self.key = key
+        self.timestep = int(timestep)
+        self.delta = self.flags = self.status = None
+        self.prev = None
+        self.max_timediff = -1
+        self.updates = 0
+
+
+class _Ring:
+    """A small ring of pinned host buffers, each guarded by a CUDA event."""
+
+    def __init__(self, torch, depth, make):
+        self.bufs = [make() for _ in range(depth)]
+        self.events = [None] * depth
+        self.torch = torch
+        self.i = 0
+
+    def acquire(self):
+        self.i = (self.i + 1) % len(self.bufs)
+        ev = self.events[self.i]
+        if ev is not None:
+            ev.synchronize()
+        return self.i, self.bufs[self.i]
+
+    def release(self, i):
+        ev = self.torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
+        return ev
+
+
+class StepResult:
+    """Handle to the sums of one engine step; ``rows()`` waits for the device and finalises."""
+
+    def __init__(self, engine, keys, timediffs, sums_host, event):
+        self.engine = engine
+        self.keys = keys
+        self.timediffs = timediffs
+        self._sums = sums_host
+        self._event = event
+
+    def sums(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+        return self._sums
+
+    def rows(self, check=True, strict=True):
+        """One dict of the 15 ``compute_all`` quantities per active origin, in ``keys`` order.
+        ``strict``: raise ZeroDivisionError for N < 10 like ``mobile_overlap`` does in compute_all."""
+        return self.engine.finalize_rows(self.sums(), self.timediffs, check=check, strict=strict)
+
+
+class DynamicsEngine:
+    def __init__(
+        self,
+        num_mols,
+        box,
+        wave_number=None,
+        *,
+        trackers="default",
+        compute_sums=True,
+        compute_overlap=True,
+        compute_struct=True,
+        struct_mode="reference",
+        mol_sites=None,
+        device=None,
+        ring_depth=3,
+        overlap_fraction=0.1,
+    ):
+        self.torch = torch = _lib.torch()
+        self.device = _lib.require_cuda(device)
+        self.lib = _lib.load()
+        self.n = int(num_mols)
+        if self.n <= 0:
+            raise RuntimeError("Position must contain values, has length of 0.")
+        self.stride = (self.n + 3) // 4 * 4
+        box = np.asarray(box, dtype=F32).reshape(-1)
+        self.box = np.zeros(6, dtype=F32)
+        self.box[: len(box)] = box
+        self.wave_number = wave_number
+        self.distance = None if wave_number is None else np.pi / (2 * wave_number)
+
+        if isinstance(trackers, str) and trackers == "default":
+            trackers = None if self.distance is None else default_tracker_definitions(self.distance)
+        self.compute_sums = bool(compute_sums)
+        self.compute_overlap = bool(compute_overlap) and self.compute_sums
+        self.overlap_k = int(self.n * overlap_fraction)
+        self.mol_sites = None if mol_sites is None else np.asarray(mol_sites, dtype=F32)[:, :2].copy()
+        self.compute_struct = (
+            bool(compute_struct) and self.compute_sums and self.distance is not None and self.mol_sites is not None
+        )
+        if struct_mode not in ("reference", "physical"):
+            raise ValueError("struct_mode must be 'reference' or 'physical'")
+        self.struct_mode = 0 if struct_mode == "reference" else 1
+
+        p = SdbDynParams()
+        p.n, p.stride = self.n, self.stride
+        p.lx, p.ly, p.xy = float(self.box[0]), float(self.box[1]), float(self.box[3])
+        p.com_cut_lt = float(_cut_sqrt(self.distance, False)) if self.distance is not None else -1.0
+        p.do_sums = int(self.compute_sums)
+        self.params = p
+        self.origins = OrderedDict()
+        self.set_trackers(trackers)
+
+        self._free_frames = []
+        self._n_parts = int(self.lib.sdb_dyn_num_parts(self.n))
+        self._ring_depth = ring_depth
+        self._cap = 0  # capacity (origins) of the per-step scratch
+        self._frame_ring = None
+        self._dev_frames = None
+        self._frame_i = 0
+        self._sites_c = None if self.mol_sites is None else _lib.float_array(self.mol_sites.reshape(-1))
+        self.frames_seen = 0
+        self.updates = 0  # molecule x origin updates performed
+
+    # ------------------------------------------------------------------------------------------
+    def _ensure_capacity(self, n_active):
+        if n_active <= self._cap:
+            return
+        torch = self.torch
+        cap = max(16, 1 << (n_active - 1).bit_length())
+        dev = self.device
+        self._cap = cap
+        n_desc = cap * 32 + (cap + 8) * 24  # origins (32 B) + segments (24 B), generous
+        self._desc_ring = _Ring(torch, self._ring_depth, lambda: torch.empty(n_desc, dtype=torch.uint8).pin_memory())
+        self._desc_dev = [torch.empty(n_desc, dtype=torch.uint8, device=dev) for _ in range(self._ring_depth)]
+        self._sums_ring = _Ring(
+            torch, self._ring_depth, lambda: torch.zeros((cap, SDB_NSUM), dtype=torch.float64).pin_memory()
+        )
+        self._sums_dev = [torch.zeros((cap, SDB_NSUM), dtype=torch.float64, device=dev) for _ in range(self._ring_depth)]
+        self._partials = torch.empty((cap, self._n_parts, SDB_NSUM), dtype=torch.float64, device=dev)
+        if self.compute_overlap and self.overlap_k > 0:
+            nbytes = int(self.lib.sdb_overlap_scratch_bytes(cap, self.n))
+            self._ov_scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+    def _stage_frame(self, position, orientation):
+        """Return device tensors (pos (N,3) f32, quat (N,4) f32 or None) for host or device input."""
+        torch = self.torch
+        if isinstance(position, torch.Tensor) and position.is_cuda:
+            pos = position
+            quat = orientation
+            if pos.dtype != torch.float32 or not pos.is_contiguous():
+                pos = pos.to(torch.float32).contiguous()
+            if quat is not None and (quat.dtype != torch.float32 or not quat.is_contiguous()):
+                quat = quat.to(torch.float32).contiguous()
+            if pos.data_ptr() % 16:
+                pos = pos.clone()
+            if quat is not None and quat.data_ptr() % 16:
+                quat = quat.clone()
+            return pos, quat
+        position = np.asarray(position)
+        if position.shape != (self.n, 3):
+            raise RuntimeError(f"position has shape {position.shape}, expected {(self.n, 3)}")
+        if orientation is not None:
+            orientation = np.asarray(orientation)
+            if orientation.shape != (self.n, 4):
+                raise RuntimeError(f"orientation has shape {orientation.shape}, expected {(self.n, 4)}")
+        qoff = (3 * self.n + 3) // 4 * 4  # quaternions start 16-byte aligned (float4 loads)
+        if self._frame_ring is None:
+            self._frame_ring = _Ring(
+                torch, self._ring_depth, lambda: torch.zeros(qoff + 4 * self.n, dtype=torch.float32).pin_memory()
+            )
+            self._dev_frames = [
+                torch.empty(qoff + 4 * self.n, dtype=torch.float32, device=self.device) for _ in range(self._ring_depth)
+            ]
+        i, pinned = self._frame_ring.acquire()
+        host = pinned.numpy()
+        np.copyto(host[: 3 * self.n].reshape(self.n, 3), position, casting="same_kind")
+        nfl = 3 * self.n
+        if orientation is not None:
+            np.copyto(host[qoff : qoff + 4 * self.n].reshape(self.n, 4), orientation, casting="same_kind")
+            nfl = qoff + 4 * self.n
+        dev = self._dev_frames[i]
+        dev[:nfl].copy_(pinned[:nfl], non_blocking=True)
+        self._frame_ring.release(i)
+        self.h2d_bytes = 4 * (7 * self.n if orientation is not None else 3 * self.n)
+        pos = dev[: 3 * self.n].view(self.n, 3)
+        quat = dev[qoff : qoff + 4 * self.n].view(self.n, 4) if orientation is not None else None
+        return pos, quat
+
+    def _new_pool_frame(self):
+        if self._free_frames:
+            return self._free_frames.pop()
+        return _PoolFrame(self.torch.zeros((4, self.stride), dtype=self.torch.float32, device=self.device))
+
+    def _release(self, frame):
+        if frame is None:
+            return
+        frame.refs -= 1
+        if frame.refs == 0:
+            self._free_frames.append(frame)
+
+    def _alloc_origin(self, org):
+        torch, dev = self.torch, self.device
+        org.delta = torch.empty((3, self.stride), dtype=torch.float32, device=dev)
+        if self.trackers:
+            org.flags = torch.empty(self.stride, dtype=torch.uint8, device=dev)
+            org.status = torch.empty((len(self.trackers), self.stride), dtype=torch.int32, device=dev)
+
+    def set_trackers(self, definitions):
+        """Replace the tracker set; every origin's passage state starts afresh while its accumulated
+        motion is kept (``Relaxations.set_mol_relax``, ``relaxations.py:108-133``)."""
+        self.trackers = build_trackers(definitions) if definitions else []
+        p = self.params
+        p.n_trackers = len(self.trackers)
+        for i, spec in enumerate(self.trackers):
+            cut = _cut_direct if spec.type == "rotation" else _cut_sqrt
+            t = p.trackers[i]
+            t.is_rotation = int(spec.type == "rotation")
+            t.is_last = int(spec.last_passage)
+            t.bit = spec.bit
+            t.cut_gt = float(cut(spec.threshold, True))
+            t.cut_lt = float(cut(spec.threshold, False))
+            t.cut_irr = float(cut(spec.cutoff, True))
+        torch, dev = self.torch, self.device
+        for org in self.origins.values():
+            if self.trackers:
+                org.flags = torch.zeros(self.stride, dtype=torch.uint8, device=dev)
+                org.status = torch.full((len(self.trackers), self.stride), -1, dtype=torch.int32, device=dev)
+            else:
+                org.flags = org.status = None
+
+    def drop_origin(self, key):
+        org = self.origins.pop(key)
+        self._release(org.prev)
+
+    # ------------------------------------------------------------------------------------------
+    def step(self, timestep, position, orientation, active, *, zero_step=False, want_sums=None, chunk=None):
+        """Advance every origin in ``active`` (iterable of hashable keys) with one frame.
+
+        Unknown keys are created at this frame (``Dynamics.from_frame`` + first ``compute_all``,
+        ``read/_read.py:135-152``).  Returns a :class:`StepResult` (asynchronous).
+        """
+        torch, lib = self.torch, self.lib
+        active = list(active)
+        n_active = len(active)
+        if n_active == 0:
+            return StepResult(self, [], [], np.zeros((0, SDB_NSUM)), None)
+        self._ensure_capacity(n_active)
+        do_sums = self.compute_sums if want_sums is None else bool(want_sums)
+
+        with torch.cuda.device(self.device):
+            if zero_step:
+                pos = quat = None
+            else:
+                pos, quat = self._stage_frame(position, orientation)
+
+            # ---- group the active origins by previous sample --------------------------------
+            groups = OrderedDict()
+            fresh = []
+            for key in active:
+                org = self.origins.get(key)
+                if org is None:
+                    org = _Origin(key, timestep)
+                    self._alloc_origin(org)
+                    self.origins[key] = org
+                    fresh.append(org)
+                else:
+                    groups.setdefault(id(org.prev), (org.prev, []))[1].append(org)
+            if zero_step and fresh:
+                raise RuntimeError("zero_step on an origin that does not exist")
+
+            target_blocks = 148 * 16
+            blocks_per_segment = (self._n_parts + 3) // 4
+            seg_rows = []  # (prev planes ptr, flags, [origins])
+            ordered = []
+            for prev, members in groups.values():
+                flags = 0
+                if zero_step:
+                    flags |= SEG_ZERO_STEP
+                elif quat is None or prev is None or not prev.has_orientation:
+                    flags |= SEG_NO_ROTATION
+                size = chunk or max(8, math.ceil(len(members) * blocks_per_segment / target_blocks))
+                for s in range(0, len(members), size):
+                    part = members[s : s + size]
+                    seg_rows.append((0 if prev is None else prev.planes.data_ptr(), flags, len(ordered), len(part)))
+                    ordered.extend(part)
+            if fresh:
+                flags = SEG_NO_ROTATION if quat is None else 0
+                seg_rows.append((0, flags, len(ordered), len(fresh)))
+                ordered.extend(fresh)
+
+            odesc = np.zeros(n_active, dtype=ORIGIN_DTYPE)
+            timediffs = []
+            for i, org in enumerate(ordered):
+                td = int(timestep) - org.timestep
+                if not 0 <= td < MAX_STATUS:
+                    raise OverflowError(
+                        f"time difference {td} outside [0, 2**32-1): passage times are 32-bit on the device"
+                    )
+                fl = 0
+                if org.updates == 0:
+                    fl |= ORIGIN_NEW
+                elif td < org.max_timediff:
+                    fl |= ORIGIN_LITERAL
+                odesc[i] = (
+                    org.delta.data_ptr(),
+                    0 if org.flags is None else org.flags.data_ptr(),
+                    0 if org.status is None else org.status.data_ptr(),
+                    td,
+                    fl,
+                )
+                timediffs.append(td)
+            sdesc = np.array([(p, f, c, fl, 0) for (p, fl, f, c) in seg_rows], dtype=SEGMENT_DTYPE)
+
+            ri, pinned = self._desc_ring.acquire()
+            ob, sb = odesc.nbytes, sdesc.nbytes
+            seg_off = (ob + 15) // 16 * 16
+            host = pinned.numpy()
+            host[:ob] = odesc.view(np.uint8)
+            host[seg_off : seg_off + sb] = sdesc.view(np.uint8)
+            ddev = self._desc_dev[ri]
+            ddev[: seg_off + sb].copy_(pinned[: seg_off + sb], non_blocking=True)
+            self._desc_ring.release(ri)
+            d_origins = ddev.data_ptr()
+            d_segments = d_origins + seg_off
+
+            # ---- the frame that becomes everybody's previous sample ---------------------------
+            new_prev = None
+            if not zero_step:
+                new_prev = self._new_pool_frame()
+                new_prev.has_orientation = quat is not None
+
+            si, sums_pinned = self._sums_ring.acquire()
+            sums_dev = self._sums_dev[si]
+            stream = _lib.stream_ptr(self.device)
+            params = self.params
+            params.do_sums = int(do_sums)
+            _lib.check(
+                lib.sdb_dyn_step(
+                    params,
+                    _lib.ptr(pos),
+                    _lib.ptr(quat),
+                    0 if new_prev is None else new_prev.planes.data_ptr(),
+                    d_origins,
+                    n_active,
+                    d_segments,
+                    len(seg_rows),
+                    self._partials.data_ptr(),
+                    sums_dev.data_ptr(),
+                    stream,
+                )
+            )
+            if do_sums and self.compute_struct:
+                _lib.check(
+                    lib.sdb_struct(
+                        d_origins, n_active, self.n, self.stride, self._sites_c, len(self.mol_sites),
+                        float(self.distance), self.struct_mode, sums_dev.data_ptr(), stream,
+                    )
+                )
+            if do_sums and self.compute_overlap and self.overlap_k > 0:
+                _lib.check(
+                    lib.sdb_overlap(
+                        d_origins, n_active, self.n, self.stride, 0, self.overlap_k,
+                        self._ov_scratch.data_ptr(), sums_dev.data_ptr(), stream,
+                    )
+                )
+            event = None
+            if do_sums:
+                sums_pinned[:n_active].copy_(sums_dev[:n_active], non_blocking=True)
+                event = self._sums_ring.release(si)
+                self.d2h_bytes = n_active * SDB_NSUM * 8
+
+            # ---- bookkeeping -------------------------------------------------------------------
+            for org, td in zip(ordered, timediffs):
+                if not zero_step:
+                    self._release(org.prev)
+                    org.prev = new_prev
+                    new_prev.refs += 1
+                    org.updates += 1
+                    org.max_timediff = max(org.max_timediff, td)
+            if not zero_step:
+                self.frames_seen += 1
+                self.updates += n_active * self.n
+
+        keys = [org.key for org in ordered]
+        sums_host = sums_pinned.numpy()[:n_active] if do_sums else None
+        return StepResult(self, keys, timediffs, sums_host, event)
+
+    # ------------------------------------------------------------------------------------------
+    def finalize_rows(self, sums, timediffs, check=True, strict=True):
+        """Host-side closed forms of ``Dynamics.compute_all`` (``dynamics.py:183-303,328-394``)."""
+        rows = []
+        for s, td in zip(sums, timediffs):
+            if check and s[S_BADQUAT] > 0:
+                # rowan.to_euler raises ValueError for non-unit quaternions (process_file skips the row)
+                raise ValueError("Arguments must be unit quaternions (planar, rotation about z)")
+            rows.append(
+                finalize_row(
+                    s,
+                    td,
+                    self.n,
+                    distance=self.distance,
+                    overlap_k=self.overlap_k if self.compute_overlap else None,
+                    n_sites=len(self.mol_sites) if self.compute_struct else None,
+                    strict=strict,
+                )
+            )
+        return rows
+
+    # ------------------------------------------------------------------------------------------
+    def delta_arrays(self, key):
+        """(delta_translation (N,3), delta_rotation (N,3)) of one origin as host arrays."""
+        org = self.origins[key]
+        planes = org.delta[:, : self.n].cpu().numpy()
+        trans = np.zeros((self.n, 3), dtype=F32)
+        rot = np.zeros((self.n, 3), dtype=F32)
+        trans[:, 0], trans[:, 1], rot[:, 0] = planes[0], planes[1], planes[2]
+        return trans, rot
+
+    def norms(self, key):
+        """(|dr|, |dtheta|) per molecule, computed on the device."""
+        torch = self.torch
+        org = self.origins[key]
+        with torch.cuda.device(self.device):
+            out = torch.empty((2, self.n), dtype=torch.float32, device=self.device)
+            _lib.check(
+                self.lib.sdb_dyn_norms(
+                    org.delta.data_ptr(), self.n, self.stride, out[0].data_ptr(), out[1].data_ptr(),
+                    _lib.stream_ptr(self.device),
+                )
+            )
+            host = out.cpu().numpy()
+        return host[0], host[1]
+
+    def tracker_state(self, key):
+        """Raw passage times (uint32 (T, N)) and the flag byte per molecule of one origin."""
+        org = self.origins[key]
+        status = org.status[:, : self.n].cpu().numpy().view(np.uint32)
+        flags = org.flags[: self.n].cpu().numpy()
+        return status, flags
+
+    def summary(self, key):
+        """``{tracker name: get_status()}`` like ``Relaxations.summary`` (``relaxations.py:181-184``):
+        first-passage trackers give the raw word, last-passage ones mask everything that is not in
+        the irreversible state (``relaxations.py:291-294``)."""
+        status, flags = self.tracker_state(key)
+        out = {}
+        for i, spec in enumerate(self.trackers):
+            col = status[i].astype(np.int64)
+            if spec.last_passage:
+                state = (flags >> spec.bit) & 3
+                col[state != 2] = MAX_STATUS
+            out[spec.name] = col
+        return out
+
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)

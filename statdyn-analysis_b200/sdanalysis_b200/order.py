@@ -1,0 +1,172 @@
+"""Neighbour lists and orientational order, drop-in for the hot-path part of reference ``order.py``.
+
+``compute_neighbours`` / ``orientational_order`` / ``num_neighbours`` / ``relative_distances`` /
+``relative_orientations`` keep the reference signatures (``order.py:186-309``).  The search is a GPU
+cell list (``csrc/neighbours.cu``) replacing ``freud.locality.NearestNeighbors``; one call of
+:func:`neighbour_analysis` produces everything from a single build, where the reference rebuilds the
+neighbour structure for each function.  Voronoi counts and the sklearn classifier factories of the
+reference (``order.py:89-171,312-315``) are outside the accelerated path.
+"""
+
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+F32 = np.float32
+
+
+def _box6(box):
+    box = np.asarray(box, dtype=F32).reshape(-1)
+    out = np.zeros(6, dtype=F32)
+    out[: len(box)] = box
+    return out
+
+
+def _to_device(array, width, torch, device):
+    if isinstance(array, torch.Tensor):
+        t = array.to(device=device, dtype=torch.float32)
+        return t.contiguous()
+    array = np.ascontiguousarray(array, dtype=F32)
+    if array.ndim != 2 or array.shape[1] != width:
+        raise ValueError(f"expected an (N, {width}) array, got {array.shape}")
+    return torch.from_numpy(array).to(device)
+
+
+def neighbour_analysis(
+    box, position, orientation=None, max_radius=3.5, max_neighbours=8, *, want=("nlist",), device=None, to_host=True
+):
+    """One cell-list build, any of ``nlist`` (N,k) uint32, ``rsq`` (N,k) f32, ``counts`` (N,) uint32,
+    ``order`` (N,) f64.  Missing neighbours are 2**32-1 in ``nlist`` and -1 in ``rsq``."""
+    torch = _lib.torch()
+    device = _lib.require_cuda(device)
+    lib = _lib.load()
+    k = int(max_neighbours)
+    if not 0 < k <= _lib.SDB_MAX_K:
+        raise ValueError(f"max_neighbours must be in 1..{_lib.SDB_MAX_K}")
+    with torch.cuda.device(device):
+        pos = _to_device(position, 3, torch, device)
+        n = pos.shape[0]
+        if n == 0:
+            raise RuntimeError("Position must contain values, has length of 0.")
+        quat = None
+        if "order" in want:
+            if orientation is None:
+                raise ValueError("orientational order needs orientations")
+            quat = _to_device(orientation, 4, torch, device)
+        box_c = _lib.float_array(_box6(box))
+        nbytes = int(lib.sdb_neighbours_scratch_bytes(box_c, n, float(max_radius)))
+        if nbytes == 0:
+            raise ValueError("invalid box or radius")
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        out = {}
+        if "nlist" in want:
+            out["nlist"] = torch.empty((n, k), dtype=torch.int32, device=device)
+        if "rsq" in want:
+            out["rsq"] = torch.empty((n, k), dtype=torch.float32, device=device)
+        if "counts" in want:
+            out["counts"] = torch.empty(n, dtype=torch.int32, device=device)
+        if "order" in want:
+            out["order"] = torch.empty(n, dtype=torch.float64, device=device)
+        _lib.check(
+            lib.sdb_neighbours(
+                box_c, n, pos.data_ptr(), _lib.ptr(quat), float(max_radius), k,
+                _lib.ptr(out.get("nlist")), _lib.ptr(out.get("rsq")), _lib.ptr(out.get("counts")),
+                _lib.ptr(out.get("order")), scratch.data_ptr(), nbytes, _lib.stream_ptr(device),
+            )
+        )
+        if not to_host:
+            return out
+        host = {key: val.cpu().numpy() for key, val in out.items()}
+    for key in ("nlist", "counts"):
+        if key in host:
+            host[key] = host[key].view(np.uint32)
+    return host
+
+
+def compute_neighbours(box, position, max_radius: float = 3.5, max_neighbours: int = 8) -> np.ndarray:
+    """Indices of the nearest neighbours of each molecule, (N, max_neighbours) uint32, sorted by
+    distance, ``2**32 - 1`` marking a missing neighbour (reference ``order.py:186-207``)."""
+    return neighbour_analysis(box, position, None, max_radius, max_neighbours, want=("nlist",))["nlist"]
+
+
+def _list_on_device(neighbourlist, orientation, torch, device):
+    neighbourlist = np.asarray(neighbourlist)
+    if len(neighbourlist) != len(orientation):
+        warnings.warn(
+            "Having different lengths for the neighbourlist and orientation arguments can lead to unusual "
+            f"outcomes. Found {len(neighbourlist)} and {len(orientation)}"
+        )
+    n = len(orientation)
+    # order.py:56-59 -- entries that are not valid molecule indices mean "missing"
+    nl = np.where((neighbourlist >= 0) & (neighbourlist < n), neighbourlist, 2 ** 32 - 1).astype(np.uint32)
+    d_nl = torch.from_numpy(np.ascontiguousarray(nl).view(np.int32)).to(device)
+    return d_nl, _to_device(orientation, 4, torch, device)
+
+
+def _neighbour_relative_angle(neighbourlist: np.ndarray, orientation: np.ndarray) -> np.ndarray:
+    """Relative angle to every listed neighbour in [0, 2 pi], 0 for missing ones
+    (reference ``order.py:28-65``)."""
+    torch = _lib.torch()
+    device = _lib.require_cuda()
+    with torch.cuda.device(device):
+        d_nl, quat = _list_on_device(neighbourlist, orientation, torch, device)
+        n, k = d_nl.shape
+        angles = torch.empty((n, k), dtype=torch.float64, device=device)
+        _lib.check(
+            _lib.load().sdb_orientational_order(
+                d_nl.data_ptr(), n, k, quat.data_ptr(), 0, angles.data_ptr(), _lib.stream_ptr(device)
+            )
+        )
+        return angles.cpu().numpy()
+
+
+def _orientational_order(neighbourlist: np.ndarray, orientation: np.ndarray) -> np.ndarray:
+    """mean_k cos^2(relative angle), in [0, 1] (reference ``order.py:68-86``)."""
+    torch = _lib.torch()
+    device = _lib.require_cuda()
+    with torch.cuda.device(device):
+        d_nl, quat = _list_on_device(neighbourlist, orientation, torch, device)
+        n, k = d_nl.shape
+        order = torch.empty(n, dtype=torch.float64, device=device)
+        _lib.check(
+            _lib.load().sdb_orientational_order(
+                d_nl.data_ptr(), n, k, quat.data_ptr(), order.data_ptr(), 0, _lib.stream_ptr(device)
+            )
+        )
+        return order.cpu().numpy()
+
+
+def relative_orientations(box, position, orientation, max_radius: float = 3.5, max_neighbours: int = 8) -> np.ndarray:
+    """Reference ``order.py:210-231``."""
+    neighbours = compute_neighbours(box, position, max_radius, max_neighbours)
+    return _neighbour_relative_angle(neighbours, orientation)
+
+
+def orientational_order(box, position, orientation, max_radius: float = 3.5, max_neighbours: int = 8) -> np.ndarray:
+    """Orientational order parameter of every molecule (reference ``order.py:234-262``)."""
+    return neighbour_analysis(box, position, orientation, max_radius, max_neighbours, want=("order",))["order"]
+
+
+def num_neighbours(box, position, max_radius: float = 3.5) -> np.ndarray:
+    """Number of neighbours within ``max_radius``; k = 9, so it saturates at 9 like the reference
+    (``order.py:265-281``, SURVEY trap T8)."""
+    return neighbour_analysis(box, position, None, max_radius, 9, want=("counts",))["counts"]
+
+
+def relative_distances(box, position, max_radius: float = 3.5, max_neighbours: int = 8) -> np.ndarray:
+    """Distance to each neighbour, 0 where missing (reference ``order.py:284-309``)."""
+    rsq = neighbour_analysis(box, position, None, max_radius, max_neighbours, want=("rsq",))["rsq"]
+    distances = rsq.astype(np.float64)
+    distances[distances < 0] = 0
+    return np.sqrt(distances)
+
+
+def create_orient_ordering(threshold: float):
+    """Reference ``order.py:126-147``."""
+
+    def compute_orient_ordering(snap) -> np.ndarray:
+        return orientational_order(snap.box, snap.position, snap.orientation) > threshold
+
+    return compute_orient_ordering

@@ -1,0 +1,230 @@
+"""The driver loop: read a trajectory and compute the dynamics of every active time-origin.
+
+Drop-in for reference ``read/_read.py``: ``process_file`` keeps the signature, the row schema (15
+``compute_all`` quantities + ``keyframe``, ``temperature``, ``pressure``) and the per-row error
+handling, but instead of one ``(Dynamics, Relaxations)`` pair of Python objects per origin
+(``_read.py:117,135-141``) all origins live in one :class:`~sdanalysis_b200.engine.DynamicsEngine`
+and each frame costs one fused kernel pass; result rows come back asynchronously.
+"""
+
+import datetime
+import logging
+from collections import deque
+from pathlib import Path
+from typing import Any, Dict, Iterator, List, Optional
+
+import numpy as np
+import pandas
+
+from ..engine import DynamicsEngine
+from ..frame import Frame, HoomdFrame
+from ..gsdio import open_gsd
+from ..molecules import Trimer
+from ..util import get_filename_vars
+from ._gsd import FileIterator, read_gsd_trajectory
+
+logger = logging.getLogger(__name__)
+
+
+def _write_table(df: pandas.DataFrame, filename: Path, group: str, append: bool) -> None:
+    """HDF5 like the reference when PyTables is present (``_read.py:57-61``); otherwise the table
+    goes to ``<stem>.<group>.parquet`` / ``.csv`` next to the requested file."""
+    filename = Path(filename)
+    if filename.suffix in (".h5", ".hdf5", ".hdf"):
+        try:
+            import tables  # noqa: F401
+
+            df.to_hdf(filename, key=group, format="table", append=append)
+            return
+        except ImportError:
+            logger.warning("PyTables is not installed: writing %s as parquet instead of HDF5", group)
+            filename = filename.with_suffix(f".{group}.parquet")
+    if filename.suffix == ".csv":
+        df.to_csv(filename, mode="a" if append else "w", header=not append, index=False)
+        return
+    target = filename if filename.suffix == ".parquet" else filename.with_suffix(f".{group}.parquet")
+    if append and target.exists():
+        df = pandas.concat([pandas.read_parquet(target), df], ignore_index=True)
+    df.to_parquet(target, index=False)
+
+
+class WriteCache:
+    """Rows buffered in memory and flushed to ``filename`` every 8192 (reference ``_read.py:31-79``)."""
+
+    def __init__(self, filename: Optional[Path] = None, group: str = "dynamics", cache_multiplier: int = 1, to_append: bool = False):
+        if group is None:
+            raise ValueError("Group can not be None.")
+        self._filename = filename
+        self.group = group
+        self.cache_multiplier = cache_multiplier
+        self.to_append = to_append
+        self._cache: List[Any] = []
+        self._cache_default = 8192
+        self._emptied_count = 0
+
+    @property
+    def _cache_size(self) -> int:
+        return self.cache_multiplier * self._cache_default
+
+    def append(self, item: Any) -> None:
+        if self._cache and len(self._cache) == self._cache_size:
+            self.flush()
+            self._emptied_count += 1
+        self._cache.append(item)
+
+    def flush(self) -> None:
+        assert self.filename is not None
+        _write_table(self.to_dataframe(), self.filename, self.group, self.to_append)
+        self.to_append = True
+        self._cache.clear()
+
+    @property
+    def filename(self) -> Optional[Path]:
+        return None if self._filename is None else Path(self._filename)
+
+    def __len__(self) -> int:
+        return self._cache_size * self._emptied_count + len(self._cache)
+
+    def to_dataframe(self):
+        return pandas.DataFrame.from_records(self._cache)
+
+
+def process_frames(
+    file_iterator: FileIterator,
+    wave_number: float,
+    *,
+    mol_relaxations: List[Dict[str, Any]] = None,
+    scattering_function: bool = False,
+    temperature: float = np.nan,
+    pressure: float = np.nan,
+    sink=None,
+    device=None,
+    struct_mode: str = "reference",
+    pipeline_depth: int = 3,
+):
+    """Run the hot loop of ``process_file`` (reference ``_read.py:128-168``) over any iterator of
+    ``(indexes, frame)`` pairs.  Rows are passed to ``sink(row)``; returns the engine (per-origin
+    passage times stay on the device until ``engine.summary(key)`` is called)."""
+    if scattering_function:
+        logger.warning("scattering_function is not on the accelerated path; the column stays NaN")
+    engine = None
+    pending = deque()
+
+    def drain(limit):
+        while len(pending) > limit:
+            result = pending.popleft()
+            try:
+                rows = result.rows()
+            except (ValueError, RuntimeError) as e:  # _read.py:154-156
+                logger.warning(e)
+                continue
+            for key, row in zip(result.keys, rows):
+                row["keyframe"] = key
+                row["temperature"] = temperature
+                row["pressure"] = pressure
+                sink(row)
+
+    for indexes, frame in file_iterator:
+        if frame.position.shape[0] == 0:
+            logger.warning("Found malformed frame ... continuing")
+            continue
+        logger.info("Indexes for step %s: %s", frame.timestep, indexes)
+        if engine is None:
+            engine = DynamicsEngine(
+                frame.position.shape[0],
+                frame.box,
+                wave_number,
+                trackers=mol_relaxations if mol_relaxations is not None else "default",
+                mol_sites=Trimer().positions,
+                device=device,
+                struct_mode=struct_mode,
+                ring_depth=pipeline_depth + 1,
+            )
+        try:
+            pending.append(engine.step(frame.timestep, frame.position, frame.orientation, list(indexes)))
+        except (ValueError, RuntimeError) as e:
+            logger.warning(e)
+            continue
+        drain(pipeline_depth - 1)
+    drain(0)
+    return engine
+
+
+def process_file(
+    infile: Path,
+    wave_number: float,
+    steps_max: Optional[int] = None,
+    linear_steps: Optional[int] = None,
+    keyframe_interval: int = 1_000_000,
+    keyframe_max: int = 500,
+    mol_relaxations: List[Dict[str, Any]] = None,
+    outfile: Optional[Path] = None,
+    scattering_function: bool = False,
+) -> Optional[pandas.DataFrame]:
+    """Read a trajectory and compute the dynamic quantities of every time-origin.
+
+    Same arguments and results as reference ``_read.py:82-195``: returns the ``dynamics`` DataFrame
+    when ``outfile`` is None, otherwise writes the ``dynamics`` and ``molecular_relaxations`` tables
+    and returns None.
+    """
+    assert infile is not None
+    infile = Path(infile)
+    logger.info("Processing %s", infile)
+    start_time = datetime.datetime.now()
+
+    sim_variables = get_filename_vars(infile)
+    temperature = np.nan if sim_variables.temperature is None else float(sim_variables.temperature)
+    pressure = np.nan if sim_variables.pressure is None else float(sim_variables.pressure)
+    dataframes = WriteCache(filename=outfile) if outfile is not None else WriteCache()
+
+    if infile.suffix == ".gsd":
+        file_iterator = read_gsd_trajectory(
+            infile=infile,
+            steps_max=steps_max,
+            linear_steps=linear_steps,
+            keyframe_interval=keyframe_interval,
+            keyframe_max=keyframe_max,
+        )
+    else:
+        raise ValueError(f"unsupported trajectory format {infile.suffix!r}: only .gsd is on the accelerated path")
+
+    engine = process_frames(
+        file_iterator,
+        wave_number,
+        mol_relaxations=mol_relaxations,
+        scattering_function=scattering_function,
+        temperature=temperature,
+        pressure=pressure,
+        sink=dataframes.append,
+    )
+    logger.info("Finished processing %s, took %s", infile, datetime.datetime.now() - start_time)
+
+    if outfile is not None:
+        dataframes.flush()
+        if engine is not None and engine.trackers:
+            keys = list(engine.origins.keys())
+            mol_relax = pandas.concat((pandas.DataFrame(engine.summary(k)) for k in keys), keys=keys)
+            mol_relax["temperature"] = temperature
+            mol_relax["pressure"] = pressure
+            mol_relax.index.names = ["keyframe", "molecule"]
+            mol_relax = mol_relax.reset_index()
+            _write_table(mol_relax, Path(outfile), "molecular_relaxations", False)
+        return None
+
+    df = dataframes.to_dataframe()
+    assert len(df) > 0
+    return df
+
+
+def open_trajectory(filename: Path, progressbar=None, frame_interval=1) -> Iterator[Frame]:
+    """Frames of a GSD trajectory, skipping corrupt ones (reference ``_read.py:198-241``)."""
+    filename = Path(filename)
+    if filename.suffix != ".gsd":
+        raise ValueError(f"unsupported trajectory format {filename.suffix!r}")
+    with open_gsd(filename) as trj:
+        for index in range(0, len(trj), frame_interval):
+            try:
+                yield HoomdFrame(trj[index])
+            except RuntimeError:
+                logger.info("Found corrupt frame at index %s continuing", index)
+                continue

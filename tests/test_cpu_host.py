@@ -1,0 +1,167 @@
+"""CPU-only tests of the host logic: step schedules, GSD reader/writer, trajectory iterators."""
+
+import json
+
+import numpy as np
+import pytest
+
+from sdanalysis_b200 import StepSize
+from sdanalysis_b200.frame import HoomdFrame
+from sdanalysis_b200.gsdio import GSDWriter, open_gsd
+from sdanalysis_b200.read import WriteCache, open_trajectory, read_gsd_trajectory
+from sdanalysis_b200.read import _gsd
+from sdanalysis_b200.synthetic import SyntheticTrimer, exponential_schedule, linear_schedule
+from sdanalysis_b200.util import get_filename_vars
+
+
+def test_stepsize_matches_reference_golden(golden_dir):
+    """Sequences produced by the reference's own StepSize.py (tests/golden/make_golden.py)."""
+    gold = json.loads((golden_dir / "stepsize_golden.json").read_text())
+    for case in gold["generate_steps"]:
+        assert list(StepSize.generate_steps(*case["args"])) == case["steps"]
+    for case in gold["series"]:
+        total, lin, gen, max_gen = case["args"]
+        series = StepSize.GenerateStepSeries(total, num_linear=lin, gen_steps=gen, max_gen=max_gen)
+        assert [[int(s), list(series.get_index())] for s in series] == case["pairs"], case["args"]
+
+
+@pytest.mark.parametrize("total,lin", [(100, 10), (1000, 100), (12345, 7)])
+def test_stepsize_properties(total, lin):
+    """stepsize_test.py:105-222: strictly increasing, no duplicates, ends on total_steps."""
+    steps = list(StepSize.GenerateStepSeries(total, num_linear=lin, gen_steps=50, max_gen=4))
+    assert steps == sorted(set(steps)) and steps[0] == 0 and steps[-1] == total
+
+
+@pytest.fixture()
+def gsd_trajectory(tmp_path):
+    """read_gsd_test.py:24-43: 10 particles on the GenerateStepSeries(10000, 100, 1000) schedule."""
+    path = tmp_path / "test-Trimer-P13.50-T3.00.gsd"
+    with GSDWriter(path) as dst:
+        for timestep in StepSize.GenerateStepSeries(total_steps=10000, num_linear=100, gen_steps=1000):
+            dst.append(timestep, [1.0, 1.0, 0.0, 0.0, 0.0, 0.0], np.zeros((10, 3)), dimensions=2)
+    return path
+
+
+def test_gsd_roundtrip(tmp_path):
+    walk = SyntheticTrimer(257, seed=3)
+    path = tmp_path / "walk.gsd"
+    frames = []
+    with GSDWriter(path) as dst:
+        for step in (0, 5, 50):
+            walk.advance(step - walk.timestep)
+            pos, quat = walk.frame()
+            frames.append((step, pos, quat))
+            dst.append(step, walk.box, pos, quat)
+    with open_gsd(path) as trj:
+        assert len(trj) == 3
+        for snap, (step, pos, quat) in zip(trj, frames):
+            assert snap.step == step and snap.dimensions == 2 and len(snap) == 257
+            assert np.array_equal(snap.position, pos) and np.array_equal(snap.orientation, quat)
+            assert np.array_equal(snap.box, walk.box)
+            assert not snap.position.flags.writeable  # zero-copy, read-only views
+        assert trj[-1].step == 50
+        with pytest.raises(IndexError):
+            trj[3]
+
+
+def test_gsd_bodies_define_molecules(tmp_path):
+    """frame.py:136-156: num_mols = max(body) + 1, clamped to the particle count."""
+    path = tmp_path / "b.gsd"
+    pos = np.arange(27, dtype=np.float32).reshape(9, 3)
+    with GSDWriter(path) as dst:
+        dst.append(7, [5, 5, 1, 0, 0, 0], pos, body=[0, 1, 2, 0, 0, 1, 1, 2, 2])
+        dst.append(8, [5, 5, 1, 0, 0, 0], pos, body=[-1] * 9)
+    with open_gsd(path) as trj:
+        assert len(trj[0]) == 3 and trj[0].position.shape == (3, 3) and trj[0].orientation.shape == (3, 4)
+        assert len(trj[1]) == 9
+        assert np.all(trj[0].orientation[:, 0] == 1)  # default orientation (1,0,0,0)
+
+
+def test_golden_dump_matches_reference_test_expectations(golden_dir):
+    """frame_test.py:46-72 contract on data decoded from the bundled dump files."""
+    g = np.load(golden_dir / "liquid.npz")
+    assert g["position"].dtype == np.float32 and g["position"].shape == (1250, 3)
+    assert g["orientation"].dtype == np.float32 and g["orientation"].shape == (1250, 4)
+    assert int(g["num_particles"]) == 3750 and int(g["timestep"]) == 20_000_000
+    assert not np.any(g["orientation"][:, 1:3])  # planar quaternions
+    assert np.allclose(np.linalg.norm(g["orientation"], axis=1), 1, atol=1e-6)
+
+
+def test_read_trajectory_linear(gsd_trajectory):
+    """read_gsd_test.py:51-57."""
+    for index, (_, snap) in enumerate(read_gsd_trajectory(gsd_trajectory, steps_max=100, linear_steps=None)):
+        assert isinstance(snap, HoomdFrame) and snap.timestep == index
+
+
+def test_read_trajectory_exp(gsd_trajectory):
+    """read_gsd_test.py:60-67."""
+    traj = read_gsd_trajectory(gsd_trajectory, steps_max=200, linear_steps=100, keyframe_interval=1000)
+    steps = StepSize.GenerateStepSeries(total_steps=200, num_linear=100, gen_steps=1000)
+    count = 0
+    for index, (_, snap) in zip(steps, traj):
+        assert snap.timestep == index
+        count += 1
+    assert count > 100
+
+
+def test_linear_sequence_keyframes(gsd_trajectory):
+    """read_test.py:49-66: one shared growing index list; keyframe_max + 1 origins (trap T5)."""
+    for index, _ in _gsd._gsd_linear_trajectory(gsd_trajectory):
+        assert index == [0]
+    seen = 0
+    for index, frame in read_gsd_trajectory(gsd_trajectory, linear_steps=None, keyframe_interval=10, steps_max=100):
+        assert index == list(range(frame.timestep // 10 + 1))
+        seen += 1
+    assert seen == 101
+    longest = max(len(i) for i, _ in read_gsd_trajectory(gsd_trajectory, linear_steps=None, keyframe_interval=1, keyframe_max=4, steps_max=50))
+    assert longest == 5
+
+
+def test_exponential_iterator_skips_missing_steps(tmp_path):
+    """_gsd.py:154-182: trajectory frames absent from the schedule and vice versa are skipped."""
+    path = tmp_path / "gaps.gsd"
+    steps = [0, 1, 2, 3, 5, 7, 8, 9, 10, 15, 20, 30]
+    with GSDWriter(path) as dst:
+        for s in steps:
+            dst.append(s, [1, 1, 0, 0, 0, 0], np.zeros((4, 3)))
+    got = [f.timestep for _, f in read_gsd_trajectory(path, steps_max=30, linear_steps=10, keyframe_interval=1000)]
+    assert got == [0, 1, 2, 3, 5, 7, 8, 9, 10, 20, 30]
+
+
+def test_open_trajectory(gsd_trajectory):
+    frames = list(open_trajectory(gsd_trajectory, frame_interval=50))
+    assert [f.timestep for f in frames][:3] == [0, 50, 100]
+    with pytest.raises(ValueError):
+        next(open_trajectory("x.lammpstrj"))
+
+
+def test_write_cache(tmp_path):
+    """read_test.py:69-110."""
+    out = tmp_path / "cache.parquet"
+    cache = WriteCache(out)
+    for i in range(9000):
+        cache.append({"value": i})
+    assert len(cache._cache) == 9000 - 8192 and len(cache) == 9000
+    cache.flush()
+    assert len(cache._cache) == 0 and out.is_file()
+    import pandas
+
+    assert len(pandas.read_parquet(out)) == 9000
+
+
+def test_filename_variables():
+    """util_test.py:86-148 (subset relevant to process_file)."""
+    v = get_filename_vars("trajectory-Trimer-P13.50-T3.00.gsd")
+    # "Trimer" starts with "T": the reference parses it as a temperature that the real one overrides
+    assert (v.temperature, v.pressure, v.crystal) == ("3.00", "13.50", None)
+    v = get_filename_vars("dump-Trimer-P1.00-T0.40-p2gg-ID3.gsd")
+    assert (v.temperature, v.pressure, v.crystal, v.iteration_id) == ("0.40", "1.00", "p2gg", "3")
+    assert get_filename_vars("test.gsd") == (None, None, None, None)
+
+
+def test_schedules_match_survey_counts():
+    """(frame, origin) pair counts of the BASELINE configs."""
+    pairs = list(exponential_schedule(1000, 10, 10, 100))
+    assert len(pairs) == 1001 and sum(len(i) for _, i in pairs) == 2405
+    pairs = list(linear_schedule(1000, 10, 99))
+    assert len(pairs[-1][1]) == 100 and sum(len(i) for _, i in pairs) == 50500

@@ -1,0 +1,132 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol ``include/sdb200.h``
+declares, and its host-compiled arithmetic helpers agree with the oracle.  No GPU compute."""
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import rowan_shim as rowan
+from oracle.freud_shim import Box
+
+REPO = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+
+    __graft_entry__.build()
+    from sdanalysis_b200 import _lib
+
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    from sdanalysis_b200 import _lib
+
+    header = (REPO / "include" / "sdb200.h").read_text()
+    declared = set(re.findall(r"\b(sdb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.sdb_version()
+
+
+def test_struct_layouts_match_header():
+    from sdanalysis_b200 import _lib
+
+    assert ctypes.sizeof(_lib.SdbOrigin) == 32 == np.dtype(_lib.ORIGIN_DTYPE).itemsize
+    assert ctypes.sizeof(_lib.SdbSegment) == 24 == np.dtype(_lib.SEGMENT_DTYPE).itemsize
+    assert ctypes.sizeof(_lib.SdbTracker) == 24
+    assert ctypes.sizeof(_lib.SdbDynParams) == 32 + 6 * 24
+
+
+def test_missing_gpu_fails_loudly():
+    """No CPU fallback: without a CUDA device the product path raises instead of computing."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from sdanalysis_b200 import dynamics, order
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dynamics.Dynamics(0, [10, 10, 10], np.zeros((4, 3), np.float32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        order.compute_neighbours([10, 10, 1, 0, 0, 0], np.zeros((4, 3), np.float32))
+
+
+def test_wrap_helper_is_bit_exact(lib):
+    rng = np.random.default_rng(0)
+    n = 4000
+    v = np.zeros((n, 3), np.float32)
+    v[:, 0] = rng.uniform(-300, 300, n)
+    v[:, 1] = rng.uniform(-300, 300, n)
+    v[:200, :2] = rng.normal(0, 1e-5, (200, 2))
+    v[200:210] = 0
+    ox, oy = ctypes.c_float(), ctypes.c_float()
+    for lx, ly, xy in [(62.75029, 108.68669, 0.0), (10.0, 7.0, 0.3), (2236.068, 2236.068, 0.0)]:
+        want = Box(lx, ly, xy=xy, is2D=True).wrap(v)
+        for i in range(n):
+            lib.sdb_test_wrap2d(lx, ly, xy, v[i, 0], v[i, 1], ctypes.byref(ox), ctypes.byref(oy))
+            assert np.float32(ox.value) == want[i, 0] and np.float32(oy.value) == want[i, 1], (lx, i)
+
+
+def test_rotation_increment_helper_matches_oracle(lib):
+    rng = np.random.default_rng(1)
+    n = 6000
+    th0 = rng.uniform(-np.pi, np.pi, n)
+    th1 = th0 + np.concatenate([rng.normal(0, 0.05, n // 2), rng.uniform(-np.pi, np.pi, n - n // 2)])
+    q0 = np.zeros((n, 4), np.float32)
+    q1 = np.zeros((n, 4), np.float32)
+    q0[:, 0], q0[:, 3] = np.cos(th0 / 2), np.sin(th0 / 2)
+    q1[:, 0], q1[:, 3] = np.cos(th1 / 2), np.sin(th1 / 2)
+    want = rowan.to_euler(rowan.divide(q1, q0))[:, 0]
+    bad = ctypes.c_int32(0)
+    got = np.array(
+        [lib.sdb_test_rot_increment(q1[i, 0], q1[i, 3], q0[i, 0], q0[i, 3], ctypes.byref(bad)) for i in range(n)]
+    )
+    assert np.max(np.abs(got - want)) < 4e-15
+    # what matters: the f32 accumulator after adding the increment
+    acc = rng.normal(0, 1.0, n).astype(np.float32)
+    a = (acc.astype(np.float64) + want).astype(np.float32)
+    b = (acc.astype(np.float64) + got).astype(np.float32)
+    assert np.sum(a != b) <= 1
+    # rowan rejects non-unit quotients with ValueError: the helper flags them
+    lib.sdb_test_rot_increment(0.6, 0.9, 0.6, 0.8, ctypes.byref(bad))
+    assert bad.value == 1
+    assert lib.sdb_test_rot_increment(0.6, 0.8, 0.6, 0.8, ctypes.byref(bad)) == 0.0 and bad.value == 0
+
+
+def test_threshold_cuts_are_exact():
+    """disp2 >= cut  <=>  fl32(sqrt(disp2)) > thr, checked on both sides of every cut."""
+    from sdanalysis_b200.engine import _cut_direct, _cut_sqrt
+
+    for thr in [0.0, 0.4, np.pi / (2 * 2.9), 3 * np.pi / (2 * 2.9), 1.0, 1e-3, 123.456]:
+        t32 = np.float32(thr)
+        gt, ge = _cut_sqrt(thr, True), _cut_sqrt(thr, False)
+        assert np.sqrt(gt) > t32 and not np.sqrt(np.nextafter(gt, np.float32(0))) > t32 or gt == 0
+        assert np.sqrt(ge) >= t32
+        if ge > 0:
+            assert not np.sqrt(np.nextafter(ge, np.float32(0))) >= t32
+        assert _cut_direct(thr, True) == np.nextafter(t32, np.float32(np.inf)) and _cut_direct(thr, False) == t32
+
+
+def test_tracker_validation_errors():
+    """Error behaviour of Relaxations.set_mol_relax / create_mol_relaxations (relaxations.py:108-116,316-329)."""
+    from sdanalysis_b200.engine import build_trackers
+
+    with pytest.raises(ValueError):
+        build_trackers([{"threshold": 1.0}])
+    with pytest.raises(ValueError):
+        build_trackers([{"name": "a"}])
+    with pytest.raises(ValueError):
+        build_trackers([{"name": "a", "threshold": -1.0}])
+    with pytest.raises(ValueError):
+        build_trackers([{"name": "a", "threshold": 1.0, "last_passage": True, "last_passage_cutoff": -2.0}])
+    specs = build_trackers(
+        [{"name": "a", "threshold": 1.0}, {"name": "b", "threshold": 0.5, "last_passage": True}, {"name": "c", "threshold": 1, "type": "rotation"}]
+    )
+    assert [s.bit for s in specs] == [0, 1, 3] and specs[1].cutoff == 1.5

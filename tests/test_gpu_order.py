@@ -1,0 +1,88 @@
+"""Parity of the cell-list neighbour kernel and the order parameter with the CPU oracle."""
+
+import numpy as np
+import pytest
+
+from oracle import order as oorder
+
+pytestmark = pytest.mark.gpu
+MISSING = 2 ** 32 - 1
+
+
+def _no_ties(rsq):
+    """Rows whose listed distances are strictly increasing (tie order is implementation-defined)."""
+    valid = rsq >= 0
+    d = np.where(valid, rsq, np.inf)
+    return np.all((np.diff(d, axis=1) > 0) | ~valid[:, 1:], axis=1)
+
+
+def _compare(box, pos, quat, r, k):
+    from sdanalysis_b200 import order
+
+    got = order.neighbour_analysis(box, pos, quat, r, k, want=("nlist", "rsq", "counts", "order"))
+    nn = oorder.setup_neighbours(box, pos, r, k)
+    want_list, want_rsq = nn.getNeighborList(), nn.r_sq_list
+    rows = _no_ties(want_rsq)
+    assert rows.mean() > 0.99
+    # bit-exact lists and squared distances (same f32 operations as the oracle's freud restatement)
+    assert np.array_equal(got["nlist"][rows], want_list[rows])
+    assert np.array_equal(got["rsq"][rows], want_rsq[rows])
+    assert np.array_equal(got["counts"], nn.nlist.neighbor_counts)
+    want_order = oorder._orientational_order(want_list, quat)
+    np.testing.assert_allclose(got["order"][rows], want_order[rows], rtol=1e-5, atol=1e-7)
+    return got
+
+
+def test_liquid_frame(golden_dir):
+    g = np.load(golden_dir / "liquid.npz")
+    got = _compare(g["box"], g["position"], g["orientation"], 3.5, 8)
+    assert (got["nlist"] == MISSING).any()  # the liquid has molecules with fewer than 8 neighbours
+
+
+def test_liquid_num_neighbours_saturates(golden_dir):
+    """SURVEY trap T8: counts saturate at k = 9."""
+    from sdanalysis_b200 import order
+
+    g = np.load(golden_dir / "liquid.npz")
+    counts = order.num_neighbours(g["box"], g["position"], 3.5)
+    assert np.array_equal(counts, oorder.num_neighbours(g["box"], g["position"], 3.5))
+    assert counts.max() == 9
+
+
+@pytest.mark.parametrize("n,r,k", [(4096, 3.5, 8), (5000, 3.5, 9), (3000, 6.0, 16), (700, 2.0, 3)])
+def test_synthetic_liquid(n, r, k):
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    walk = SyntheticTrimer(n, seed=n)
+    walk.advance(400)
+    pos, quat = walk.frame()
+    _compare(walk.box, pos, quat, r, k)
+
+
+def test_small_and_tilted_boxes():
+    """Boxes with fewer than 3 cells per side and a tilted box (brute-force oracle)."""
+    from sdanalysis_b200 import order
+
+    rng = np.random.default_rng(4)
+    for box in ([7.5, 12.0, 1, 0, 0, 0], [9.0, 9.0, 1, 0.25, 0, 0], [40.0, 8.0, 1, 0, 0, 0]):
+        box = np.array(box, dtype=np.float32)
+        n = 300
+        pos = np.zeros((n, 3), np.float32)
+        pos[:, 0] = rng.uniform(-box[0] / 2, box[0] / 2, n)
+        pos[:, 1] = rng.uniform(-box[1] / 2, box[1] / 2, n)
+        got = order.neighbour_analysis(box, pos, None, 3.5, 8, want=("nlist", "rsq", "counts"))
+        nn = oorder.setup_neighbours(box, pos, 3.5, 8)
+        rows = _no_ties(nn.r_sq_list)
+        assert np.array_equal(got["nlist"][rows], nn.getNeighborList()[rows]), box
+        assert np.array_equal(got["counts"], nn.nlist.neighbor_counts), box
+
+
+def test_isolated_molecules_have_no_neighbours():
+    from sdanalysis_b200 import order
+
+    pos = np.array([[0, 0, 0], [20, 20, 0], [-20, 20, 0], [20, -20, 0]], dtype=np.float32)
+    box = [100, 100, 1, 0, 0, 0]
+    quat = np.tile(np.array([1, 0, 0, 0], np.float32), (4, 1))
+    got = order.neighbour_analysis(box, pos, quat, 3.5, 8, want=("nlist", "rsq", "counts", "order"))
+    assert np.all(got["nlist"] == MISSING) and np.all(got["rsq"] == -1) and np.all(got["counts"] == 0)
+    assert np.all(got["order"] == 1.0)  # missing neighbours are replaced by the molecule itself
