@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame dynamics hot path (BASELINE.json: molecule*origin updates/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[3], the configuration the target is quoted on): synthetic 2D Trimer
+liquid, 1,000,000 molecules, 200 time-origins, dense (linear) schedule in its steady state -- every
+frame updates all 200 origins (Dynamics.compute_all + Relaxations.add each).  A *step* is one frame:
+200 x 1e6 molecule*origin updates.  With N GPUs the 200 origins are sharded round-robin over the
+ranks and each frame is broadcast from rank 0 over NCCL (strong scaling: total work is fixed).
+
+* ``value``  frames already resident in HBM (rank 0) when the timed region starts.
+* ``e2e``    the same loop through the public host API with frames in pinned HOST memory: the H2D
+             copy of every frame and the D2H read of its result rows are inside the timed region.
+* ``roofline``      dominant kernel (``dyn_step_kernel``) timed with CUDA events on its stream.
+* ``cpu_baseline``  the CPU oracle (a numpy restatement of the reference; the reference itself cannot
+             run here: freud/rowan/gsd are not installed) on a bounded sample, one core.
+* ``--impl reference``  the CPU arm alone: origin-parallel oracle processes on all host cores.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+for _p in (REPO, REPO / "statdyn-analysis_b200"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
+
+METRIC = "molecule*origin updates/sec (dynamics+relaxation)"
+UNIT = "updates/s"
+N_MOLS = 1_000_000
+N_ORIGINS = 200
+WAVE_NUMBER = 2.9
+SIGMA_R, SIGMA_T = 0.01, 0.02
+WORKLOAD = (
+    "configs[3]: synthetic 2D Trimer liquid, 1M molecules, 200 time-origins, dense linear schedule "
+    "(steady state: all origins active every frame), Dynamics.compute_all + Relaxations.add"
+)
+
+
+def _peaks():
+    path = REPO / "MEASURED_PEAKS.json"
+    if path.exists():
+        return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    QUERY = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, sm_max, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                sm_max = max(sm_max, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": sm_max or None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy restatement of the reference), timed on host cores
+# ------------------------------------------------------------------------------------------------
+def _oracle_worker(n_mols, seed, n_frames, barrier, out_q, widx):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import dynamics as odyn
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    walk = SyntheticTrimer(n_mols, seed=seed, sigma_r=SIGMA_R, sigma_theta=SIGMA_T)
+    pos, quat = walk.frame()
+    dyn = odyn.Dynamics(0, walk.box, pos, quat, "trimer", WAVE_NUMBER)
+    relax = odyn.Relaxations(0, walk.box, pos, quat, "trimer", wave_number=WAVE_NUMBER)
+    frames = []
+    for _ in range(n_frames):
+        walk.advance(1)
+        frames.append((walk.timestep,) + walk.frame())
+    times = []
+    for ts, pos, quat in frames:
+        barrier.wait()
+        t0 = time.perf_counter()
+        dyn.compute_all(ts, pos, quat)
+        relax.add(ts, pos, quat)
+        barrier.wait()
+        times.append(time.perf_counter() - t0)
+    out_q.put((widx, times))
+
+
+def cpu_arm(n_mols, workers, steps, warmup):
+    """Origin-parallel oracle: ``workers`` processes, one origin each; a step = one frame for every
+    worker's origin.  Returns (updates/s, ms per step)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    barrier = ctx.Barrier(workers)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_oracle_worker, args=(n_mols, 100 + w, steps + warmup, barrier, q, w)) for w in range(workers)]
+    for p in procs:
+        p.start()
+    results = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    per_step = [max(r[1][i] for r in results) for i in range(warmup, warmup + steps)]
+    total = sum(per_step)
+    return workers * n_mols * steps / total, 1e3 * total / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 16))
+    n_mols = args.molecules
+    # bounded sample: every step is one frame of `workers` origins (of the 200) at full N
+    steps, warmup = min(args.steps, 6), min(args.warmup, 1)
+    value, ms = cpu_arm(n_mols, workers, steps, warmup)
+    sample = (
+        f"{steps} timed frames x {workers} of {N_ORIGINS} origins at N={n_mols} "
+        f"(one oracle process per origin, {workers} processes); per-origin cost is independent of the other origins"
+    )
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "molecules": n_mols, "origins": N_ORIGINS, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle port of the reference (numpy restatement; freud/rowan/gsd are not installable here)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    __graft_entry__.build()
+
+    from sdanalysis_b200 import _lib
+    from sdanalysis_b200.distributed import ShardedDynamics, partition
+    from sdanalysis_b200.engine import DynamicsEngine
+    from sdanalysis_b200.molecules import Trimer
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    n, n_origins = args.molecules, args.origins
+    steps, warmup = args.steps, max(args.warmup, 3)
+    all_keys = list(range(n_origins))
+    local_keys = partition(all_keys, rank, world)
+
+    from sdanalysis_b200.synthetic import box_for
+
+    def make_engine():
+        return DynamicsEngine(n, box_for(n), WAVE_NUMBER, mol_sites=Trimer().positions, device=device, ring_depth=4)
+
+    n_frames = warmup + steps
+
+    def phase(host_frames):
+        """Create the origins (untimed), then W warm-up + K timed steps.  Returns timing info."""
+        engine = make_engine()
+        sharded = None
+        if world > 1:
+            def step_fn(ts, pos, quat, keys):
+                return engine.step(ts, pos, quat, keys, to_host=False)
+
+            sharded = ShardedDynamics(n, step_fn, max_local=len(local_keys) + 1, device=device)
+        # origin creation: origin k starts at frame k (linear schedule, keyframe_interval = 1)
+        timestep = 0
+        # frames: a random walk generated on rank 0's GPU
+        walk = SyntheticTrimer(n, seed=4, sigma_r=SIGMA_R, sigma_theta=SIGMA_T, device=device) if rank == 0 else None
+        for k in range(n_origins):
+            active = all_keys[: k + 1]
+            if world > 1:
+                h = sharded.post_frame(*(walk.frame() if rank == 0 else (None, None)))
+                sharded.step(timestep, active, h, gather=False)
+            else:
+                pos, quat = walk.frame()
+                engine.step(timestep, pos, quat, active, want_sums=False)
+            if rank == 0:
+                walk.advance(1)
+            timestep += 1
+        torch.cuda.synchronize()
+        # the frames of the measured steps
+        frames = []
+        if rank == 0:
+            for _ in range(n_frames):
+                pos, quat = walk.frame()
+                walk.advance(1)
+                if host_frames:
+                    frames.append((pos.cpu().pin_memory(), quat.cpu().pin_memory()))
+                else:
+                    frames.append((pos.clone(), quat.clone()))
+        else:
+            frames = [(None, None)] * n_frames
+        torch.cuda.synchronize()
+
+        results = []
+
+        def one_step(i, ts):
+            pos, quat = frames[i]
+            if world > 1:
+                h = sharded.post_frame(pos, quat)
+                results.append(sharded.step(ts, all_keys, h, gather=True))
+            else:
+                results.append(engine.step(ts, pos, quat, all_keys))
+            if len(results) > 2:
+                r = results.pop(0)
+                r() if callable(r) else r.rows()
+
+        for i in range(warmup):
+            one_step(i, timestep)
+            timestep += 1
+        while results:
+            r = results.pop(0)
+            r() if callable(r) else r.rows()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        engine.profile = []
+        launches0 = _lib.launch_count()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t_start.record()
+        for i in range(steps):
+            one_step(warmup + i, timestep)
+            timestep += 1
+        last_rows = None
+        while results:
+            r = results.pop(0)
+            last_rows = r() if callable(r) else r.rows()
+        t_end.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = t_start.elapsed_time(t_end)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        launches = _lib.launch_count() - launches0
+        prof = engine.profile
+        engine.profile = None
+        kern = {"dyn": 0.0, "struct": 0.0, "overlap": 0.0, "count": len(prof), "origins": prof[0][0] if prof else 0}
+        for _, e0, e1, e2, e3 in prof:
+            kern["dyn"] += e0.elapsed_time(e1)
+            kern["struct"] += e1.elapsed_time(e2)
+            kern["overlap"] += e2.elapsed_time(e3)
+        h2d, d2h = engine.h2d_bytes, engine.d2h_bytes
+        del engine, sharded
+        torch.cuda.empty_cache()
+        return {"ms": ms, "clocks": clocks, "launches": launches, "kern": kern, "h2d": h2d, "d2h": d2h, "rows": last_rows}
+
+    dev = phase(host_frames=False)
+    e2e = phase(host_frames=True)
+
+    updates_per_step = n * n_origins
+    value = updates_per_step * steps / (dev["ms"] * 1e-3)
+    e2e_value = updates_per_step * steps / (e2e["ms"] * 1e-3)
+
+    # ---- roofline of the dominant kernel (this rank's share) --------------------------------------
+    peak, peak_kind = _peaks()
+    a_local = dev["kern"]["origins"]
+    dyn_ms = dev["kern"]["dyn"] / max(dev["kern"]["count"], 1)
+    bytes_per_update = 49.0 + 56.0 / max(a_local, 1)  # SURVEY 8(d), linear (dense) schedule
+    algo_bytes = bytes_per_update * a_local * n
+    achieved = algo_bytes / (dyn_ms * 1e-3) / 1e9 if dyn_ms > 0 else 0.0
+    roofline = {
+        "kernel": "dyn_step_kernel (+ dyn_finalize_kernel)",
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None,
+        "algorithmic_bytes_per_update": bytes_per_update,
+        "updates_per_launch": a_local * n,
+        "launch_ms": dyn_ms,
+        "peak_source": peak_kind,
+        "other_kernels_ms_per_step": {
+            "struct": dev["kern"]["struct"] / max(dev["kern"]["count"], 1),
+            "overlap": dev["kern"]["overlap"] / max(dev["kern"]["count"], 1),
+        },
+    }
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 runs only) -----------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample_steps = 4
+        v, _ = cpu_arm(n, 1, sample_steps, 1)
+        cpu = {
+            "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{sample_steps} (frame, origin) pairs at N={n}: oracle Dynamics.compute_all + Relaxations.add, 1 process",
+        }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": dev["ms"] / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD, "molecules": n, "origins": n_origins, "origins_per_gpu": len(local_keys),
+            "parallelism": f"origin-sharded x{world}, NCCL frame broadcast" if world > 1 else "single GPU",
+            "l2": "inputs larger than L2 (>= 25 MB of state per origin and step)",
+        },
+        "e2e": {
+            "value": e2e_value, "unit": UNIT, "ms_per_step": e2e["ms"] / steps,
+            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+        },
+        "gpu_launches": dev["launches"],
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": dev["clocks"],
+        "check": {k: dev["rows"][0][k] for k in ("time", "msd", "alpha", "rot1", "overlap", "struct")}
+        if isinstance(dev["rows"], list) and dev["rows"] else None,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--molecules", type=int, default=N_MOLS)
+    ap.add_argument("--origins", type=int, default=N_ORIGINS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

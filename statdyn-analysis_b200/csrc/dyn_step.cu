@@ -30,9 +30,69 @@ struct StepArgs {
 
 constexpr int NM = SDB_LANE_MOLS * SDB_GROUPS;  // molecules per lane
 
-__global__ void __launch_bounds__(SDB_BLOCK_THREADS) dyn_step_kernel(const StepArgs a)
+// cos(x) for x >= 0 with ~1e-7 absolute error: two-constant Cody-Waite reduction to [-pi, pi], then
+// cos r = 1 - 2 sin^2(r/2) with an odd polynomial for sin on [-pi/2, pi/2].  Used for the rot1/rot2
+// means only (rtol 1e-5 on a mean of N terms); huge arguments fall back to cosf.
+__device__ __forceinline__ float sdb_cos_reduced(float x)
 {
-    __shared__ double red[SDB_BLOCK_WARPS][SDB_NFSUM][33];
+    if (x > 8192.0f) return cosf(x);
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.28125f, x);
+    r = fmaf(-k, 1.9353071795864769e-3f, r);
+    const float h = 0.5f * r, h2 = h * h;
+    float p = fmaf(h2, 1.6059043836821613e-10f, -2.5052108385441720e-8f);
+    p = fmaf(h2, p, 2.7557319223985893e-6f);
+    p = fmaf(h2, p, -1.9841269841269841e-4f);
+    p = fmaf(h2, p, 8.3333333333333332e-3f);
+    p = fmaf(h2, p, -1.6666666666666666e-1f);
+    const float sn = fmaf(h * h2, p, h);
+    return fmaf(-2.0f * sn, sn, 1.0f);
+}
+
+__device__ __forceinline__ float sdb_sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Slow path of the passage trackers (something may change for this molecule):
+// MolecularRelaxation.add relaxations.py:209-218, LastMolecularRelaxation.add :238-289.
+__device__ __forceinline__ uint32_t sdb_track(const SdbDynParams& p, uint32_t fl, float d2, float th, uint32_t* status,
+                                           long stride, uint32_t timediff, bool literal)
+{
+#pragma unroll 1
+    for (int t = 0; t < p.n_trackers; ++t) {
+        const SdbTracker tr = p.trackers[t];
+        const float val = tr.is_rotation ? th : d2;
+        uint32_t* st_word = status + (long)t * stride;
+        if (!tr.is_last) {
+            if (val >= tr.cut_gt) {
+                const bool fired = (fl >> tr.bit) & 1u;
+                if (!fired || (literal && *st_word > timediff)) *st_word = timediff;
+                fl |= 1u << tr.bit;
+            }
+        } else {
+            uint32_t s = (fl >> tr.bit) & 3u;
+            if (s == 0 && val >= tr.cut_gt) {
+                s = 1;
+                *st_word = timediff;
+            } else if (s == 1 && val < tr.cut_lt) {
+                s = 0;
+            }
+            if (s == 1 && val >= tr.cut_irr) s = 2;
+            fl = (fl & ~(3u << tr.bit)) | (s << tr.bit);
+        }
+    }
+    return fl;
+}
+
+__global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const StepArgs a)
+{
+    __shared__ float red[SDB_BLOCK_WARPS][SDB_NFSUM][33];
+    __shared__ __align__(16) float s_wx[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
+    __shared__ __align__(16) float s_wy[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
+    __shared__ __align__(16) double s_al[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -45,199 +105,226 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS) dyn_step_kernel(const StepA
     const float* prev = static_cast<const float*>(seg.d_prev);
     const bool zero_step = (seg.flags & SDB_SEG_ZERO_STEP) != 0 || a.pos == nullptr;
 
-    // ---- current frame (GSD layout) for this lane's 8 molecules -------------------------------
+    // ---- phase 1: per-segment increments for this lane's 8 molecules, parked in shared memory -----
+    //   w = box.wrap(prev - cur)  (f32, freud operation order)     _util.py:149
+    //   alpha = to_euler(q / q_prev)[0]  (f64)                     _util.py:150-153
     int j0[SDB_GROUPS];
-    float cx[NM], cy[NM], cw[NM], cz[NM];
-    int nonplanar = 0;
-#pragma unroll
+    int bad = 0;
+    const bool rotate = (seg.flags & SDB_SEG_NO_ROTATION) == 0 && !zero_step;
+#pragma unroll 1
     for (int g = 0; g < SDB_GROUPS; ++g) {
-        j0[g] = part * SDB_WARP_MOLS + g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
-        if (zero_step) {
+        const int jg = part * SDB_WARP_MOLS + g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
+        float cx[4], cy[4], cw[4], cz[4];
+        if (zero_step || jg >= n) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                cx[4 * g + e] = 0.f; cy[4 * g + e] = 0.f; cw[4 * g + e] = 1.f; cz[4 * g + e] = 0.f;
+                cx[e] = 0.f; cy[e] = 0.f; cw[e] = 1.f; cz[e] = 0.f;
             }
-        } else if (j0[g] + SDB_LANE_MOLS <= n) {
-            const float4 p0 = sdb_ldg4(a.pos + 3L * j0[g]);
-            const float4 p1 = sdb_ldg4(a.pos + 3L * j0[g] + 4);
-            const float4 p2 = sdb_ldg4(a.pos + 3L * j0[g] + 8);
-            cx[4 * g + 0] = p0.x; cy[4 * g + 0] = p0.y;
-            cx[4 * g + 1] = p0.w; cy[4 * g + 1] = p1.x;
-            cx[4 * g + 2] = p1.z; cy[4 * g + 2] = p1.w;
-            cx[4 * g + 3] = p2.y; cy[4 * g + 3] = p2.z;
+        } else if (jg + SDB_LANE_MOLS <= n) {
+            const float4 p0 = sdb_ldg4(a.pos + 3L * jg);
+            const float4 p1 = sdb_ldg4(a.pos + 3L * jg + 4);
+            const float4 p2 = sdb_ldg4(a.pos + 3L * jg + 8);
+            cx[0] = p0.x; cy[0] = p0.y;
+            cx[1] = p0.w; cy[1] = p1.x;
+            cx[2] = p1.z; cy[2] = p1.w;
+            cx[3] = p2.y; cy[3] = p2.z;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
-                if (a.quat) q = sdb_ldg4(a.quat + 4L * (j0[g] + e));
-                cw[4 * g + e] = q.x; cz[4 * g + e] = q.w;
-                nonplanar += (q.y != 0.f) | (q.z != 0.f);
+                if (a.quat) q = sdb_ldg4(a.quat + 4L * (jg + e));
+                cw[e] = q.x; cz[e] = q.w;
+                bad += (q.y != 0.f) | (q.z != 0.f);
             }
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int j = j0[g] + e;
+                const int j = jg + e;
                 const bool ok = j < n;
-                cx[4 * g + e] = ok ? __ldg(a.pos + 3L * j) : 0.f;
-                cy[4 * g + e] = ok ? __ldg(a.pos + 3L * j + 1) : 0.f;
+                cx[e] = ok ? __ldg(a.pos + 3L * j) : 0.f;
+                cy[e] = ok ? __ldg(a.pos + 3L * j + 1) : 0.f;
                 float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
                 if (ok && a.quat) q = sdb_ldg4(a.quat + 4L * j);
-                cw[4 * g + e] = q.x; cz[4 * g + e] = q.w;
-                nonplanar += (q.y != 0.f) | (q.z != 0.f);
+                cw[e] = q.x; cz[e] = q.w;
+                bad += (q.y != 0.f) | (q.z != 0.f);
             }
         }
-    }
-    if (a.cur_compact && blockIdx.y == 0 && !zero_step) {
+        if (a.cur_compact && blockIdx.y == 0 && !zero_step && jg < n) {
+            // planes are padded to a multiple of 4: whole-vector stores are safe
+            float* c = a.cur_compact + jg;
+            *reinterpret_cast<float4*>(c) = make_float4(cx[0], cx[1], cx[2], cx[3]);
+            *reinterpret_cast<float4*>(c + stride) = make_float4(cy[0], cy[1], cy[2], cy[3]);
+            *reinterpret_cast<float4*>(c + 2 * stride) = make_float4(cw[0], cw[1], cw[2], cw[3]);
+            *reinterpret_cast<float4*>(c + 3 * stride) = make_float4(cz[0], cz[1], cz[2], cz[3]);
+        }
+        float px[4], py[4], pw[4], pz[4];
+        if (prev != nullptr && jg < n && !zero_step) {
+            const float4 vx = sdb_ldg4(prev + jg);
+            const float4 vy = sdb_ldg4(prev + stride + jg);
+            const float4 vw = sdb_ldg4(prev + 2 * stride + jg);
+            const float4 vz = sdb_ldg4(prev + 3 * stride + jg);
+            px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
+            py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
+            pw[0] = vw.x; pw[1] = vw.y; pw[2] = vw.z; pw[3] = vw.w;
+            pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
+        } else {  // origin created at this frame: previous sample == current sample
 #pragma unroll
-        for (int g = 0; g < SDB_GROUPS; ++g) {
-            if (j0[g] < n) {  // planes are padded to a multiple of 4: whole-vector store is safe
-                float* c = a.cur_compact + j0[g];
-                *reinterpret_cast<float4*>(c) = make_float4(cx[4 * g], cx[4 * g + 1], cx[4 * g + 2], cx[4 * g + 3]);
-                *reinterpret_cast<float4*>(c + stride) = make_float4(cy[4 * g], cy[4 * g + 1], cy[4 * g + 2], cy[4 * g + 3]);
-                *reinterpret_cast<float4*>(c + 2 * stride) = make_float4(cw[4 * g], cw[4 * g + 1], cw[4 * g + 2], cw[4 * g + 3]);
-                *reinterpret_cast<float4*>(c + 3 * stride) = make_float4(cz[4 * g], cz[4 * g + 1], cz[4 * g + 2], cz[4 * g + 3]);
+            for (int e = 0; e < 4; ++e) {
+                px[e] = cx[e]; py[e] = cy[e]; pw[e] = cw[e]; pz[e] = cz[e];
             }
         }
-    }
-
-    // ---- per-segment increments: w = box.wrap(prev - cur), alpha = to_euler(q / q_prev)[0] ------
-    float wx[NM], wy[NM];
-    double alpha[NM];
-    int bad = nonplanar;
-    {
-        float px[NM], py[NM], pw[NM], pz[NM];
+        float wx[4], wy[4];
+        double al[4];
 #pragma unroll
-        for (int g = 0; g < SDB_GROUPS; ++g) {
-            if (prev != nullptr && j0[g] < n && !zero_step) {
-                const float4 vx = sdb_ldg4(prev + j0[g]);
-                const float4 vy = sdb_ldg4(prev + stride + j0[g]);
-                const float4 vw = sdb_ldg4(prev + 2 * stride + j0[g]);
-                const float4 vz = sdb_ldg4(prev + 3 * stride + j0[g]);
-                px[4 * g] = vx.x; px[4 * g + 1] = vx.y; px[4 * g + 2] = vx.z; px[4 * g + 3] = vx.w;
-                py[4 * g] = vy.x; py[4 * g + 1] = vy.y; py[4 * g + 2] = vy.z; py[4 * g + 3] = vy.w;
-                pw[4 * g] = vw.x; pw[4 * g + 1] = vw.y; pw[4 * g + 2] = vw.z; pw[4 * g + 3] = vw.w;
-                pz[4 * g] = vz.x; pz[4 * g + 1] = vz.y; pz[4 * g + 2] = vz.z; pz[4 * g + 3] = vz.w;
-            } else {  // origin created at this frame: previous sample == current sample
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    px[4 * g + e] = cx[4 * g + e]; py[4 * g + e] = cy[4 * g + e];
-                    pw[4 * g + e] = cw[4 * g + e]; pz[4 * g + e] = cz[4 * g + e];
-                }
-            }
-        }
-        const bool rotate = (seg.flags & SDB_SEG_NO_ROTATION) == 0 && !zero_step;
-#pragma unroll
-        for (int m = 0; m < NM; ++m) {
-            sdb_wrap2d(a.p.lx, a.p.ly, a.p.xy, SDB_FSUB(px[m], cx[m]), SDB_FSUB(py[m], cy[m]), wx[m], wy[m]);
-            alpha[m] = 0.0;
+        for (int e = 0; e < 4; ++e) {
+            sdb_wrap2d(a.p.lx, a.p.ly, a.p.xy, SDB_FSUB(px[e], cx[e]), SDB_FSUB(py[e], cy[e]), wx[e], wy[e]);
+            al[e] = 0.0;
             if (rotate) {
                 int b;
-                alpha[m] = sdb_rot_increment(cw[m], cz[m], pw[m], pz[m], a.atan_tab, b);
-                const int g = m / SDB_LANE_MOLS, e = m % SDB_LANE_MOLS;
-                bad += (b != 0) & (j0[g] + e < n);
+                al[e] = sdb_rot_increment(cw[e], cz[e], pw[e], pz[e], a.atan_tab, b);
+                bad += (b != 0) & (jg + e < n);
             }
         }
+        const int base = g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
+        *reinterpret_cast<float4*>(&s_wx[warp][base]) = make_float4(wx[0], wx[1], wx[2], wx[3]);
+        *reinterpret_cast<float4*>(&s_wy[warp][base]) = make_float4(wy[0], wy[1], wy[2], wy[3]);
+        *reinterpret_cast<double2*>(&s_al[warp][base]) = make_double2(al[0], al[1]);
+        *reinterpret_cast<double2*>(&s_al[warp][base + 2]) = make_double2(al[2], al[3]);
     }
+#pragma unroll
+    for (int g = 0; g < SDB_GROUPS; ++g)
+        j0[g] = part * SDB_WARP_MOLS + g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
     const int bad_warp = __reduce_add_sync(0xffffffffu, bad);
+    __syncwarp();
+
+    // ---- tracker pre-digestion (uniform across the grid) ------------------------------------------
+    // A molecule's flag byte cannot change when (a) it is below every "greater than" cut and no
+    // last-passage tracker is in state 1, or (b) every tracker has reached its final state.
+    float min_cut_d2 = INFINITY, min_cut_th = INFINITY;
+    uint32_t state1_bits = 0, done_pattern = 0;
+    for (int t = 0; t < a.p.n_trackers; ++t) {
+        const SdbTracker tr = a.p.trackers[t];
+        if (tr.is_rotation) min_cut_th = fminf(min_cut_th, tr.cut_gt);
+        else min_cut_d2 = fminf(min_cut_d2, tr.cut_gt);
+        if (tr.is_last) {
+            state1_bits |= 1u << tr.bit;
+            done_pattern |= 2u << tr.bit;
+        } else {
+            done_pattern |= 1u << tr.bit;
+        }
+    }
+    const bool track = a.p.n_trackers > 0;
+    const bool do_sums = a.p.do_sums != 0;
+    int live_count = 0;
+#pragma unroll
+    for (int g = 0; g < SDB_GROUPS; ++g) live_count += max(0, min(SDB_LANE_MOLS, n - j0[g]));
+    const int live_warp = __reduce_add_sync(0xffffffffu, live_count);
 
     // ---- stream the per-origin state ----------------------------------------------------------
     for (int oi = 0; oi < seg.count; ++oi) {
         const int o = seg.first + oi;
         const SdbOrigin org = a.origins[o];
-        const bool is_new = org.flags & SDB_ORIGIN_NEW;
-        const bool literal = org.flags & SDB_ORIGIN_LITERAL;
         float* dbase = org.d_delta;
         uint8_t* fbase = org.d_flags;
         uint32_t* sbase = org.d_status;
+        double* out = a.partials + ((long)o * a.n_parts + part) * SDB_NSUM;
 
-        double acc[SDB_NFSUM];
+        if (org.flags & SDB_ORIGIN_NEW) {
+            // Dynamics.from_frame / Relaxations.from_frame followed by the first compute_all / add with
+            // the same frame: zero motion, nothing relaxed (read/_read.py:135-153).
 #pragma unroll
-        for (int v = 0; v < SDB_NFSUM; ++v) acc[v] = 0.0;
+            for (int g = 0; g < SDB_GROUPS; ++g) {
+                if (j0[g] >= n) continue;
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                sdb_st_stream4(dbase + j0[g], zero);
+                sdb_st_stream4(dbase + stride + j0[g], zero);
+                sdb_st_stream4(dbase + 2 * stride + j0[g], zero);
+                if (track) {
+                    *reinterpret_cast<uint32_t*>(fbase + j0[g]) = 0u;
+                    for (int t = 0; t < a.p.n_trackers; ++t)
+                        *reinterpret_cast<uint4*>(sbase + (long)t * stride + j0[g]) =
+                            make_uint4(SDB_NO_STATUS, SDB_NO_STATUS, SDB_NO_STATUS, SDB_NO_STATUS);
+                }
+            }
+            if (do_sums && lane < SDB_NSUM) {
+                double v = 0.0;  // all sums vanish except cos(0) = 1 terms and the |dr| < d count
+                if (lane == SDB_S_COS || lane == SDB_S_COS2) v = (double)live_warp;
+                if (lane == SDB_S_COMSTRUCT && a.p.com_cut_lt > 0.f) v = (double)live_warp;
+                if (lane == SDB_S_BADQUAT) v = (double)bad_warp;
+                if (lane < SDB_NFSUM || lane == SDB_S_COMSTRUCT || lane == SDB_S_BADQUAT) out[lane] = v;
+            }
+            continue;
+        }
+        const bool literal = org.flags & SDB_ORIGIN_LITERAL;
+
+        float acc[SDB_NFSUM];
+#pragma unroll
+        for (int v = 0; v < SDB_NFSUM; ++v) acc[v] = 0.f;
         int com_count = 0;
 
 #pragma unroll
         for (int g = 0; g < SDB_GROUPS; ++g) {
             if (j0[g] >= n) continue;
-            float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), dy = dx, dt = dx;
+            const float4 dx = sdb_ld_stream4(dbase + j0[g]);
+            const float4 dy = sdb_ld_stream4(dbase + stride + j0[g]);
+            const float4 dt = sdb_ld_stream4(dbase + 2 * stride + j0[g]);
             uint32_t fl4 = 0;
-            if (!is_new) {
-                dx = sdb_ld_stream4(dbase + j0[g]);
-                dy = sdb_ld_stream4(dbase + stride + j0[g]);
-                dt = sdb_ld_stream4(dbase + 2 * stride + j0[g]);
-                if (a.p.n_trackers) fl4 = __ldcs(reinterpret_cast<const uint32_t*>(fbase + j0[g]));
-            }
+            if (track) fl4 = __ldcs(reinterpret_cast<const uint32_t*>(fbase + j0[g]));
             float ddx[4] = {dx.x, dx.y, dx.z, dx.w};
             float ddy[4] = {dy.x, dy.y, dy.z, dy.w};
             float ddt[4] = {dt.x, dt.y, dt.z, dt.w};
-            uint32_t fl4_new = 0;
+            const int sbase_i = g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
+            const float4 vwx = *reinterpret_cast<const float4*>(&s_wx[warp][sbase_i]);
+            const float4 vwy = *reinterpret_cast<const float4*>(&s_wy[warp][sbase_i]);
+            const double2 va0 = *reinterpret_cast<const double2*>(&s_al[warp][sbase_i]);
+            const double2 va1 = *reinterpret_cast<const double2*>(&s_al[warp][sbase_i + 2]);
+            const float wx[4] = {vwx.x, vwx.y, vwx.z, vwx.w};
+            const float wy[4] = {vwy.x, vwy.y, vwy.z, vwy.w};
+            const double alpha[4] = {va0.x, va0.y, va1.x, va1.y};
+            uint32_t fl4_new = fl4;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int m = 4 * g + e;
-                const int j = j0[g] + e;
                 // TrackedMotion.add, _util.py:149-153
-                ddx[e] = SDB_FSUB(ddx[e], wx[m]);
-                ddy[e] = SDB_FSUB(ddy[e], wy[m]);
-                ddt[e] = (float)((double)ddt[e] + alpha[m]);
-                // np.square(delta).sum(axis=1) / np.linalg.norm(delta, axis=1) in f32
+                ddx[e] = SDB_FSUB(ddx[e], wx[e]);
+                ddy[e] = SDB_FSUB(ddy[e], wy[e]);
+                ddt[e] = (float)((double)ddt[e] + alpha[e]);
+                // np.square(delta).sum(axis=1) in f32, one rounding per operation
                 const float d2 = SDB_FADD(SDB_FMUL(ddx[e], ddx[e]), SDB_FMUL(ddy[e], ddy[e]));
                 const float th = fabsf(ddt[e]);
-                const bool live = j < n;
-                if (a.p.do_sums && live) {
-                    const float disp = __fsqrt_rn(d2);
-                    const float t2 = SDB_FMUL(ddt[e], ddt[e]);
-                    const float c = cosf(th);
-                    acc[SDB_S_DISP] += (double)disp;
-                    acc[SDB_S_DISP2] += (double)d2;
-                    acc[SDB_S_DISP4] += (double)SDB_FMUL(d2, d2);
-                    acc[SDB_S_ROT] += (double)th;
-                    acc[SDB_S_ROT2] += (double)t2;
-                    acc[SDB_S_COS] += (double)c;
-                    acc[SDB_S_COS2] += (double)SDB_FSUB(SDB_FMUL(2.0f, SDB_FMUL(c, c)), 1.0f);
-                    acc[SDB_S_ROT4] += (double)SDB_FMUL(t2, t2);
-                    acc[SDB_S_D2R2] += (double)SDB_FMUL(d2, t2);
+                const bool live = j0[g] + e < n;
+                if (do_sums && live) {
+                    const float t2 = th * th;
+                    const float c = sdb_cos_reduced(th);
+                    acc[SDB_S_DISP] += sdb_sqrt_approx(d2);
+                    acc[SDB_S_DISP2] += d2;
+                    acc[SDB_S_DISP4] = fmaf(d2, d2, acc[SDB_S_DISP4]);
+                    acc[SDB_S_ROT] += th;
+                    acc[SDB_S_ROT2] += t2;
+                    acc[SDB_S_COS] += c;
+                    acc[SDB_S_COS2] += fmaf(2.0f * c, c, -1.0f);
+                    acc[SDB_S_ROT4] = fmaf(t2, t2, acc[SDB_S_ROT4]);
+                    acc[SDB_S_D2R2] = fmaf(d2, t2, acc[SDB_S_D2R2]);
                     com_count += d2 < a.p.com_cut_lt;
                 }
-                // Relaxations.add, relaxations.py:152-162 with MolecularRelaxation.add :209-218 and
-                // LastMolecularRelaxation.add :238-289
-                uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
-                if (live) {
-#pragma unroll
-                    for (int t = 0; t < SDB_MAX_TRACKERS; ++t) {
-                        if (t >= a.p.n_trackers) break;
-                        const SdbTracker tr = a.p.trackers[t];
-                        const float val = tr.is_rotation ? th : d2;
-                        uint32_t* st_word = sbase + (long)t * stride + j;
-                        if (is_new) *st_word = SDB_NO_STATUS;
-                        if (!tr.is_last) {
-                            if (val >= tr.cut_gt) {
-                                const bool fired = (fl >> tr.bit) & 1u;
-                                if (!fired || (literal && *st_word > org.timediff)) *st_word = org.timediff;
-                                fl |= 1u << tr.bit;
-                            }
-                        } else {
-                            uint32_t s = (fl >> tr.bit) & 3u;
-                            if (s == 0 && val >= tr.cut_gt) {
-                                s = 1;
-                                *st_word = org.timediff;
-                            } else if (s == 1 && val < tr.cut_lt) {
-                                s = 0;
-                            }
-                            if (s == 1 && val >= tr.cut_irr) s = 2;
-                            fl = (fl & ~(3u << tr.bit)) | (s << tr.bit);
-                        }
+                if (track && live) {
+                    const uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
+                    const bool quiet = (d2 < min_cut_d2 && th < min_cut_th && (fl & state1_bits) == 0u) ||
+                                       (fl == done_pattern && !literal);
+                    if (!quiet) {
+                        const uint32_t fl_new =
+                            sdb_track(a.p, fl, d2, th, sbase + j0[g] + e, stride, org.timediff, literal);
+                        fl4_new = (fl4_new & ~(0xffu << (8 * e))) | (fl_new << (8 * e));
                     }
                 }
-                fl4_new |= fl << (8 * e);
             }
             sdb_st_stream4(dbase + j0[g], make_float4(ddx[0], ddx[1], ddx[2], ddx[3]));
             sdb_st_stream4(dbase + stride + j0[g], make_float4(ddy[0], ddy[1], ddy[2], ddy[3]));
             sdb_st_stream4(dbase + 2 * stride + j0[g], make_float4(ddt[0], ddt[1], ddt[2], ddt[3]));
-            if (a.p.n_trackers && (is_new || fl4_new != fl4))
-                *reinterpret_cast<uint32_t*>(fbase + j0[g]) = fl4_new;
+            if (track && fl4_new != fl4) *reinterpret_cast<uint32_t*>(fbase + j0[g]) = fl4_new;
         }
 
-        if (a.p.do_sums) {
-            // warp reduction of the 10 fp64 sums through shared memory: lane (v, third) adds every
-            // third entry of row v, two shuffles combine the thirds.
+        if (do_sums) {
+            // Per-lane f32 partials (8 molecules) -> fp64 across the warp through shared memory:
+            // lane (v, third) adds every third entry of row v, two shuffles combine the thirds.
             __syncwarp();
 #pragma unroll
             for (int v = 0; v < SDB_NFSUM; ++v) red[warp][v][lane] = acc[v];
@@ -248,12 +335,11 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS) dyn_step_kernel(const StepA
 #pragma unroll
                 for (int i = 0; i < 11; ++i) {
                     const int idx = third + 3 * i;
-                    if (idx < 32) s += red[warp][v][idx];
+                    if (idx < 32) s += (double)red[warp][v][idx];
                 }
             }
             s += __shfl_down_sync(0xffffffffu, s, SDB_NFSUM) + __shfl_down_sync(0xffffffffu, s, 2 * SDB_NFSUM);
             const int com_warp = __reduce_add_sync(0xffffffffu, com_count);
-            double* out = a.partials + ((long)o * a.n_parts + part) * SDB_NSUM;
             if (lane < SDB_NFSUM) {
                 out[lane] = s;
             } else if (lane == SDB_NFSUM) {

@@ -8,8 +8,8 @@
 // mode 1 is the physical definition: every molecule's own sites rotated in-plane by its own angle
 // and translated by its own displacement.
 //
-// One thread per (origin, molecule j): one sincos of dtheta_j/2 (f32, like numpy on an f32 array),
-// then n_sites rows in f64 in the operation order of rowan.rotate (oracle/rowan_shim.py).
+// One thread per (origin, molecule j); every row is decided by an f32 filter unless it lies within a
+// safety margin of the cutoff, in which case the exact f64 sequence of rowan.rotate is evaluated.
 #include "sdb_internal.cuh"
 
 namespace {
@@ -25,43 +25,115 @@ struct StructArgs {
     float sx[8], sy[8];
 };
 
+// Exact reference row (f64, operation order of rowan.rotate; see oracle/rowan_shim.py).
+__device__ __noinline__ bool struct_row_exact(float theta, double tx, double ty, double vx, double vy, double cut2)
+{
+    // rowan.from_axis_angle: half angle, cos and sin in f32; basis axis in f64
+    const float half = theta / 2.0f;
+    const double c = (double)cosf(half), s = (double)sinf(half);
+    // inner = (0, v) (x) conj(q) = (vx s, c vx, c vy, vy s) ; outer = q (x) inner
+    const double iw = __dmul_rn(vx, s), ix = __dmul_rn(c, vx), iy = __dmul_rn(c, vy), iz = __dmul_rn(vy, s);
+    const double rx = __dadd_rn(__dmul_rn(c, ix), __dmul_rn(iw, s));
+    const double ry = __dadd_rn(__dmul_rn(c, iy), -__dmul_rn(s, iz));
+    const double rz = __dadd_rn(__dmul_rn(c, iz), __dmul_rn(s, iy));
+    const double ex = __dadd_rn(__dadd_rn(rx, tx), -vx);
+    const double ey = __dadd_rn(__dadd_rn(ry, ty), -vy);
+    const double ss = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(rz, rz));
+    return ss < cut2;
+}
+
+// 2 (1 - cos x) = 4 sin^2(x/2) with ~1e-7 absolute error (Cody-Waite reduction + odd polynomial);
+// only used by the f32 filter below, whose margin is two orders of magnitude wider.
+__device__ __forceinline__ float two_one_minus_cos(float x)
+{
+    if (fabsf(x) > 8192.0f) {
+        const float sh = sinf(0.5f * x);
+        return 4.0f * sh * sh;
+    }
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.28125f, x);
+    r = fmaf(-k, 1.9353071795864769e-3f, r);
+    const float h = 0.5f * r, h2 = h * h;
+    float p = fmaf(h2, 1.6059043836821613e-10f, -2.5052108385441720e-8f);
+    p = fmaf(h2, p, 2.7557319223985893e-6f);
+    p = fmaf(h2, p, -1.9841269841269841e-4f);
+    p = fmaf(h2, p, 8.3333333333333332e-3f);
+    p = fmaf(h2, p, -1.6666666666666666e-1f);
+    const float sn = fmaf(h * h2, p, h);
+    return 4.0f * sn * sn;
+}
+
+// mode 0.  A site (vx, vy, 0) rotated about x by theta and translated by t moves by
+//   e = (tx, ty - vy (1 - cos theta), vy sin theta)  =>  |e|^2 = |t|^2 + 2 (1 - cos theta) vy (vy - ty)
+// up to terms of relative size 1e-7 (f32 cos/sin of the half angle are not exactly normalised).
+// This f32 value decides every row that is not within a safety margin of the cutoff; the rows
+// inside the margin (about one in 1e5) are decided by the exact f64 sequence above, so the count is
+// identical to evaluating every row exactly.
+//
+// Each thread owns 4 consecutive rotation molecules j0..j0+3 (one float4 of dtheta).  Row
+// i = site * n + j pairs with translation molecule i / n_sites: for 4 consecutive rows that is at
+// most two consecutive molecules, fetched once per site.
+template <int NSITES>
 __global__ void __launch_bounds__(256) struct_kernel(const StructArgs a)
 {
     const int o = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const float* d = a.origins[o].d_delta;
+    const unsigned n = (unsigned)a.n;
+    const unsigned n_sites = NSITES > 0 ? (unsigned)NSITES : (unsigned)a.n_sites;
+    const float cut = (float)a.cut2;
     int count = 0;
-    if (j < a.n) {
-        const float theta = d[2 * a.stride + j];
+    for (unsigned j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; j0 < n; j0 += gridDim.x * blockDim.x * 4u) {
+        const float4 t4 = sdb_ldg4(d + 2 * a.stride + j0);
+        const float theta[4] = {t4.x, t4.y, t4.z, t4.w};
         if (a.mode == 0) {
-            // rowan.from_axis_angle: half angle, cos and sin in f32; basis axis in f64
-            const float half = theta / 2.0f;
-            const double c = (double)cosf(half), s = (double)sinf(half);
-            for (int site = 0; site < a.n_sites; ++site) {
-                const long row = (long)site * a.n + j;
-                const long m = row / a.n_sites;
-                const double tx = (double)d[m], ty = (double)d[a.stride + m];
-                const double vx = (double)a.sx[site], vy = (double)a.sy[site];
-                // inner = (0, v) (x) conj(q) = (vx s, c vx, c vy, vy s) ; outer = q (x) inner
-                const double iw = __dmul_rn(vx, s), ix = __dmul_rn(c, vx), iy = __dmul_rn(c, vy), iz = __dmul_rn(vy, s);
-                const double rx = __dadd_rn(__dmul_rn(c, ix), __dmul_rn(iw, s));
-                const double ry = __dadd_rn(__dmul_rn(c, iy), -__dmul_rn(s, iz));
-                const double rz = __dadd_rn(__dmul_rn(c, iz), __dmul_rn(s, iy));
-                const double ex = __dadd_rn(__dadd_rn(rx, tx), -vx);
-                const double ey = __dadd_rn(__dadd_rn(ry, ty), -vy);
-                const double ss = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(rz, rz));
-                count += ss < a.cut2;
+            float g[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) g[e] = two_one_minus_cos(theta[e]);
+#pragma unroll
+            for (int site = 0; site < (NSITES > 0 ? NSITES : 8); ++site) {
+                if (site >= (int)n_sites) break;
+                const unsigned row0 = (unsigned)site * n + j0;  // host guarantees n * n_sites < 2^32
+                const unsigned m0 = row0 / n_sites, r0 = row0 - m0 * n_sites;
+                const unsigned m1 = min(m0 + 1u, n - 1u);
+                const float tx0 = __ldg(d + m0), ty0 = __ldg(d + a.stride + m0);
+                const float tx1 = __ldg(d + m1), ty1 = __ldg(d + a.stride + m1);
+                const float vx = a.sx[site], vy = a.sy[site];
+                const float vmargin = 1.0f + 8.0f * vy * vy;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float tx, ty;
+                    if (NSITES >= 3) {
+                        const bool second = r0 + (unsigned)e >= n_sites;  // (r0 + e) / n_sites is 0 or 1
+                        tx = second ? tx1 : tx0;
+                        ty = second ? ty1 : ty0;
+                    } else {  // generic site count: one lookup per row
+                        const unsigned m = min((row0 + (unsigned)e) / n_sites, n - 1u);
+                        tx = __ldg(d + m);
+                        ty = __ldg(d + a.stride + m);
+                    }
+                    const float t2 = fmaf(tx, tx, ty * ty);
+                    const float e2 = fmaf(g[e], vy * (vy - ty), t2);
+                    const float margin = 8e-6f * (t2 + vmargin);
+                    bool inside = e2 < cut;
+                    if (!(fabsf(e2 - cut) > margin))
+                        inside = struct_row_exact(theta[e], (double)tx, (double)ty, (double)vx, (double)vy, a.cut2);
+                    count += inside && (j0 + (unsigned)e < n);
+                }
             }
         } else {
-            float sn, cs;
-            sincosf(theta, &sn, &cs);
-            const double c = cs, s = sn;
-            const double tx = (double)d[j], ty = (double)d[a.stride + j];
-            for (int site = 0; site < a.n_sites; ++site) {
-                const double vx = (double)a.sx[site], vy = (double)a.sy[site];
-                const double ex = (c * vx - s * vy) + tx - vx;
-                const double ey = (s * vx + c * vy) + ty - vy;
-                count += (ex * ex + ey * ey) < a.cut2;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (j0 + (unsigned)e >= n) break;
+                float sn, cs;
+                sincosf(theta[e], &sn, &cs);
+                const double c = cs, s = sn;
+                const double tx = (double)d[j0 + e], ty = (double)d[a.stride + j0 + e];
+                for (int site = 0; site < (int)n_sites; ++site) {
+                    const double vx = (double)a.sx[site], vy = (double)a.sy[site];
+                    const double ex = (c * vx - s * vy) + tx - vx;
+                    const double ey = (s * vx + c * vy) + ty - vy;
+                    count += (ex * ex + ey * ey) < a.cut2;
+                }
             }
         }
     }
@@ -83,7 +155,8 @@ extern "C" int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t
                           const float* h_sites_xy, int32_t n_sites, double dist, int32_t mode, double* d_sums,
                           void* stream)
 {
-    if (!d_origins || !h_sites_xy || !d_sums || n <= 0 || n_sites <= 0 || n_sites > 8 || mode < 0 || mode > 1) {
+    if (!d_origins || !h_sites_xy || !d_sums || n <= 0 || n_sites <= 0 || n_sites > 8 || mode < 0 || mode > 1 ||
+        (long long)n * n_sites >= 0xffffffffLL) {
         sdb_set_error("sdb_struct: bad argument");
         return SDB_EINVAL;
     }
@@ -109,8 +182,12 @@ extern "C" int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t
                                               (size_t)n_origins, s),
                             "sdb_struct: clear");
     if (rc) return rc;
-    dim3 grid((n + 255) / 256, n_origins);
-    struct_kernel<<<grid, 256, 0, s>>>(a);
+    const int tiles = (n + 1023) / 1024;
+    dim3 grid(tiles < 48 ? tiles : 48, n_origins);
+    if (n_sites == 3)
+        struct_kernel<3><<<grid, 256, 0, s>>>(a);
+    else
+        struct_kernel<0><<<grid, 256, 0, s>>>(a);
     SDB_CHECK_LAUNCH("struct_kernel");
     return SDB_OK;
 }

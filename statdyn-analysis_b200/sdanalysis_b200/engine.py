@@ -316,6 +316,9 @@ class DynamicsEngine:
         self._frame_ring = None
         self._dev_frames = None
         self._frame_i = 0
+        self._staged_slot = None
+        self.h2d_bytes = self.d2h_bytes = 0
+        self.profile = None  # set to a list to collect (name, start_event, end_event) per kernel group
         self._sites_c = None if self.mol_sites is None else _lib.float_array(self.mol_sites.reshape(-1))
         self.frames_seen = 0
         self.updates = 0  # molecule x origin updates performed
@@ -341,7 +344,12 @@ class DynamicsEngine:
             self._ov_scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
     def _stage_frame(self, position, orientation):
-        """Return device tensors (pos (N,3) f32, quat (N,4) f32 or None) for host or device input."""
+        """Return device tensors (pos (N,3) f32, quat (N,4) f32 or None).
+
+        Device tensors are used in place.  Host input (numpy arrays or CPU tensors) is copied to a
+        ring of device frame buffers on a dedicated copy stream, so the upload of frame t+1 overlaps
+        the kernels of frame t; numpy arrays first go through a ring of pinned staging buffers, pinned
+        CPU tensors are uploaded directly."""
         torch = self.torch
         if isinstance(position, torch.Tensor) and position.is_cuda:
             pos = position
@@ -354,35 +362,59 @@ class DynamicsEngine:
                 pos = pos.clone()
             if quat is not None and quat.data_ptr() % 16:
                 quat = quat.clone()
+            self.h2d_bytes = 0
             return pos, quat
-        position = np.asarray(position)
-        if position.shape != (self.n, 3):
-            raise RuntimeError(f"position has shape {position.shape}, expected {(self.n, 3)}")
-        if orientation is not None:
-            orientation = np.asarray(orientation)
-            if orientation.shape != (self.n, 4):
-                raise RuntimeError(f"orientation has shape {orientation.shape}, expected {(self.n, 4)}")
-        qoff = (3 * self.n + 3) // 4 * 4  # quaternions start 16-byte aligned (float4 loads)
-        if self._frame_ring is None:
-            self._frame_ring = _Ring(
-                torch, self._ring_depth, lambda: torch.zeros(qoff + 4 * self.n, dtype=torch.float32).pin_memory()
-            )
+        n = self.n
+        qoff = (3 * n + 3) // 4 * 4  # quaternions start 16-byte aligned (float4 loads)
+        if self._dev_frames is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
             self._dev_frames = [
-                torch.empty(qoff + 4 * self.n, dtype=torch.float32, device=self.device) for _ in range(self._ring_depth)
+                torch.empty(qoff + 4 * n, dtype=torch.float32, device=self.device) for _ in range(self._ring_depth)
             ]
-        i, pinned = self._frame_ring.acquire()
-        host = pinned.numpy()
-        np.copyto(host[: 3 * self.n].reshape(self.n, 3), position, casting="same_kind")
-        nfl = 3 * self.n
-        if orientation is not None:
-            np.copyto(host[qoff : qoff + 4 * self.n].reshape(self.n, 4), orientation, casting="same_kind")
-            nfl = qoff + 4 * self.n
-        dev = self._dev_frames[i]
-        dev[:nfl].copy_(pinned[:nfl], non_blocking=True)
-        self._frame_ring.release(i)
-        self.h2d_bytes = 4 * (7 * self.n if orientation is not None else 3 * self.n)
-        pos = dev[: 3 * self.n].view(self.n, 3)
-        quat = dev[qoff : qoff + 4 * self.n].view(self.n, 4) if orientation is not None else None
+            self._dev_consumed = [None] * self._ring_depth
+        if isinstance(position, torch.Tensor):
+            if tuple(position.shape) != (n, 3) or (orientation is not None and tuple(orientation.shape) != (n, 4)):
+                raise RuntimeError("frame tensors must have shapes (N,3) and (N,4)")
+            src_pos, src_quat, ring_i = position, orientation, None
+        else:
+            position = np.asarray(position)
+            if position.shape != (n, 3):
+                raise RuntimeError(f"position has shape {position.shape}, expected {(n, 3)}")
+            if orientation is not None:
+                orientation = np.asarray(orientation)
+                if orientation.shape != (n, 4):
+                    raise RuntimeError(f"orientation has shape {orientation.shape}, expected {(n, 4)}")
+            if self._frame_ring is None:
+                self._frame_ring = _Ring(
+                    torch, self._ring_depth, lambda: torch.zeros(qoff + 4 * n, dtype=torch.float32).pin_memory()
+                )
+            ring_i, pinned = self._frame_ring.acquire()
+            host = pinned.numpy()
+            np.copyto(host[: 3 * n].reshape(n, 3), position, casting="same_kind")
+            src_pos = pinned[: 3 * n].view(n, 3)
+            src_quat = None
+            if orientation is not None:
+                np.copyto(host[qoff : qoff + 4 * n].reshape(n, 4), orientation, casting="same_kind")
+                src_quat = pinned[qoff : qoff + 4 * n].view(n, 4)
+        self._frame_i = (self._frame_i + 1) % self._ring_depth
+        dev = self._dev_frames[self._frame_i]
+        pos = dev[: 3 * n].view(n, 3)
+        quat = dev[qoff : qoff + 4 * n].view(n, 4) if src_quat is not None else None
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            consumed = self._dev_consumed[self._frame_i]
+            if consumed is not None:
+                self._copy_stream.wait_event(consumed)  # kernels that read this buffer are done
+            pos.copy_(src_pos, non_blocking=True)
+            if quat is not None:
+                quat.copy_(src_quat, non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(self._copy_stream)
+        if ring_i is not None:
+            self._frame_ring.events[ring_i] = uploaded
+        main.wait_event(uploaded)
+        self._staged_slot = self._frame_i
+        self.h2d_bytes = 4 * (7 * n if src_quat is not None else 3 * n)
         return pos, quat
 
     def _new_pool_frame(self):
@@ -432,7 +464,7 @@ class DynamicsEngine:
         self._release(org.prev)
 
     # ------------------------------------------------------------------------------------------
-    def step(self, timestep, position, orientation, active, *, zero_step=False, want_sums=None, chunk=None):
+    def step(self, timestep, position, orientation, active, *, zero_step=False, want_sums=None, chunk=None, to_host=True):
         """Advance every origin in ``active`` (iterable of hashable keys) with one frame.
 
         Unknown keys are created at this frame (``Dynamics.from_frame`` + first ``compute_all``,
@@ -447,6 +479,7 @@ class DynamicsEngine:
         do_sums = self.compute_sums if want_sums is None else bool(want_sums)
 
         with torch.cuda.device(self.device):
+            self._staged_slot = None
             if zero_step:
                 pos = quat = None
             else:
@@ -533,6 +566,10 @@ class DynamicsEngine:
             stream = _lib.stream_ptr(self.device)
             params = self.params
             params.do_sums = int(do_sums)
+            prof = self.profile
+            if prof is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
             _lib.check(
                 lib.sdb_dyn_step(
                     params,
@@ -548,6 +585,9 @@ class DynamicsEngine:
                     stream,
                 )
             )
+            if prof is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
             if do_sums and self.compute_struct:
                 _lib.check(
                     lib.sdb_struct(
@@ -555,6 +595,9 @@ class DynamicsEngine:
                         float(self.distance), self.struct_mode, sums_dev.data_ptr(), stream,
                     )
                 )
+            if prof is not None:
+                ev2 = torch.cuda.Event(enable_timing=True)
+                ev2.record()
             if do_sums and self.compute_overlap and self.overlap_k > 0:
                 _lib.check(
                     lib.sdb_overlap(
@@ -562,8 +605,16 @@ class DynamicsEngine:
                         self._ov_scratch.data_ptr(), sums_dev.data_ptr(), stream,
                     )
                 )
+            if prof is not None:
+                ev3 = torch.cuda.Event(enable_timing=True)
+                ev3.record()
+                prof.append((n_active, ev0, ev1, ev2, ev3))
+            if self._staged_slot is not None:
+                consumed = torch.cuda.Event()
+                consumed.record()
+                self._dev_consumed[self._staged_slot] = consumed
             event = None
-            if do_sums:
+            if do_sums and to_host:
                 sums_pinned[:n_active].copy_(sums_dev[:n_active], non_blocking=True)
                 event = self._sums_ring.release(si)
                 self.d2h_bytes = n_active * SDB_NSUM * 8
@@ -581,6 +632,9 @@ class DynamicsEngine:
                 self.updates += n_active * self.n
 
         keys = [org.key for org in ordered]
+        if not to_host:
+            # device-resident result (multi-GPU gather path): valid until ring_depth further steps
+            return keys, timediffs, (sums_dev[:n_active] if do_sums else None)
         sums_host = sums_pinned.numpy()[:n_active] if do_sums else None
         return StepResult(self, keys, timediffs, sums_host, event)
 
