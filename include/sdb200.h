@@ -48,9 +48,9 @@ enum {
     SDB_S_OVERLAP = 11,/* |top-k(|dr|) & top-k(|dtheta|)| (written by sdb_overlap_*) */
     SDB_S_BADQUAT = 12,/* count of quaternion quotients that are not unit (rowan raises ValueError)
                           or not planar (x or y != 0) */
-    SDB_S_SPARE0 = 13,
-    SDB_S_SPARE1 = 14,
-    SDB_S_SPARE2 = 15
+    SDB_S_OV_RABOVE = 13, /* overlap bookkeeping: |dr|^2 keys above the sampled bracket       */
+    SDB_S_OV_TABOVE = 14, /*                      |dtheta| keys above the sampled bracket     */
+    SDB_S_OV_BOTH = 15    /*                      molecules above both brackets               */
 };
 
 /* One first/last-passage tracker (relaxations.py:187-294,308-335), thresholds pre-digested by the
@@ -122,11 +122,13 @@ typedef struct {
  *   d_origins / d_segments  device copies of the descriptor arrays (n_origins / n_segments entries)
  *   d_partials double[n_origins][sdb_dyn_num_parts(n)][SDB_NSUM] scratch
  *   d_sums  double[n_origins][SDB_NSUM] out, filled by the finalize kernel launched by this call
+ *   d_ov_ws workspace of the bracketed `overlap` selection prepared by sdb_overlap_prepare for the
+ *           same descriptors (NULL: no overlap bookkeeping), sized for ov_ws_origins origins
  */
 int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
                  float* d_cur_compact, const SdbOrigin* d_origins, int32_t n_origins,
                  const SdbSegment* d_segments, int32_t n_segments, double* d_partials,
-                 double* d_sums, void* stream);
+                 double* d_sums, void* d_ov_ws, int32_t ov_ws_origins, void* stream);
 /* |dr| and |dtheta| of every molecule of one origin (compute_displacement / compute_rotation,
  * dynamics.py:179-181,217-219): d_disp, d_rot float[n] (either may be NULL). */
 int sdb_dyn_norms(const float* d_delta, int32_t n, int32_t stride, float* d_disp, float* d_rot,
@@ -149,11 +151,26 @@ int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t
                void* stream);
 
 /* ---- `overlap` (dynamics.py:431-445) -----------------------------------------------------------
- * Exact: the k largest |dr| and |dtheta| per origin (ties by larger molecule index first),
- * intersection count into d_sums[o][SDB_S_OVERLAP].
- * key_mode 0: keys are computed from the (dx, dy, dtheta) planes of each origin's d_delta exactly as the reference
- * computes compute_displacement() / compute_rotation(); key_mode 1: plane 0 holds non-negative
- * displacement keys and plane 2 rotation keys (abs applied) -- mobile_overlap() on caller arrays.
+ * k largest |dr| and k largest |dtheta| per origin, intersection count into
+ * d_sums[o][SDB_S_OVERLAP].  Exact; among equal keys the larger molecule indices win.
+ *
+ * Fused path, three calls per frame around sdb_dyn_step with the same descriptor arrays:
+ *   sdb_overlap_prepare  samples the updated keys of every origin and brackets the k-th largest;
+ *   sdb_dyn_step         (given d_ov_ws) counts keys above the brackets and lists the candidates;
+ *   sdb_overlap_resolve  finds the exact thresholds among the candidates and counts the overlap;
+ *                        origins whose bracket failed are redone by the exact kernel below.
+ * d_ws: sdb_overlap_ws_bytes(ws_origins, n) bytes, ws_origins >= n_origins. */
+size_t sdb_overlap_ws_bytes(int32_t max_origins, int32_t n);
+int sdb_overlap_prepare(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
+                        const SdbOrigin* d_origins, int32_t n_origins, const SdbSegment* d_segments,
+                        int32_t n_segments, int32_t max_segment_count, int32_t k, void* d_ws,
+                        int32_t ws_origins, void* stream);
+int sdb_overlap_resolve(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride,
+                        int32_t k, void* d_ws, int32_t ws_origins, double* d_sums, void* stream);
+/* Stand-alone exact selection over the whole arrays (radix select, cooperative kernel).
+ * key_mode 0: keys are computed from the (dx, dy, dtheta) planes of each origin's d_delta
+ * (|dr|^2 and |dtheta|); key_mode 1: plane 0 holds non-negative displacement keys and plane 2
+ * rotation keys (abs applied) -- mobile_overlap() on caller arrays.
  * d_scratch: sdb_overlap_scratch_bytes(n_origins, n) bytes. */
 int sdb_overlap(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride,
                 int32_t key_mode, int32_t k, void* d_scratch, double* d_sums, void* stream);

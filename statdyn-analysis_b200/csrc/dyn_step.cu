@@ -26,9 +26,10 @@ struct StepArgs {
     double* partials;    // double[n_origins][n_parts][SDB_NSUM]
     const double (*atan_tab)[2];
     int n_parts;
+    int ov_on;  // bracketed overlap selection: count keys above the brackets, collect candidates
+    SdbOvWorkspace ov;
 };
 
-constexpr int NM = SDB_LANE_MOLS * SDB_GROUPS;  // molecules per lane
 
 // cos(x) for x >= 0 with ~1e-7 absolute error: two-constant Cody-Waite reduction to [-pi, pi], then
 // cos r = 1 - 2 sin^2(r/2) with an odd polynomial for sin on [-pi/2, pi/2].  Used for the rot1/rot2
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
     __shared__ __align__(16) float s_wx[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
     __shared__ __align__(16) float s_wy[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
     __shared__ __align__(16) double s_al[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
+    __shared__ uint32_t s_cand[SDB_BLOCK_WARPS][3][SDB_OV_STAGE];  // staged overlap candidates (idx, d2, |dtheta|)
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -250,7 +252,8 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
                 if (lane == SDB_S_COS || lane == SDB_S_COS2) v = (double)live_warp;
                 if (lane == SDB_S_COMSTRUCT && a.p.com_cut_lt > 0.f) v = (double)live_warp;
                 if (lane == SDB_S_BADQUAT) v = (double)bad_warp;
-                if (lane < SDB_NFSUM || lane == SDB_S_COMSTRUCT || lane == SDB_S_BADQUAT) out[lane] = v;
+                if (lane < SDB_NFSUM || lane == SDB_S_COMSTRUCT || lane == SDB_S_BADQUAT || lane >= SDB_S_OV_RABOVE)
+                    out[lane] = v;
             }
             continue;
         }
@@ -260,15 +263,24 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
 #pragma unroll
         for (int v = 0; v < SDB_NFSUM; ++v) acc[v] = 0.f;
         int com_count = 0;
+        // overlap: keys above the bracket of each array, and molecules inside a bracket (candidates)
+        const bool ov = a.ov_on && do_sums;
+        float4 br = make_float4(0.f, INFINITY, 0.f, INFINITY);  // lo_r, hi_r, lo_t, hi_t
+        if (ov) br = __ldg(reinterpret_cast<const float4*>(a.ov.brackets) + o);
+        int n_ar = 0, n_at = 0, n_both = 0, n_cand = 0;
+        const uint32_t lanemask_lt = (1u << lane) - 1u;
 
 #pragma unroll
         for (int g = 0; g < SDB_GROUPS; ++g) {
-            if (j0[g] >= n) continue;
-            const float4 dx = sdb_ld_stream4(dbase + j0[g]);
-            const float4 dy = sdb_ld_stream4(dbase + stride + j0[g]);
-            const float4 dt = sdb_ld_stream4(dbase + 2 * stride + j0[g]);
+            const bool valid = j0[g] < n;  // only the last warp tile has invalid groups
+            float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), dy = dx, dt = dx;
             uint32_t fl4 = 0;
-            if (track) fl4 = __ldcs(reinterpret_cast<const uint32_t*>(fbase + j0[g]));
+            if (valid) {
+                dx = sdb_ld_stream4(dbase + j0[g]);
+                dy = sdb_ld_stream4(dbase + stride + j0[g]);
+                dt = sdb_ld_stream4(dbase + 2 * stride + j0[g]);
+                if (track) fl4 = __ldcs(reinterpret_cast<const uint32_t*>(fbase + j0[g]));
+            }
             float ddx[4] = {dx.x, dx.y, dx.z, dx.w};
             float ddy[4] = {dy.x, dy.y, dy.z, dy.w};
             float ddt[4] = {dt.x, dt.y, dt.z, dt.w};
@@ -283,13 +295,8 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
             uint32_t fl4_new = fl4;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                // TrackedMotion.add, _util.py:149-153
-                ddx[e] = SDB_FSUB(ddx[e], wx[e]);
-                ddy[e] = SDB_FSUB(ddy[e], wy[e]);
-                ddt[e] = (float)((double)ddt[e] + alpha[e]);
-                // np.square(delta).sum(axis=1) in f32, one rounding per operation
-                const float d2 = SDB_FADD(SDB_FMUL(ddx[e], ddx[e]), SDB_FMUL(ddy[e], ddy[e]));
-                const float th = fabsf(ddt[e]);
+                float d2, th;
+                sdb_apply_increment(ddx[e], ddy[e], ddt[e], wx[e], wy[e], alpha[e], d2, th);
                 const bool live = j0[g] + e < n;
                 if (do_sums && live) {
                     const float t2 = th * th;
@@ -305,6 +312,23 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
                     acc[SDB_S_D2R2] = fmaf(d2, t2, acc[SDB_S_D2R2]);
                     com_count += d2 < a.p.com_cut_lt;
                 }
+                if (ov) {  // warp-uniform
+                    const bool ar = live && d2 > br.y, at = live && th > br.w;
+                    n_ar += ar;
+                    n_at += at;
+                    n_both += ar && at;
+                    const bool is_cand = live && ((d2 >= br.x && !ar) || (th >= br.z && !at));
+                    const unsigned m = __ballot_sync(0xffffffffu, is_cand);
+                    if (m) {
+                        const int slot = n_cand + __popc(m & lanemask_lt);
+                        if (is_cand && slot < SDB_OV_STAGE) {
+                            s_cand[warp][0][slot] = (uint32_t)(j0[g] + e);
+                            s_cand[warp][1][slot] = __float_as_uint(d2);
+                            s_cand[warp][2][slot] = __float_as_uint(th);
+                        }
+                        n_cand += __popc(m);
+                    }
+                }
                 if (track && live) {
                     const uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
                     const bool quiet = (d2 < min_cut_d2 && th < min_cut_th && (fl & state1_bits) == 0u) ||
@@ -316,10 +340,35 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
                     }
                 }
             }
-            sdb_st_stream4(dbase + j0[g], make_float4(ddx[0], ddx[1], ddx[2], ddx[3]));
-            sdb_st_stream4(dbase + stride + j0[g], make_float4(ddy[0], ddy[1], ddy[2], ddy[3]));
-            sdb_st_stream4(dbase + 2 * stride + j0[g], make_float4(ddt[0], ddt[1], ddt[2], ddt[3]));
-            if (track && fl4_new != fl4) *reinterpret_cast<uint32_t*>(fbase + j0[g]) = fl4_new;
+            if (valid) {
+                sdb_st_stream4(dbase + j0[g], make_float4(ddx[0], ddx[1], ddx[2], ddx[3]));
+                sdb_st_stream4(dbase + stride + j0[g], make_float4(ddy[0], ddy[1], ddy[2], ddy[3]));
+                sdb_st_stream4(dbase + 2 * stride + j0[g], make_float4(ddt[0], ddt[1], ddt[2], ddt[3]));
+                if (track && fl4_new != fl4) *reinterpret_cast<uint32_t*>(fbase + j0[g]) = fl4_new;
+            }
+        }
+        if (ov && n_cand > 0) {  // warp-uniform: append the staged candidates to the origin's dense list
+            uint32_t base = 0;
+            const bool fits = n_cand <= SDB_OV_STAGE;
+            if (lane == 0) {
+                if (fits) base = atomicAdd(a.ov.cand_cnt + 2 * o, (uint32_t)n_cand);
+                else a.ov.cand_cnt[2 * o + 1] = 1u;  // staging overflow: this origin takes the exact path
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            __syncwarp();
+            if (fits) {
+                if (base + (uint32_t)n_cand <= (uint32_t)a.ov.cand_cap) {
+                    const long row = (long)o * a.ov.cand_cap + base;
+                    for (int s = lane; s < n_cand; s += 32) {
+                        a.ov.cand_idx[row + s] = s_cand[warp][0][s];
+                        a.ov.cand_r[row + s] = s_cand[warp][1][s];
+                        a.ov.cand_t[row + s] = s_cand[warp][2][s];
+                    }
+                } else if (lane == 0) {
+                    a.ov.cand_cnt[2 * o + 1] = 1u;
+                }
+            }
+            __syncwarp();
         }
 
         if (do_sums) {
@@ -347,13 +396,23 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
             } else if (lane == SDB_NFSUM + 1) {
                 out[SDB_S_BADQUAT] = (double)bad_warp;
             }
+            if (ov) {
+                const int w_ar = __reduce_add_sync(0xffffffffu, n_ar);
+                const int w_at = __reduce_add_sync(0xffffffffu, n_at);
+                const int w_both = __reduce_add_sync(0xffffffffu, n_both);
+                if (lane == 0) {
+                    out[SDB_S_OV_RABOVE] = (double)w_ar;
+                    out[SDB_S_OV_TABOVE] = (double)w_at;
+                    out[SDB_S_OV_BOTH] = (double)w_both;
+                }
+            }
         }
     }
 }
 
 // Sum the per-warp-tile partials of one origin: block = 256 threads = 16 sums x 16 strided readers.
 __global__ void __launch_bounds__(256) dyn_finalize_kernel(const double* __restrict__ partials, int n_parts,
-                                                            double* __restrict__ sums)
+                                                            double* __restrict__ sums, int with_ov)
 {
     __shared__ double sh[16][17];
     const int o = blockIdx.x;
@@ -370,7 +429,8 @@ __global__ void __launch_bounds__(256) dyn_finalize_kernel(const double* __restr
         const int vv = threadIdx.x;
         // the struct / overlap slots are owned by their own kernels; spare slots are zeroed
         if (vv != SDB_S_STRUCT && vv != SDB_S_OVERLAP) {
-            const bool produced = vv < SDB_NFSUM || vv == SDB_S_COMSTRUCT || vv == SDB_S_BADQUAT;
+            const bool produced = vv < SDB_NFSUM || vv == SDB_S_COMSTRUCT || vv == SDB_S_BADQUAT ||
+                                  (with_ov && vv >= SDB_S_OV_RABOVE);
             sums[(long)o * SDB_NSUM + vv] = produced ? t : 0.0;
         }
     }
@@ -422,9 +482,10 @@ extern "C" int32_t sdb_dyn_num_parts(int32_t n) { return (n + SDB_WARP_MOLS - 1)
 
 extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat, float* d_cur_compact,
                             const SdbOrigin* d_origins, int32_t n_origins, const SdbSegment* d_segments,
-                            int32_t n_segments, double* d_partials, double* d_sums, void* stream)
+                            int32_t n_segments, double* d_partials, double* d_sums, void* d_ov_ws,
+                            int32_t ov_ws_origins, void* stream)
 {
-    if (!h_params || !d_origins || !d_segments) {
+    if (!h_params || !d_origins || !d_segments || (d_ov_ws && n_origins > ov_ws_origins)) {
         sdb_set_error("sdb_dyn_step: null argument");
         return SDB_EINVAL;
     }
@@ -449,12 +510,15 @@ extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, co
     a.atan_tab = sdb_device_atan_table();
     a.n_parts = sdb_dyn_num_parts(p.n);
     if (!a.atan_tab) return SDB_ECUDA;
+    a.ov_on = d_ov_ws != nullptr && p.do_sums;
+    if (a.ov_on) sdb_ov_layout(d_ov_ws, ov_ws_origins, p.n, &a.ov);
+    else a.ov = SdbOvWorkspace{};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     dim3 grid((a.n_parts + SDB_BLOCK_WARPS - 1) / SDB_BLOCK_WARPS, n_segments);
     dyn_step_kernel<<<grid, SDB_BLOCK_THREADS, 0, s>>>(a);
     SDB_CHECK_LAUNCH("dyn_step_kernel");
     if (p.do_sums) {
-        dyn_finalize_kernel<<<n_origins, 256, 0, s>>>(d_partials, a.n_parts, d_sums);
+        dyn_finalize_kernel<<<n_origins, 256, 0, s>>>(d_partials, a.n_parts, d_sums, a.ov_on);
         SDB_CHECK_LAUNCH("dyn_finalize_kernel");
     }
     return SDB_OK;

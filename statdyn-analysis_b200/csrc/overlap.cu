@@ -1,288 +1,720 @@
-// overlap.cu -- exact `overlap` of Dynamics.compute_all (reference dynamics/dynamics.py:380-382,431-445):
+// overlap.cu -- `overlap` of Dynamics.compute_all (reference dynamics/dynamics.py:380-382,431-445):
 //   k = int(N * 0.1); |argsort(|dr|)[-k:]  intersect  argsort(|dtheta|)[-k:]| / k
 //
-// Exact selection of the k largest keys of two f32 arrays per origin without sorting: a three-digit
-// (11 + 11 + 9 bit) most-significant-digit radix select on the f32 bit patterns of the non-negative
-// keys finds the k-th largest value t; members of the top-k set are the keys > t plus, of the keys
-// == t, the ones with the largest molecule indices (numpy's introsort leaves the choice among equal
-// keys unspecified -- parity trap T4 -- this is our deterministic rule; for all-equal arrays it
-// gives identical sets for both arrays, hence overlap = 1 like the reference).
-// Keys are exactly the reference's: |dr| = fl32(sqrt(fl32(dx^2 + dy^2))), |dtheta| = |dth|.
+// The reference sorts both arrays completely for every (frame, origin).  Here the k-th largest value
+// of each array is found exactly without sorting and without an extra pass over the state:
+//
+//   1. sample   a strided sample (~16k molecules) of the *updated* keys of every active origin is
+//               computed from the old state and the frame increments (same arithmetic as the fused
+//               kernel, so the keys are bit-identical);
+//   2. bracket  one block per (origin, array) selects two order statistics of the sample that enclose
+//               the k-th largest of the full array with probability 1 - 1e-9: the bracket [lo, hi];
+//   3. fused    dyn_step_kernel (dyn_step.cu) counts the keys above hi and appends the ~3 % of
+//               molecules inside a bracket to a per-warp-tile candidate list;
+//   4. resolve  one block per origin selects the exact threshold among the candidates (radix select
+//               on the key offset from lo), breaks ties by molecule index, counts the intersection;
+//   5. exact    origins whose bracket failed (all keys equal, overflow, 1e-9 events) are redone by a
+//               cooperative kernel that radix-selects over the whole array (3 digits of the f32 bit
+//               pattern).  The same kernel serves mobile_overlap() on caller-provided arrays.
+//
+// Keys: translation d2 = |dr|^2 = fl32(dx^2 + dy^2) -- monotone in the reference's |dr| = sqrt(d2) --
+// and rotation |dtheta|.  Members of a top-k set are the keys above the threshold plus, among keys
+// equal to it, those with the largest molecule indices (numpy's introsort leaves the choice among
+// equal keys unspecified -- parity trap T4; for all-equal arrays this rule gives identical sets for
+// both arrays, i.e. overlap = 1, like the reference).
+#include <cooperative_groups.h>
+
 #include "sdb_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int OV_BINS = 2048;
-constexpr int OV_SEL = 8;  // words per (origin, array) selection record
+constexpr int OV_SEL = 8;  // words per (array) selection record of the exact kernel
 enum { SEL_PREFIX = 0, SEL_REMAINING = 1, SEL_COUNT_EQ = 2, SEL_IDXCUT = 3, SEL_NEED_TIE = 4 };
-constexpr int OV_THREADS = 256;
-constexpr int OV_ITERS = 4;
-constexpr int OV_BLOCK_MOLS = OV_THREADS * 4 * OV_ITERS;  // 4096
 
-struct OvArgs {
+// =================================================================================================
+// 1. sample
+// =================================================================================================
+struct SampleArgs {
+    SdbDynParams p;
+    const float* pos;
+    const float* quat;
     const SdbOrigin* origins;
-    uint32_t* scratch;
+    const SdbSegment* segments;
+    const double (*atan_tab)[2];
+    SdbOvWorkspace w;
+};
+
+// The sample consists of groups of 4 consecutive molecules (one 16-byte vector per state plane),
+// group g covering molecules 4 g stride .. 4 g stride + 3; sample slot i = 4 g + e.
+// Stage 1, grid = (group tiles, segments): frame increments (wx, wy, alpha) of the sampled
+// molecules, once per segment.
+__global__ void __launch_bounds__(128) ov_increment_kernel(const SampleArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.w.n_samples) return;
+    const SdbSegment seg = a.segments[blockIdx.y];
+    const long j = (long)(i >> 2) * 4 * a.w.sample_stride + (i & 3);
+    const long stride = a.p.stride;
+    const bool zero_step = (seg.flags & SDB_SEG_ZERO_STEP) != 0 || a.pos == nullptr;
+    float wx = 0.f, wy = 0.f;
+    double alpha = 0.0;
+    if (!zero_step && j < a.p.n) {
+        const float cx = __ldg(a.pos + 3 * j), cy = __ldg(a.pos + 3 * j + 1);
+        float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (a.quat) q = sdb_ldg4(a.quat + 4 * j);
+        float px = cx, py = cy, pw = q.x, pz = q.w;
+        const float* prev = static_cast<const float*>(seg.d_prev);
+        if (prev) {
+            px = __ldg(prev + j);
+            py = __ldg(prev + stride + j);
+            pw = __ldg(prev + 2 * stride + j);
+            pz = __ldg(prev + 3 * stride + j);
+        }
+        sdb_wrap2d(a.p.lx, a.p.ly, a.p.xy, SDB_FSUB(px, cx), SDB_FSUB(py, cy), wx, wy);
+        if ((seg.flags & SDB_SEG_NO_ROTATION) == 0) {
+            int bad;
+            alpha = sdb_rot_increment(q.x, q.w, pw, pz, a.atan_tab, bad);
+        }
+    }
+    float4 out;
+    out.x = wx;
+    out.y = wy;
+    out.z = __int_as_float(__double2loint(alpha));
+    out.w = __int_as_float(__double2hiint(alpha));
+    reinterpret_cast<float4*>(a.w.increments)[(long)blockIdx.y * a.w.n_samples + i] = out;
+}
+
+// Stage 2, grid = (group tiles, origins of the longest segment, segments): the updated keys of one
+// sampled group of one origin (same arithmetic as dyn_step_kernel: bit-identical keys).  Molecules
+// past the end of the array (last group only) get key 0, which can only widen the bracket.
+__global__ void __launch_bounds__(128) ov_sample_kernel(const SampleArgs a)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const SdbSegment seg = a.segments[blockIdx.z];
+    if (4 * g >= a.w.n_samples || (int)blockIdx.y >= seg.count) return;
+    const int o = seg.first + blockIdx.y;
+    const SdbOrigin org = a.origins[o];
+    if (org.flags & SDB_ORIGIN_NEW) return;
+    const long j = (long)g * 4 * a.w.sample_stride;
+    const long stride = a.p.stride;
+    const float4 vx = sdb_ldg4(org.d_delta + j), vy = sdb_ldg4(org.d_delta + stride + j), vt = sdb_ldg4(org.d_delta + 2 * stride + j);
+    float dx[4] = {vx.x, vx.y, vx.z, vx.w}, dy[4] = {vy.x, vy.y, vy.z, vy.w}, dt[4] = {vt.x, vt.y, vt.z, vt.w};
+    const float4* incs = reinterpret_cast<const float4*>(a.w.increments) + (long)blockIdx.z * a.w.n_samples + 4 * g;
+    float d2[4], th[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float4 inc = __ldg(incs + e);
+        const double alpha = __hiloint2double(__float_as_int(inc.w), __float_as_int(inc.z));
+        sdb_apply_increment(dx[e], dy[e], dt[e], inc.x, inc.y, alpha, d2[e], th[e]);
+        if (j + e >= a.p.n) d2[e] = th[e] = 0.f;
+    }
+    float* out = a.w.samples + (long)o * 2 * a.w.n_samples + 4 * g;
+    *reinterpret_cast<float4*>(out) = make_float4(d2[0], d2[1], d2[2], d2[3]);
+    *reinterpret_cast<float4*>(out + a.w.n_samples) = make_float4(th[0], th[1], th[2], th[3]);
+}
+
+// =================================================================================================
+// block-wide helpers
+// =================================================================================================
+// Given hist[0..nbins) (shared, nbins <= 2 * blockDim) find the bin b with
+//   count(bins > b) < remaining <= count(bins >= b)
+// Returns (in every thread) b, the count above b and hist[b].  `scratch` holds blockDim words.
+__device__ void block_pick(const uint32_t* hist, int nbins, uint32_t remaining, uint32_t* scratch, uint32_t& bin,
+                           uint32_t& above, uint32_t& at_bin)
+{
+    __shared__ uint32_t res[3];
+    const int per = (nbins + blockDim.x - 1) / blockDim.x;
+    const int first = threadIdx.x * per;
+    uint32_t mine = 0;
+    for (int b = first; b < first + per && b < nbins; ++b) mine += hist[b];
+    scratch[threadIdx.x] = mine;
+    __syncthreads();
+    for (int off = 1; off < (int)blockDim.x; off <<= 1) {  // inclusive suffix sum over threads
+        const uint32_t add = threadIdx.x + off < blockDim.x ? scratch[threadIdx.x + off] : 0;
+        __syncthreads();
+        scratch[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t higher = scratch[threadIdx.x] - mine;
+    if (higher < remaining && higher + mine >= remaining) {
+        for (int b = min(first + per, nbins) - 1; b >= first; --b) {
+            const uint32_t h = hist[b];
+            if (higher + h >= remaining) {
+                res[0] = (uint32_t)b;
+                res[1] = higher;
+                res[2] = h;
+                break;
+            }
+            higher += h;
+        }
+    }
+    __syncthreads();
+    bin = res[0];
+    above = res[1];
+    at_bin = res[2];
+    __syncthreads();
+}
+
+// =================================================================================================
+// 2. bracket: two order statistics of the sample, one block per (array, origin)
+// =================================================================================================
+struct BracketArgs {
+    const SdbOrigin* origins;
+    SdbOvWorkspace w;
+    uint32_t rank_hi, rank_lo;  // ranks counted from the largest sample value (1 = maximum)
+};
+
+__global__ void __launch_bounds__(512) ov_bracket_kernel(const BracketArgs a)
+{
+    __shared__ uint32_t hist[2][OV_BINS];
+    __shared__ uint32_t scratch[512];
+    const int arr = blockIdx.x, o = blockIdx.y;
+    if (a.origins[o].flags & SDB_ORIGIN_NEW) return;
+    const uint32_t* keys = reinterpret_cast<const uint32_t*>(a.w.samples + ((long)o * 2 + arr) * a.w.n_samples);
+    const int ns = a.w.n_samples;
+    uint32_t prefix[2] = {0u, 0u};
+    uint32_t remaining[2] = {a.rank_hi, a.rank_lo};
+    const bool active[2] = {a.rank_hi >= 1u && a.rank_hi <= (uint32_t)ns, a.rank_lo >= 1u && a.rank_lo <= (uint32_t)ns};
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
+        const int upper = pass == 0 ? 31 : (pass == 1 ? 20 : 9);
+        const uint32_t mask = pass == 2 ? 511u : 2047u;
+        for (int b = threadIdx.x; b < 2 * OV_BINS; b += blockDim.x) (&hist[0][0])[b] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+            const uint32_t key = keys[i];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (active[s] && (upper >= 31 || (key >> upper) == (prefix[s] >> upper)))
+                    atomicAdd(&hist[s][(key >> shift) & mask], 1u);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (!active[s]) continue;
+            uint32_t bin, above, at_bin;
+            block_pick(hist[s], OV_BINS, remaining[s], scratch, bin, above, at_bin);
+            prefix[s] |= bin << shift;
+            remaining[s] -= above;
+        }
+    }
+    if (threadIdx.x == 0) {
+        // inactive selections: the bracket is open on that side
+        const uint32_t hi = active[0] ? prefix[0] : 0x7f800000u;
+        const uint32_t lo = active[1] ? prefix[1] : 0u;
+        a.w.brackets[o * 4 + 2 * arr + 0] = __uint_as_float(lo);
+        a.w.brackets[o * 4 + 2 * arr + 1] = __uint_as_float(hi);
+    }
+}
+
+// =================================================================================================
+// 4. resolve: exact threshold among the candidates of one origin
+// =================================================================================================
+struct ResolveArgs {
+    const SdbOrigin* origins;
+    SdbOvWorkspace w;
+    double* sums;
+    uint32_t k;
+};
+
+// Strided walk over an array with 8 independent loads in flight per thread (the walks are latency
+// bound otherwise: ~80k candidates per origin, 512 threads).
+template <class F>
+__device__ __forceinline__ void walk8(const uint32_t* __restrict__ v, uint32_t n, F f)
+{
+    const uint32_t step = blockDim.x;
+    uint32_t i = threadIdx.x;
+    for (; i + 7 * step < n; i += 8 * step) {
+        uint32_t x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = __ldg(v + i + u * step);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f(x[u], i + u * step);
+    }
+    for (; i < n; i += step) f(__ldg(v + i), i);
+}
+
+// select record per origin (8 words): thr_r, cut_r, thr_t, cut_t, -, -, fail_r, fail_t
+enum { RS_THR = 0, RS_CUT = 1, RS_FAIL = 6 };
+
+// One block per (array, origin): the need-th largest candidate key inside the bracket (radix select
+// on the offset from lo, 11 bits per walk over the dense candidate array) and, when several keys
+// equal it, the index cut that keeps the `rem` largest molecule indices.
+__global__ void __launch_bounds__(512) ov_select_kernel(const ResolveArgs a)
+{
+    __shared__ uint32_t hist[OV_BINS];
+    __shared__ uint32_t scratch[512];
+    __shared__ uint32_t tot;
+    const int x = blockIdx.x, o = blockIdx.y;
+    uint32_t* sel = a.w.select + 8L * o;
+    if (a.origins[o].flags & SDB_ORIGIN_NEW) return;
+    const double* sums = a.sums + (long)o * SDB_NSUM;
+    const uint32_t plo = __float_as_uint(a.w.brackets[o * 4 + 2 * x]), phi = __float_as_uint(a.w.brackets[o * 4 + 2 * x + 1]);
+    const long need = (long)a.k - (long)sums[x == 0 ? SDB_S_OV_RABOVE : SDB_S_OV_TABOVE];
+    const uint32_t n_cand = a.w.cand_cnt[2 * o];
+    const bool overflow = a.w.cand_cnt[2 * o + 1] != 0 || n_cand > (uint32_t)a.w.cand_cap;
+    const uint32_t* keys = (x == 0 ? a.w.cand_r : a.w.cand_t) + (long)o * a.w.cand_cap;
+    const uint32_t* idx = a.w.cand_idx + (long)o * a.w.cand_cap;
+
+    // walk 0: candidates inside this bracket
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    uint32_t inside = 0;
+    if (!overflow) walk8(keys, n_cand, [&](uint32_t kv, uint32_t) { inside += kv >= plo && kv <= phi; });
+    inside = __reduce_add_sync(0xffffffffu, inside);
+    if ((threadIdx.x & 31) == 0 && inside) atomicAdd(&tot, inside);
+    __syncthreads();
+    const uint32_t total = tot;
+    if (overflow || need < 1 || need > (long)total) {
+        if (threadIdx.x == 0) sel[RS_FAIL + x] = 1u;
+        return;
+    }
+
+    const int bits = phi > plo ? 32 - __clz(phi - plo) : 0;
+    uint32_t value = 0, rem = (uint32_t)need, eq = total;
+    for (int done = 0; done < bits;) {
+        const int nb = min(11, bits - done), shift = bits - done - nb;
+        for (int b = threadIdx.x; b < OV_BINS; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        walk8(keys, n_cand, [&](uint32_t key, uint32_t) {
+            if (key < plo || key > phi) return;
+            const uint32_t kv = key - plo;
+            if (done > 0 && (kv >> (shift + nb)) != (value >> (shift + nb))) return;
+            atomicAdd(&hist[(kv >> shift) & ((1u << nb) - 1u)], 1u);
+        });
+        __syncthreads();
+        uint32_t bin, above, at_bin;
+        block_pick(hist, 1 << nb, rem, scratch, bin, above, at_bin);
+        value |= bin << shift;
+        rem -= above;
+        eq = at_bin;
+        done += nb;
+    }
+    const uint32_t thr = value + plo;
+
+    uint32_t cut = 0;
+    if (eq > rem) {  // keep the rem largest molecule indices among the keys equal to the threshold
+        const int idx_bits = 32 - __clz(max(a.w.n_parts * SDB_WARP_MOLS - 1, 1));
+        uint32_t r = rem;
+        for (int done = 0; done < idx_bits;) {
+            const int nb = min(11, idx_bits - done), shift = idx_bits - done - nb;
+            for (int b = threadIdx.x; b < OV_BINS; b += blockDim.x) hist[b] = 0;
+            __syncthreads();
+            walk8(keys, n_cand, [&](uint32_t key, uint32_t i) {
+                if (key != thr) return;
+                const uint32_t id = __ldg(idx + i);
+                if (done > 0 && (id >> (shift + nb)) != (cut >> (shift + nb))) return;
+                atomicAdd(&hist[(id >> shift) & ((1u << nb) - 1u)], 1u);
+            });
+            __syncthreads();
+            uint32_t bin, above, at_bin;
+            block_pick(hist, 1 << nb, r, scratch, bin, above, at_bin);
+            cut |= bin << shift;
+            r -= above;
+            done += nb;
+        }
+    }
+    if (threadIdx.x == 0) {
+        sel[2 * x + RS_THR] = thr;
+        sel[2 * x + RS_CUT] = cut;
+    }
+}
+
+// grid = (chunks, origins): count the candidates inside both top-k sets; add the molecules above
+// both brackets (counted by the fused kernel).  Failed origins are queued for the exact kernel.
+__global__ void __launch_bounds__(256) ov_intersect_kernel(const ResolveArgs a)
+{
+    __shared__ uint32_t warp_counts[8];
+    const int o = blockIdx.y;
+    double* sums = a.sums + (long)o * SDB_NSUM;
+    const uint32_t* sel = a.w.select + 8L * o;
+    if (a.origins[o].flags & SDB_ORIGIN_NEW) {
+        // all keys are zero: ties are broken by index for both arrays -> identical sets
+        if (blockIdx.x == 0 && threadIdx.x == 0) sums[SDB_S_OVERLAP] = (double)a.k;
+        return;
+    }
+    if (sel[RS_FAIL] | sel[RS_FAIL + 1]) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const uint32_t slot = atomicAdd(a.w.fail, 1u);
+            a.w.fail[1 + slot] = (uint32_t)o;
+        }
+        return;
+    }
+    const uint32_t thr_r = sel[RS_THR], cut_r = sel[RS_CUT], thr_t = sel[2 + RS_THR], cut_t = sel[2 + RS_CUT];
+    const uint32_t n_cand = a.w.cand_cnt[2 * o];
+    const long row = (long)o * a.w.cand_cap;
+    uint32_t both = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += gridDim.x * blockDim.x) {
+        const uint32_t id = __ldg(a.w.cand_idx + row + i), r = __ldg(a.w.cand_r + row + i), t = __ldg(a.w.cand_t + row + i);
+        const bool in_r = r > thr_r || (r == thr_r && id >= cut_r);
+        const bool in_t = t > thr_t || (t == thr_t && id >= cut_t);
+        both += in_r && in_t;
+    }
+    both = __reduce_add_sync(0xffffffffu, both);
+    if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = both;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < 8; ++w) total += warp_counts[w];
+        double add = (double)total;
+        if (blockIdx.x == 0) add += sums[SDB_S_OV_BOTH];
+        // integer-valued doubles: exact and independent of the arrival order
+        if (add != 0.0) atomicAdd(sums + SDB_S_OVERLAP, add);
+    }
+}
+
+// =================================================================================================
+// 5. exact selection over the whole array (cooperative kernel, one origin of the list at a time)
+// =================================================================================================
+struct ExactArgs {
+    const SdbOrigin* origins;
+    const uint32_t* list;  // [0] = count, [1..] = origin indices
+    uint32_t* scratch;     // hist[2][2048], sel[2][8], tie[2][n_parts256]
     double* sums;
     int n;
     long stride;
-    int n_parts;  // 256-molecule parts (tie counting)
-    long words_per_origin;
+    int n_parts;  // 256-molecule parts
     uint32_t k;
-    int key_mode;  // 0: keys from the (dx, dy, dtheta) planes; 1: plane 0 = |dr|, plane 2 = rotation, given
+    int key_mode;  // 0: keys from the (dx, dy, dtheta) planes; 1: plane 0 = displacement, plane 2 = rotation
 };
 
-__device__ __forceinline__ uint32_t* ov_hist(const OvArgs& a, int o) { return a.scratch + o * a.words_per_origin; }
-__device__ __forceinline__ uint32_t* ov_sel(const OvArgs& a, int o) { return ov_hist(a, o) + 2 * OV_BINS; }
-__device__ __forceinline__ uint32_t* ov_tie(const OvArgs& a, int o) { return ov_sel(a, o) + 2 * OV_SEL; }
-
-__device__ __forceinline__ void ov_keys4(const float* d, long stride, int j, uint32_t kr[4], uint32_t kt[4],
-                                         int key_mode = 0)
+__device__ __forceinline__ void ex_keys4(const float* d, long stride, int j, uint32_t kr[4], uint32_t kt[4], int key_mode)
 {
     const float4 x = sdb_ldg4(d + j), y = sdb_ldg4(d + stride + j), t = sdb_ldg4(d + 2 * stride + j);
     const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w}, ts[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const float d2 = __fadd_rn(__fmul_rn(xs[e], xs[e]), __fmul_rn(ys[e], ys[e]));
-        kr[e] = key_mode ? __float_as_uint(xs[e]) : __float_as_uint(__fsqrt_rn(d2));
+        kr[e] = key_mode ? __float_as_uint(xs[e]) : __float_as_uint(d2);
         kt[e] = __float_as_uint(fabsf(ts[e]));
     }
 }
 
-__device__ __forceinline__ int ov_shift(int pass) { return pass == 0 ? 20 : (pass == 1 ? 9 : 0); }
-
-__global__ void ov_init_kernel(const OvArgs a)
+__global__ void __launch_bounds__(256) ov_exact_kernel(const ExactArgs a)
 {
-    const int o = blockIdx.x;
-    uint32_t* h = ov_hist(a, o);
-    for (int i = threadIdx.x; i < 2 * OV_BINS + 2 * OV_SEL; i += blockDim.x) h[i] = 0;
-    __syncthreads();
-    if (threadIdx.x < 2) ov_sel(a, o)[threadIdx.x * OV_SEL + SEL_REMAINING] = a.k;
-}
-
-__global__ void __launch_bounds__(OV_THREADS) ov_hist_kernel(const OvArgs a, int pass)
-{
+    cg::grid_group grid = cg::this_grid();
     __shared__ uint32_t sh[2][OV_BINS];
-    const int o = blockIdx.y;
-    for (int i = threadIdx.x; i < 2 * OV_BINS; i += OV_THREADS) (&sh[0][0])[i] = 0;
-    __syncthreads();
-    const float* d = a.origins[o].d_delta;
-    const uint32_t* sel = ov_sel(a, o);
-    const uint32_t prefix[2] = {sel[SEL_PREFIX], sel[OV_SEL + SEL_PREFIX]};
-    const int shift = ov_shift(pass);
-    const int upper = pass == 0 ? 31 : (pass == 1 ? 20 : 9);  // bits above the current digit
-    const uint32_t mask = pass == 2 ? 511u : 2047u;
-#pragma unroll
-    for (int it = 0; it < OV_ITERS; ++it) {
-        const int j = blockIdx.x * OV_BLOCK_MOLS + (it * OV_THREADS + threadIdx.x) * 4;
-        if (j >= a.n) break;
-        uint32_t kr[4], kt[4];
-        ov_keys4(d, a.stride, j, kr, kt, a.key_mode);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (j + e >= a.n) break;
-            const uint32_t keys[2] = {kr[e], kt[e]};
-#pragma unroll
-            for (int arr = 0; arr < 2; ++arr) {
-                const uint32_t key = keys[arr];
-                const bool match = upper >= 31 || (key >> upper) == (prefix[arr] >> upper);
-                if (match) atomicAdd(&sh[arr][(key >> shift) & mask], 1u);
-            }
-        }
-    }
-    __syncthreads();
-    uint32_t* h = ov_hist(a, o);
-    for (int i = threadIdx.x; i < 2 * OV_BINS; i += OV_THREADS) {
-        const uint32_t c = (&sh[0][0])[i];
-        if (c) atomicAdd(h + i, c);
-    }
-}
-
-// One block per (array, origin): locate the digit of the k-th largest key, clear the histogram.
-__global__ void __launch_bounds__(256) ov_pick_kernel(const OvArgs a, int pass)
-{
-    __shared__ uint32_t totals[256];
-    const int arr = blockIdx.x, o = blockIdx.y;
-    uint32_t* h = ov_hist(a, o) + arr * OV_BINS;
-    uint32_t* sel = ov_sel(a, o) + arr * OV_SEL;
-    uint32_t local[8];
-    uint32_t mine = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        local[i] = h[threadIdx.x * 8 + i];
-        mine += local[i];
-    }
-    totals[threadIdx.x] = mine;
-    __syncthreads();
-    // exclusive suffix sum over threads (count held by higher bins)
-    for (int off = 1; off < 256; off <<= 1) {
-        const uint32_t add = threadIdx.x + off < 256 ? totals[threadIdx.x + off] : 0;
-        __syncthreads();
-        totals[threadIdx.x] += add;
-        __syncthreads();
-    }
-    uint32_t above = totals[threadIdx.x] - mine;  // keys in bins of higher threads
-    const uint32_t remaining = sel[SEL_REMAINING];
-    __syncthreads();
-    if (above < remaining && above + mine >= remaining) {
-#pragma unroll
-        for (int i = 7; i >= 0; --i) {
-            if (above < remaining && above + local[i] >= remaining) {
-                const uint32_t bin = threadIdx.x * 8 + i;
-                sel[SEL_PREFIX] |= bin << ov_shift(pass);
-                sel[SEL_REMAINING] = remaining - above;
-                sel[SEL_COUNT_EQ] = local[i];
-                if (pass == 2) {
-                    sel[SEL_NEED_TIE] = local[i] > remaining - above;
-                    sel[SEL_IDXCUT] = 0;
-                }
-                above = 0xffffffffu;  // done
-                break;
-            }
-            above += local[i];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[threadIdx.x * 8 + i] = 0;
-}
-
-// Ties across the cut: count, per 256-molecule part, the keys equal to the threshold.
-__global__ void __launch_bounds__(256) ov_tiecount_kernel(const OvArgs a)
-{
-    const int o = blockIdx.y;
-    const uint32_t* sel = ov_sel(a, o);
-    const bool need[2] = {sel[SEL_NEED_TIE] != 0, sel[OV_SEL + SEL_NEED_TIE] != 0};
-    if (!need[0] && !need[1]) return;
-    const uint32_t thr[2] = {sel[SEL_PREFIX], sel[OV_SEL + SEL_PREFIX]};
-    const float* d = a.origins[o].d_delta;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int part = blockIdx.x * 8 + warp;
-    if (part >= a.n_parts) return;
-    int c[2] = {0, 0};
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const int j = part * 256 + g * 128 + lane * 4;
-        if (j < a.n) {
-            uint32_t kr[4], kt[4];
-            ov_keys4(d, a.stride, j, kr, kt, a.key_mode);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (j + e < a.n) {
-                    c[0] += kr[e] == thr[0];
-                    c[1] += kt[e] == thr[1];
-                }
-            }
-        }
-    }
-    c[0] = __reduce_add_sync(0xffffffffu, c[0]);
-    c[1] = __reduce_add_sync(0xffffffffu, c[1]);
-    if (lane == 0) {
-        ov_tie(a, o)[part] = c[0];
-        ov_tie(a, o)[a.n_parts + part] = c[1];
-    }
-}
-
-// One block per (array, origin): smallest molecule index still inside the top-k among the ties.
-__global__ void __launch_bounds__(256) ov_tiepick_kernel(const OvArgs a)
-{
-    __shared__ uint32_t sh[256];
+    __shared__ uint32_t scratch[256];
+    __shared__ int warp_counts[8];
     __shared__ int found_part;
     __shared__ uint32_t found_rem;
-    const int arr = blockIdx.x, o = blockIdx.y;
-    uint32_t* sel = ov_sel(a, o) + arr * OV_SEL;
-    if (!sel[SEL_NEED_TIE]) return;
-    const uint32_t* tie = ov_tie(a, o) + arr * a.n_parts;
-    const uint32_t remaining = sel[SEL_REMAINING];
-    // walk the parts from the end in chunks of 256, carrying the count found so far
-    uint32_t carried = 0;
-    if (threadIdx.x == 0) found_part = -1;
-    __syncthreads();
-    for (int hi = a.n_parts; hi > 0 && found_part < 0; hi -= 256) {
-        const int p = hi - 1 - threadIdx.x;  // thread 0 owns the last part of the chunk
-        const uint32_t mine = p >= 0 ? tie[p] : 0;
-        sh[threadIdx.x] = mine;
-        __syncthreads();
-        for (int off = 1; off < 256; off <<= 1) {  // inclusive prefix over threads (= suffix over parts)
-            const uint32_t add = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+    const uint32_t n_list = a.list[0];
+    uint32_t* hist = a.scratch;
+    uint32_t* sel = hist + 2 * OV_BINS;
+    uint32_t* tie = sel + 2 * OV_SEL;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+
+    for (uint32_t li = 0; li < n_list; ++li) {
+        const int o = (int)a.list[1 + li];
+        const float* d = a.origins[o].d_delta;
+        for (int i = gtid; i < 2 * OV_BINS + 2 * OV_SEL; i += gsize) hist[i] = 0;
+        if (gtid == 0) a.sums[(long)o * SDB_NSUM + SDB_S_OVERLAP] = 0.0;
+        grid.sync();
+        if (gtid < 2) sel[gtid * OV_SEL + SEL_REMAINING] = a.k;
+        grid.sync();
+
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
+            const int upper = pass == 0 ? 31 : (pass == 1 ? 20 : 9);
+            const uint32_t mask = pass == 2 ? 511u : 2047u;
+            for (int i = threadIdx.x; i < 2 * OV_BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
             __syncthreads();
-            sh[threadIdx.x] += add;
-            __syncthreads();
-        }
-        const uint32_t incl = carried + sh[threadIdx.x], excl = incl - mine;
-        if (p >= 0 && excl < remaining && incl >= remaining) {
-            found_part = p;
-            found_rem = remaining - excl;
-        }
-        carried += sh[255];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        uint32_t idxcut = 0;
-        if (found_part >= 0) {
-            const float* d = a.origins[o].d_delta;
-            const uint32_t thr = sel[SEL_PREFIX];
-            uint32_t need = found_rem;
-            const int lo = found_part * 256;
-            int hi = lo + 255;
-            if (hi >= a.n) hi = a.n - 1;
-            for (int j = hi; j >= lo; --j) {
-                uint32_t key;
-                if (arr == 0) {
-                    const float dx = d[j], dy = d[a.stride + j];
-                    key = a.key_mode ? __float_as_uint(dx)
-                                     : __float_as_uint(__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
-                } else {
-                    key = __float_as_uint(fabsf(d[2 * a.stride + j]));
-                }
-                if (key == thr && --need == 0) {
-                    idxcut = (uint32_t)j;
-                    break;
+            const uint32_t prefix[2] = {sel[SEL_PREFIX], sel[OV_SEL + SEL_PREFIX]};
+            for (int j = gtid * 4; j < a.n; j += gsize * 4) {
+                uint32_t kr[4], kt[4];
+                ex_keys4(d, a.stride, j, kr, kt, a.key_mode);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (j + e >= a.n) break;
+                    const uint32_t keys[2] = {kr[e], kt[e]};
+#pragma unroll
+                    for (int arr = 0; arr < 2; ++arr)
+                        if (upper >= 31 || (keys[arr] >> upper) == (prefix[arr] >> upper))
+                            atomicAdd(&sh[arr][(keys[arr] >> shift) & mask], 1u);
                 }
             }
+            __syncthreads();
+            for (int i = threadIdx.x; i < 2 * OV_BINS; i += blockDim.x) {
+                const uint32_t c = (&sh[0][0])[i];
+                if (c) atomicAdd(hist + i, c);
+            }
+            grid.sync();
+            if (blockIdx.x < 2) {  // one block per array picks the digit
+                const int arr = blockIdx.x;
+                uint32_t* s = sel + arr * OV_SEL;
+                for (int i = threadIdx.x; i < OV_BINS; i += blockDim.x) sh[0][i] = hist[arr * OV_BINS + i];
+                __syncthreads();
+                uint32_t bin, above, at_bin;
+                const uint32_t remaining = s[SEL_REMAINING];
+                block_pick(sh[0], OV_BINS, remaining, scratch, bin, above, at_bin);
+                if (threadIdx.x == 0) {
+                    s[SEL_PREFIX] |= bin << shift;
+                    s[SEL_REMAINING] = remaining - above;
+                    s[SEL_COUNT_EQ] = at_bin;
+                    if (pass == 2) {
+                        s[SEL_NEED_TIE] = at_bin > remaining - above;
+                        s[SEL_IDXCUT] = 0;
+                    }
+                }
+                for (int i = threadIdx.x; i < OV_BINS; i += blockDim.x) hist[arr * OV_BINS + i] = 0;
+            }
+            grid.sync();
         }
-        sel[SEL_IDXCUT] = idxcut;
+
+        // ---- ties across the cut: per-part counts, then the smallest index still inside ----------
+        const bool need[2] = {sel[SEL_NEED_TIE] != 0, sel[OV_SEL + SEL_NEED_TIE] != 0};
+        const uint32_t thr[2] = {sel[SEL_PREFIX], sel[OV_SEL + SEL_PREFIX]};
+        if (need[0] || need[1]) {  // uniform across the grid
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            for (int part = blockIdx.x * 8 + warp; part < a.n_parts; part += gridDim.x * 8) {
+                int c[2] = {0, 0};
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int j = part * 256 + g * 128 + lane * 4;
+                    if (j < a.n) {
+                        uint32_t kr[4], kt[4];
+                        ex_keys4(d, a.stride, j, kr, kt, a.key_mode);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (j + e < a.n) {
+                                c[0] += kr[e] == thr[0];
+                                c[1] += kt[e] == thr[1];
+                            }
+                        }
+                    }
+                }
+                c[0] = __reduce_add_sync(0xffffffffu, c[0]);
+                c[1] = __reduce_add_sync(0xffffffffu, c[1]);
+                if (lane == 0) {
+                    tie[part] = c[0];
+                    tie[a.n_parts + part] = c[1];
+                }
+            }
+            grid.sync();
+            if (blockIdx.x < 2 && need[blockIdx.x]) {
+                const int arr = blockIdx.x;
+                uint32_t* s = sel + arr * OV_SEL;
+                const uint32_t* tcount = tie + arr * a.n_parts;
+                const uint32_t remaining = s[SEL_REMAINING];
+                if (threadIdx.x == 0) found_part = -1;
+                __syncthreads();
+                uint32_t carried = 0;
+                // walk the parts from the end in chunks of 256, carrying the count found so far
+                for (int hi = a.n_parts; hi > 0 && found_part < 0; hi -= 256) {
+                    const int p = hi - 1 - threadIdx.x;  // thread 0 owns the last part of the chunk
+                    const uint32_t mine = p >= 0 ? tcount[p] : 0;
+                    scratch[threadIdx.x] = mine;
+                    __syncthreads();
+                    for (int off = 1; off < 256; off <<= 1) {
+                        const uint32_t add = threadIdx.x >= off ? scratch[threadIdx.x - off] : 0;
+                        __syncthreads();
+                        scratch[threadIdx.x] += add;
+                        __syncthreads();
+                    }
+                    const uint32_t incl = carried + scratch[threadIdx.x], excl = incl - mine;
+                    if (p >= 0 && excl < remaining && incl >= remaining) {
+                        found_part = p;
+                        found_rem = remaining - excl;
+                    }
+                    carried += scratch[255];
+                    __syncthreads();
+                }
+                if (threadIdx.x == 0) {
+                    uint32_t idxcut = 0;
+                    if (found_part >= 0) {
+                        uint32_t want = found_rem;
+                        const int lo = found_part * 256;
+                        const int hi = min(lo + 255, a.n - 1);
+                        for (int j = hi; j >= lo; --j) {
+                            uint32_t key;
+                            if (arr == 0) {
+                                const float dx = d[j], dy = d[a.stride + j];
+                                key = a.key_mode ? __float_as_uint(dx)
+                                                 : __float_as_uint(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+                            } else {
+                                key = __float_as_uint(fabsf(d[2 * a.stride + j]));
+                            }
+                            if (key == thr[arr] && --want == 0) {
+                                idxcut = (uint32_t)j;
+                                break;
+                            }
+                        }
+                    }
+                    s[SEL_IDXCUT] = idxcut;
+                }
+            }
+            grid.sync();
+        }
+
+        // ---- intersection count -------------------------------------------------------------------
+        const uint32_t cut[2] = {sel[SEL_IDXCUT], sel[OV_SEL + SEL_IDXCUT]};
+        int count = 0;
+        for (int j = gtid * 4; j < a.n; j += gsize * 4) {
+            uint32_t kr[4], kt[4];
+            ex_keys4(d, a.stride, j, kr, kt, a.key_mode);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t idx = (uint32_t)(j + e);
+                const bool in_r = kr[e] > thr[0] || (kr[e] == thr[0] && idx >= cut[0]);
+                const bool in_t = kt[e] > thr[1] || (kt[e] == thr[1] && idx >= cut[1]);
+                count += (j + e < a.n) && in_r && in_t;
+            }
+        }
+        count = __reduce_add_sync(0xffffffffu, count);
+        if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = count;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int total = 0;
+            for (int w = 0; w < 8; ++w) total += warp_counts[w];
+            // integer-valued doubles: exact and independent of the arrival order
+            if (total) atomicAdd(a.sums + (long)o * SDB_NSUM + SDB_S_OVERLAP, (double)total);
+        }
+        grid.sync();
     }
 }
 
-__global__ void __launch_bounds__(OV_THREADS) ov_count_kernel(const OvArgs a)
+__global__ void ov_fill_list_kernel(uint32_t* list, int n)
 {
-    __shared__ int warp_counts[OV_THREADS / 32];
-    const int o = blockIdx.y;
-    const float* d = a.origins[o].d_delta;
-    const uint32_t* sel = ov_sel(a, o);
-    const uint32_t thr[2] = {sel[SEL_PREFIX], sel[OV_SEL + SEL_PREFIX]};
-    const uint32_t cut[2] = {sel[SEL_IDXCUT], sel[OV_SEL + SEL_IDXCUT]};
-    int count = 0;
-#pragma unroll
-    for (int it = 0; it < OV_ITERS; ++it) {
-        const int j = blockIdx.x * OV_BLOCK_MOLS + (it * OV_THREADS + threadIdx.x) * 4;
-        if (j >= a.n) break;
-        uint32_t kr[4], kt[4];
-        ov_keys4(d, a.stride, j, kr, kt, a.key_mode);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t idx = (uint32_t)(j + e);
-            const bool in_r = kr[e] > thr[0] || (kr[e] == thr[0] && idx >= cut[0]);
-            const bool in_t = kt[e] > thr[1] || (kt[e] == thr[1] && idx >= cut[1]);
-            count += (j + e < a.n) && in_r && in_t;
-        }
-    }
-    count = __reduce_add_sync(0xffffffffu, count);
-    if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = count;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int total = 0;
-        for (int w = 0; w < OV_THREADS / 32; ++w) total += warp_counts[w];
-        if (total) atomicAdd(a.sums + (long)o * SDB_NSUM + SDB_S_OVERLAP, (double)total);
-    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) list[0] = (uint32_t)n;
+    if (i < n) list[1 + i] = (uint32_t)i;
 }
 
-long ov_words_per_origin(int n) { return 2L * OV_BINS + 2L * OV_SEL + 2L * ((n + 255) / 256); }
+int exact_grid_blocks()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && cached[dev]) return cached[dev];
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ov_exact_kernel, 256, 0);
+    const int blocks = sms * (per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm));
+    if (dev < 64) cached[dev] = blocks;
+    return blocks;
+}
+
+int launch_exact(const SdbOrigin* d_origins, const uint32_t* d_list, uint32_t* d_scratch, double* d_sums, int n,
+                 int stride, int k, int key_mode, cudaStream_t s)
+{
+    ExactArgs a;
+    a.origins = d_origins;
+    a.list = d_list;
+    a.scratch = d_scratch;
+    a.sums = d_sums;
+    a.n = n;
+    a.stride = stride;
+    a.n_parts = (n + 255) / 256;
+    a.k = (uint32_t)k;
+    a.key_mode = key_mode;
+    void* args[] = {&a};
+    const int blocks = exact_grid_blocks();
+    sdb_count_launch();
+    return sdb_check_cuda(cudaLaunchCooperativeKernel((void*)ov_exact_kernel, dim3(blocks), dim3(256), args, 0, s),
+                          "ov_exact_kernel");
+}
 
 }  // namespace
 
+// -------------------------------------------------------------------------------------------------
+extern "C" size_t sdb_overlap_ws_bytes(int32_t max_origins, int32_t n)
+{
+    if (max_origins <= 0 || n <= 0) return 0;
+    return sdb_ov_layout(nullptr, max_origins, n, nullptr);
+}
+
+extern "C" int sdb_overlap_prepare(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
+                                   const SdbOrigin* d_origins, int32_t n_origins, const SdbSegment* d_segments,
+                                   int32_t n_segments, int32_t max_segment_count, int32_t k, void* d_ws,
+                                   int32_t ws_origins, void* stream)
+{
+    if (!h_params || !d_origins || !d_segments || !d_ws || n_origins > ws_origins || k <= 0 || k > h_params->n ||
+        max_segment_count <= 0 || max_segment_count > 65535 || n_segments > 65535) {
+        sdb_set_error("sdb_overlap_prepare: bad argument");
+        return SDB_EINVAL;
+    }
+    if (n_origins <= 0) return SDB_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SampleArgs sa;
+    sa.p = *h_params;
+    sa.pos = d_pos;
+    sa.quat = d_quat;
+    sa.origins = d_origins;
+    sa.segments = d_segments;
+    sa.atan_tab = sdb_device_atan_table();
+    if (!sa.atan_tab) return SDB_ECUDA;
+    sdb_ov_layout(d_ws, ws_origins, h_params->n, &sa.w);
+    if (n_segments > ws_origins) {
+        sdb_set_error("sdb_overlap_prepare: more segments than workspace rows");
+        return SDB_EINVAL;
+    }
+    // candidate counters, select records and the fail list are contiguous: one clear
+    int rc = sdb_check_cuda(cudaMemsetAsync(sa.w.cand_cnt, 0, sizeof(uint32_t) * 2 * (size_t)ws_origins, s),
+                            "sdb_overlap_prepare: clear counters");
+    if (rc) return rc;
+    rc = sdb_check_cuda(cudaMemsetAsync(sa.w.select, 0, sizeof(uint32_t) * 8 * (size_t)ws_origins, s),
+                        "sdb_overlap_prepare: clear select");
+    if (rc) return rc;
+    rc = sdb_check_cuda(cudaMemsetAsync(sa.w.fail, 0, sizeof(uint32_t), s), "sdb_overlap_prepare: clear fail list");
+    if (rc) return rc;
+    ov_increment_kernel<<<dim3((sa.w.n_samples + 127) / 128, n_segments), 128, 0, s>>>(sa);
+    SDB_CHECK_LAUNCH("ov_increment_kernel");
+    ov_sample_kernel<<<dim3((sa.w.n_samples / 4 + 127) / 128, max_segment_count, n_segments), 128, 0, s>>>(sa);
+    SDB_CHECK_LAUNCH("ov_sample_kernel");
+
+    // ranks (from the top) of the two sample order statistics that bracket the k-th largest key
+    BracketArgs ba;
+    ba.origins = d_origins;
+    ba.w = sa.w;
+    const double n = h_params->n, ns = sa.w.n_samples, p = k / n;
+    if (sa.w.sample_stride == 1) {
+        ba.rank_hi = ba.rank_lo = (uint32_t)k;  // the sample is the whole array: lo = hi = threshold
+    } else {
+        const double mu = p * ns, sigma = sqrt(ns * p * (1.0 - p));
+        const double width = 10.0 * sigma + 4.0;  // 5 sigma with a 2x allowance: the sample consists of
+                                                   // groups of 4 neighbours, which may be correlated
+        const double hi = floor(mu - width), lo = ceil(mu + width);
+        ba.rank_hi = hi < 1.0 ? 0u : (uint32_t)hi;                // 0: open above
+        ba.rank_lo = lo > ns ? (uint32_t)ns + 1u : (uint32_t)lo;  // > ns: open below
+    }
+    ov_bracket_kernel<<<dim3(2, n_origins), 512, 0, s>>>(ba);
+    SDB_CHECK_LAUNCH("ov_bracket_kernel");
+    return SDB_OK;
+}
+
+extern "C" int sdb_overlap_resolve(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride, int32_t k,
+                                   void* d_ws, int32_t ws_origins, double* d_sums, void* stream)
+{
+    if (!d_origins || !d_ws || !d_sums || n <= 0 || k <= 0 || k > n || n_origins > ws_origins) {
+        sdb_set_error("sdb_overlap_resolve: bad argument");
+        return SDB_EINVAL;
+    }
+    if (n_origins <= 0) return SDB_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ResolveArgs ra;
+    ra.origins = d_origins;
+    ra.sums = d_sums;
+    ra.k = (uint32_t)k;
+    sdb_ov_layout(d_ws, ws_origins, n, &ra.w);
+    int rc = sdb_check_cuda(cudaMemset2DAsync(d_sums + SDB_S_OVERLAP, SDB_NSUM * sizeof(double), 0, sizeof(double),
+                                              (size_t)n_origins, s),
+                            "sdb_overlap_resolve: clear");
+    if (rc) return rc;
+    ov_select_kernel<<<dim3(2, n_origins), 512, 0, s>>>(ra);
+    SDB_CHECK_LAUNCH("ov_select_kernel");
+    ov_intersect_kernel<<<dim3(8, n_origins), 256, 0, s>>>(ra);
+    SDB_CHECK_LAUNCH("ov_intersect_kernel");
+    // origins whose bracket failed: exact selection over the whole array (no-op when the list is empty)
+    return launch_exact(d_origins, ra.w.fail, ra.w.exact, d_sums, n, stride, k, 0, s);
+}
+
 extern "C" size_t sdb_overlap_scratch_bytes(int32_t n_origins, int32_t n)
 {
-    return (size_t)n_origins * (size_t)ov_words_per_origin(n) * sizeof(uint32_t);
+    if (n_origins <= 0 || n <= 0) return 0;
+    return sizeof(uint32_t) * (sdb_ov_exact_words(n) + 1 + (size_t)n_origins + 64);
 }
 
 extern "C" int sdb_overlap(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride, int32_t key_mode,
@@ -294,34 +726,9 @@ extern "C" int sdb_overlap(const SdbOrigin* d_origins, int32_t n_origins, int32_
     }
     if (n_origins <= 0) return SDB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    OvArgs a;
-    a.origins = d_origins;
-    a.scratch = static_cast<uint32_t*>(d_scratch);
-    a.sums = d_sums;
-    a.n = n;
-    a.stride = stride;
-    a.n_parts = (n + 255) / 256;
-    a.words_per_origin = ov_words_per_origin(n);
-    a.k = (uint32_t)k;
-    a.key_mode = key_mode;
-    int rc = sdb_check_cuda(cudaMemset2DAsync(d_sums + SDB_S_OVERLAP, SDB_NSUM * sizeof(double), 0, sizeof(double),
-                                              (size_t)n_origins, s),
-                            "sdb_overlap: clear");
-    if (rc) return rc;
-    ov_init_kernel<<<n_origins, 256, 0, s>>>(a);
-    SDB_CHECK_LAUNCH("ov_init_kernel");
-    const dim3 grid_n((n + OV_BLOCK_MOLS - 1) / OV_BLOCK_MOLS, n_origins);
-    for (int pass = 0; pass < 3; ++pass) {
-        ov_hist_kernel<<<grid_n, OV_THREADS, 0, s>>>(a, pass);
-        SDB_CHECK_LAUNCH("ov_hist_kernel");
-        ov_pick_kernel<<<dim3(2, n_origins), 256, 0, s>>>(a, pass);
-        SDB_CHECK_LAUNCH("ov_pick_kernel");
-    }
-    ov_tiecount_kernel<<<dim3((a.n_parts + 7) / 8, n_origins), 256, 0, s>>>(a);
-    SDB_CHECK_LAUNCH("ov_tiecount_kernel");
-    ov_tiepick_kernel<<<dim3(2, n_origins), 256, 0, s>>>(a);
-    SDB_CHECK_LAUNCH("ov_tiepick_kernel");
-    ov_count_kernel<<<grid_n, OV_THREADS, 0, s>>>(a);
-    SDB_CHECK_LAUNCH("ov_count_kernel");
-    return SDB_OK;
+    uint32_t* list = static_cast<uint32_t*>(d_scratch);
+    uint32_t* scratch = list + ((1 + n_origins + 63) / 64) * 64;
+    ov_fill_list_kernel<<<(n_origins + 255) / 256, 256, 0, s>>>(list, n_origins);
+    SDB_CHECK_LAUNCH("ov_fill_list_kernel");
+    return launch_exact(d_origins, list, scratch, d_sums, n, stride, k, key_mode, s);
 }

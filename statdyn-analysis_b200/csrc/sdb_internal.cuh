@@ -46,3 +46,78 @@ __device__ __forceinline__ void sdb_st_stream4(float* p, float4 v)
 {
     __stcs(reinterpret_cast<float4*>(p), v);
 }
+
+// ---- TrackedMotion.add for one molecule and one origin (dynamics/_util.py:149-153) ---------------
+// Shared by the fused kernel and the overlap sample kernel so both see bit-identical keys.
+__device__ __forceinline__ void sdb_apply_increment(float& dx, float& dy, float& dt, float wx, float wy, double alpha,
+                                                    float& d2, float& th)
+{
+    dx = SDB_FSUB(dx, wx);
+    dy = SDB_FSUB(dy, wy);
+    dt = (float)((double)dt + alpha);
+    // np.square(delta).sum(axis=1) in f32, one rounding per operation
+    d2 = SDB_FADD(SDB_FMUL(dx, dx), SDB_FMUL(dy, dy));
+    th = fabsf(dt);
+}
+
+// ---- workspace of the bracketed `overlap` selection (csrc/overlap.cu) -----------------------------
+// Keys: translation d2 = |dr|^2 (f32, monotone in the reference's |dr|), rotation |dtheta|; both >= 0.
+constexpr int SDB_OV_SAMPLES = 16384;  // target number of sampled molecules per origin
+constexpr int SDB_OV_STAGE = 96;       // candidates one warp can stage per (origin, 256-molecule tile)
+
+struct SdbOvWorkspace {
+    float* brackets;     // [origins][4]: lo_r, hi_r, lo_t, hi_t (inclusive candidate intervals)
+    float* samples;      // [origins][2][n_samples]
+    float* increments;   // [segments <= origins][n_samples][4]: wx, wy, alpha (f64 in two words)
+    uint32_t* cand_cnt;  // [origins][2]: number of candidates, overflow flag
+    uint32_t* cand_idx;  // [origins][cand_cap]  molecule index        } dense, unordered
+    uint32_t* cand_r;    // [origins][cand_cap]  bits of d2            }
+    uint32_t* cand_t;    // [origins][cand_cap]  bits of |dtheta|      }
+    uint32_t* select;    // [origins][8]: thresholds and index cuts found by the resolve kernel
+    uint32_t* fail;      // [1 + origins]: count, then origin indices whose bracket failed
+    uint32_t* exact;     // scratch of the exact (radix select) kernel, one origin at a time
+    int n_samples, sample_stride, n_parts, cand_cap;
+};
+
+inline size_t sdb_ov_exact_words(int n) { return 2 * 2048 + 2 * 8 + 2 * (size_t)((n + 255) / 256) + 64; }
+
+inline size_t sdb_ov_layout(void* base, int max_origins, int n, SdbOvWorkspace* w)
+{
+    const int n_parts = (n + SDB_WARP_MOLS - 1) / SDB_WARP_MOLS;
+    // the sample: groups of 4 consecutive molecules, one group every 4 * stride molecules
+    const int stride = n / SDB_OV_SAMPLES > 1 ? n / SDB_OV_SAMPLES : 1;
+    const int n_groups = (n + 4 * stride - 1) / (4 * stride);
+    const int n_samples = 4 * n_groups;
+    // expected candidates: ~2 x 4.3 % of n; 4x head room (and never less than one staging buffer)
+    const int cand_cap = ((n / 3 > 4 * SDB_OV_STAGE ? n / 3 : 4 * SDB_OV_STAGE) + 63) & ~63;
+    auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    size_t off = 0;
+    char* b = static_cast<char*>(base);
+    const size_t o_br = off;   off = align(off + sizeof(float) * 4 * (size_t)max_origins);
+    const size_t o_sm = off;   off = align(off + sizeof(float) * 2 * (size_t)n_samples * max_origins);
+    const size_t o_in = off;   off = align(off + sizeof(float) * 4 * (size_t)n_samples * max_origins);
+    const size_t o_cc = off;   off = align(off + sizeof(uint32_t) * 2 * (size_t)max_origins);
+    const size_t o_ci = off;   off = align(off + sizeof(uint32_t) * (size_t)cand_cap * max_origins);
+    const size_t o_cr = off;   off = align(off + sizeof(uint32_t) * (size_t)cand_cap * max_origins);
+    const size_t o_ct = off;   off = align(off + sizeof(uint32_t) * (size_t)cand_cap * max_origins);
+    const size_t o_se = off;   off = align(off + sizeof(uint32_t) * 8 * (size_t)max_origins);
+    const size_t o_fl = off;   off = align(off + sizeof(uint32_t) * (size_t)(1 + max_origins));
+    const size_t o_ex = off;   off = align(off + sizeof(uint32_t) * sdb_ov_exact_words(n));
+    if (w) {
+        w->brackets = reinterpret_cast<float*>(b + o_br);
+        w->samples = reinterpret_cast<float*>(b + o_sm);
+        w->increments = reinterpret_cast<float*>(b + o_in);
+        w->cand_cnt = reinterpret_cast<uint32_t*>(b + o_cc);
+        w->cand_idx = reinterpret_cast<uint32_t*>(b + o_ci);
+        w->cand_r = reinterpret_cast<uint32_t*>(b + o_cr);
+        w->cand_t = reinterpret_cast<uint32_t*>(b + o_ct);
+        w->select = reinterpret_cast<uint32_t*>(b + o_se);
+        w->fail = reinterpret_cast<uint32_t*>(b + o_fl);
+        w->exact = reinterpret_cast<uint32_t*>(b + o_ex);
+        w->n_samples = n_samples;
+        w->sample_stride = stride;
+        w->n_parts = n_parts;
+        w->cand_cap = cand_cap;
+    }
+    return off;
+}

@@ -31,6 +31,9 @@ EXPORTS = (
     "sdb_struct",
     "sdb_overlap",
     "sdb_overlap_scratch_bytes",
+    "sdb_overlap_ws_bytes",
+    "sdb_overlap_prepare",
+    "sdb_overlap_resolve",
     "sdb_first_passage",
     "sdb_last_passage",
     "sdb_motion_general",
@@ -117,13 +120,16 @@ def load():
     lib = ctypes.CDLL(str(LIB_PATH))
     P = c_void_p
     sig = {
-        "sdb_dyn_step": (c_int32, [POINTER(SdbDynParams), P, P, P, P, c_int32, P, c_int32, P, P, P]),
+        "sdb_dyn_step": (c_int32, [POINTER(SdbDynParams), P, P, P, P, c_int32, P, c_int32, P, P, P, c_int32, P]),
         "sdb_dyn_num_parts": (c_int32, [c_int32]),
         "sdb_dyn_norms": (c_int32, [P, c_int32, c_int32, P, P, P]),
         "sdb_pack_frame": (c_int32, [P, P, c_int32, c_int32, P, P, P]),
         "sdb_struct": (c_int32, [P, c_int32, c_int32, c_int32, POINTER(c_float), c_int32, c_double, c_int32, P, P]),
         "sdb_overlap": (c_int32, [P, c_int32, c_int32, c_int32, c_int32, c_int32, P, P, P]),
         "sdb_overlap_scratch_bytes": (c_size_t, [c_int32, c_int32]),
+        "sdb_overlap_ws_bytes": (c_size_t, [c_int32, c_int32]),
+        "sdb_overlap_prepare": (c_int32, [POINTER(SdbDynParams), P, P, P, c_int32, P, c_int32, c_int32, c_int32, P, c_int32, P]),
+        "sdb_overlap_resolve": (c_int32, [P, c_int32, c_int32, c_int32, c_int32, P, c_int32, P, P]),
         "sdb_first_passage": (c_int32, [P, c_int32, c_int32, c_double, c_int64, P, P]),
         "sdb_last_passage": (c_int32, [P, c_int32, c_int32, c_double, c_double, c_int64, P, P, P]),
         "sdb_motion_general": (c_int32, [POINTER(c_float), c_int32, c_int32, P, P, P, P, c_int32, P, P, P, P]),

@@ -20,6 +20,7 @@ import numpy as np
 from . import _lib
 
 SDB_NSUM = _lib.SDB_NSUM
+ROW = SDB_NSUM + 2  # gathered rows carry (key, timediff) behind the sums
 
 
 def owner_of(key, world):
@@ -60,7 +61,7 @@ class ShardedDynamics:
         self.frames = [torch.zeros(frame_floats(self.n), dtype=torch.float32, device=self.device) for _ in range(depth)]
         self._slot = 0
         # gather buffers: one row block per rank, padded to max_local (+1 header row: count)
-        self._send = torch.zeros((self.max_local + 1, SDB_NSUM), dtype=torch.float64, device=self.device)
+        self._send = torch.zeros((self.max_local + 1, ROW), dtype=torch.float64, device=self.device)
         self._recv = (
             [torch.zeros_like(self._send) for _ in range(self.world)] if self.rank == 0 else None
         )
@@ -115,9 +116,9 @@ class ShardedDynamics:
         send.zero_()
         send[0, 0] = len(keys)
         if keys:
-            send[1 : 1 + len(keys)] = sums
+            send[1 : 1 + len(keys), :SDB_NSUM] = sums
             meta = torch.tensor([[k, t] for k, t in zip(keys, timediffs)], dtype=torch.float64, device=self.device)
-            send[1 : 1 + len(keys), SDB_NSUM - 2 :] = meta  # spare columns carry (key, timediff)
+            send[1 : 1 + len(keys), SDB_NSUM:] = meta
         dist.gather(send, self._recv if self.rank == 0 else None, dst=0, group=self.group)
         if self.rank != 0:
             return lambda: (keys, timediffs, None)
@@ -129,11 +130,10 @@ class ShardedDynamics:
                 host = block.cpu().numpy()
                 count = int(host[0, 0])
                 for row in host[1 : 1 + count]:
-                    rows[int(row[SDB_NSUM - 2])] = (int(row[SDB_NSUM - 1]), row.copy())
+                    rows[int(row[SDB_NSUM])] = (int(row[SDB_NSUM + 1]), row[:SDB_NSUM].copy())
             out_keys = [k for k in active if k in rows]
             out_td = [rows[k][0] for k in out_keys]
             out = np.stack([rows[k][1] for k in out_keys]) if out_keys else np.zeros((0, SDB_NSUM))
-            out[:, SDB_NSUM - 2 :] = 0
             return out_keys, out_td, out
 
         return collect

@@ -340,8 +340,8 @@ class DynamicsEngine:
         self._sums_dev = [torch.zeros((cap, SDB_NSUM), dtype=torch.float64, device=dev) for _ in range(self._ring_depth)]
         self._partials = torch.empty((cap, self._n_parts, SDB_NSUM), dtype=torch.float64, device=dev)
         if self.compute_overlap and self.overlap_k > 0:
-            nbytes = int(self.lib.sdb_overlap_scratch_bytes(cap, self.n))
-            self._ov_scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            nbytes = int(self.lib.sdb_overlap_ws_bytes(cap, self.n))
+            self._ov_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
     def _stage_frame(self, position, orientation):
         """Return device tensors (pos (N,3) f32, quat (N,4) f32 or None).
@@ -570,6 +570,19 @@ class DynamicsEngine:
             if prof is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
+            use_ov = do_sums and self.compute_overlap and self.overlap_k > 0
+            ov_ws = self._ov_ws.data_ptr() if use_ov else 0
+            if use_ov:
+                # sample the updated keys of every origin and bracket the k-th largest of each array
+                _lib.check(
+                    lib.sdb_overlap_prepare(
+                        params, _lib.ptr(pos), _lib.ptr(quat), d_origins, n_active, d_segments, len(seg_rows),
+                        max(row[3] for row in seg_rows), self.overlap_k, ov_ws, self._cap, stream,
+                    )
+                )
+            if prof is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
             _lib.check(
                 lib.sdb_dyn_step(
                     params,
@@ -582,12 +595,14 @@ class DynamicsEngine:
                     len(seg_rows),
                     self._partials.data_ptr(),
                     sums_dev.data_ptr(),
+                    ov_ws,
+                    self._cap,
                     stream,
                 )
             )
             if prof is not None:
-                ev1 = torch.cuda.Event(enable_timing=True)
-                ev1.record()
+                ev2 = torch.cuda.Event(enable_timing=True)
+                ev2.record()
             if do_sums and self.compute_struct:
                 _lib.check(
                     lib.sdb_struct(
@@ -596,19 +611,19 @@ class DynamicsEngine:
                     )
                 )
             if prof is not None:
-                ev2 = torch.cuda.Event(enable_timing=True)
-                ev2.record()
-            if do_sums and self.compute_overlap and self.overlap_k > 0:
+                ev3 = torch.cuda.Event(enable_timing=True)
+                ev3.record()
+            if use_ov:
                 _lib.check(
-                    lib.sdb_overlap(
-                        d_origins, n_active, self.n, self.stride, 0, self.overlap_k,
-                        self._ov_scratch.data_ptr(), sums_dev.data_ptr(), stream,
+                    lib.sdb_overlap_resolve(
+                        d_origins, n_active, self.n, self.stride, self.overlap_k, ov_ws, self._cap,
+                        sums_dev.data_ptr(), stream,
                     )
                 )
             if prof is not None:
-                ev3 = torch.cuda.Event(enable_timing=True)
-                ev3.record()
-                prof.append((n_active, ev0, ev1, ev2, ev3))
+                ev4 = torch.cuda.Event(enable_timing=True)
+                ev4.record()
+                prof.append((n_active, ev0, ev1, ev2, ev3, ev4))
             if self._staged_slot is not None:
                 consumed = torch.cuda.Event()
                 consumed.record()
