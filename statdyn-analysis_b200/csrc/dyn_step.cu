@@ -26,6 +26,7 @@ struct StepArgs {
     double* partials;    // double[n_origins][n_parts][SDB_NSUM]
     const double (*atan_tab)[2];
     int n_parts;
+    int full_parts;  // number of complete 256-molecule tiles (a partial last tile may follow)
     int ov_on;  // bracketed overlap selection: count keys above the brackets, collect candidates
     SdbOvWorkspace ov;
 };
@@ -33,10 +34,10 @@ struct StepArgs {
 
 // cos(x) for x >= 0 with ~1e-7 absolute error: two-constant Cody-Waite reduction to [-pi, pi], then
 // cos r = 1 - 2 sin^2(r/2) with an odd polynomial for sin on [-pi/2, pi/2].  Used for the rot1/rot2
-// means only (rtol 1e-5 on a mean of N terms); huge arguments fall back to cosf.
+// means only (rtol 1e-5 on a mean of N terms).
 __device__ __forceinline__ float sdb_cos_reduced(float x)
 {
-    if (x > 8192.0f) return cosf(x);
+    // |x| up to ~1e5 rad keeps the stated accuracy (k * 6.28125 is exact for k < 2^16)
     const float k = rintf(x * 0.15915494309189535f);
     float r = fmaf(-k, 6.28125f, x);
     r = fmaf(-k, 1.9353071795864769e-3f, r);
@@ -88,20 +89,28 @@ __device__ __forceinline__ uint32_t sdb_track(const SdbDynParams& p, uint32_t fl
     return fl;
 }
 
-__global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const StepArgs a)
+struct StepShared {
+    float red[SDB_BLOCK_WARPS][SDB_NFSUM][33];
+    alignas(16) float wx[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
+    alignas(16) float wy[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
+    alignas(16) double al[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
+    uint32_t cand[SDB_BLOCK_WARPS][3][SDB_OV_STAGE];  // staged overlap candidates (idx, d2, |dtheta|)
+};
+
+// One warp tile (256 molecules) of one segment.  TAIL: the tile is the partial last one (bounds checks).
+template <bool SUMS, bool OV, bool TRACK, bool TAIL>
+__device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh, const int part)
 {
-    __shared__ float red[SDB_BLOCK_WARPS][SDB_NFSUM][33];
-    __shared__ __align__(16) float s_wx[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
-    __shared__ __align__(16) float s_wy[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
-    __shared__ __align__(16) double s_al[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
-    __shared__ uint32_t s_cand[SDB_BLOCK_WARPS][3][SDB_OV_STAGE];  // staged overlap candidates (idx, d2, |dtheta|)
+    auto& red = sh.red;
+    auto& s_wx = sh.wx;
+    auto& s_wy = sh.wy;
+    auto& s_al = sh.al;
+    auto& s_cand = sh.cand;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int part = blockIdx.x * SDB_BLOCK_WARPS + warp;  // warp tile index
     const int n = a.p.n;
     const long stride = a.p.stride;
-    if (part * SDB_WARP_MOLS >= n) return;
 
     const SdbSegment seg = a.segments[blockIdx.y];
     const float* prev = static_cast<const float*>(seg.d_prev);
@@ -214,12 +223,13 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
             done_pattern |= 1u << tr.bit;
         }
     }
-    const bool track = a.p.n_trackers > 0;
-    const bool do_sums = a.p.do_sums != 0;
+    constexpr bool track = TRACK, do_sums = SUMS, ov = OV && SUMS;
     int live_count = 0;
 #pragma unroll
     for (int g = 0; g < SDB_GROUPS; ++g) live_count += max(0, min(SDB_LANE_MOLS, n - j0[g]));
     const int live_warp = __reduce_add_sync(0xffffffffu, live_count);
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
+    const float com_cut = a.p.com_cut_lt;
 
     // ---- stream the per-origin state ----------------------------------------------------------
     for (int oi = 0; oi < seg.count; ++oi) {
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
             if (do_sums && lane < SDB_NSUM) {
                 double v = 0.0;  // all sums vanish except cos(0) = 1 terms and the |dr| < d count
                 if (lane == SDB_S_COS || lane == SDB_S_COS2) v = (double)live_warp;
-                if (lane == SDB_S_COMSTRUCT && a.p.com_cut_lt > 0.f) v = (double)live_warp;
+                if (lane == SDB_S_COMSTRUCT && com_cut > 0.f) v = (double)live_warp;
                 if (lane == SDB_S_BADQUAT) v = (double)bad_warp;
                 if (lane < SDB_NFSUM || lane == SDB_S_COMSTRUCT || lane == SDB_S_BADQUAT || lane >= SDB_S_OV_RABOVE)
                     out[lane] = v;
@@ -264,15 +274,13 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
         for (int v = 0; v < SDB_NFSUM; ++v) acc[v] = 0.f;
         int com_count = 0;
         // overlap: keys above the bracket of each array, and molecules inside a bracket (candidates)
-        const bool ov = a.ov_on && do_sums;
         float4 br = make_float4(0.f, INFINITY, 0.f, INFINITY);  // lo_r, hi_r, lo_t, hi_t
         if (ov) br = __ldg(reinterpret_cast<const float4*>(a.ov.brackets) + o);
         int n_ar = 0, n_at = 0, n_both = 0, n_cand = 0;
-        const uint32_t lanemask_lt = (1u << lane) - 1u;
 
 #pragma unroll
         for (int g = 0; g < SDB_GROUPS; ++g) {
-            const bool valid = j0[g] < n;  // only the last warp tile has invalid groups
+            const bool valid = !TAIL || j0[g] < n;  // only the partial last tile has invalid groups
             float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), dy = dx, dt = dx;
             uint32_t fl4 = 0;
             if (valid) {
@@ -292,52 +300,57 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
             const float wx[4] = {vwx.x, vwx.y, vwx.z, vwx.w};
             const float wy[4] = {vwy.x, vwy.y, vwy.z, vwy.w};
             const double alpha[4] = {va0.x, va0.y, va1.x, va1.y};
-            uint32_t fl4_new = fl4;
+            float d2[4], th[4];
+            bool loud = false;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float d2, th;
-                sdb_apply_increment(ddx[e], ddy[e], ddt[e], wx[e], wy[e], alpha[e], d2, th);
-                const bool live = j0[g] + e < n;
+                sdb_apply_increment(ddx[e], ddy[e], ddt[e], wx[e], wy[e], alpha[e], d2[e], th[e]);
+                const bool live = !TAIL || j0[g] + e < n;
                 if (do_sums && live) {
-                    const float t2 = th * th;
-                    const float c = sdb_cos_reduced(th);
-                    acc[SDB_S_DISP] += sdb_sqrt_approx(d2);
-                    acc[SDB_S_DISP2] += d2;
-                    acc[SDB_S_DISP4] = fmaf(d2, d2, acc[SDB_S_DISP4]);
-                    acc[SDB_S_ROT] += th;
+                    const float t2 = th[e] * th[e];
+                    const float c = sdb_cos_reduced(th[e]);
+                    acc[SDB_S_DISP] += sdb_sqrt_approx(d2[e]);
+                    acc[SDB_S_DISP2] += d2[e];
+                    acc[SDB_S_DISP4] = fmaf(d2[e], d2[e], acc[SDB_S_DISP4]);
+                    acc[SDB_S_ROT] += th[e];
                     acc[SDB_S_ROT2] += t2;
                     acc[SDB_S_COS] += c;
                     acc[SDB_S_COS2] += fmaf(2.0f * c, c, -1.0f);
                     acc[SDB_S_ROT4] = fmaf(t2, t2, acc[SDB_S_ROT4]);
-                    acc[SDB_S_D2R2] = fmaf(d2, t2, acc[SDB_S_D2R2]);
-                    com_count += d2 < a.p.com_cut_lt;
+                    acc[SDB_S_D2R2] = fmaf(d2[e], t2, acc[SDB_S_D2R2]);
+                    com_count += d2[e] < com_cut;
                 }
-                if (ov) {  // warp-uniform
-                    const bool ar = live && d2 > br.y, at = live && th > br.w;
+                if (ov) {
+                    const bool ar = live && d2[e] > br.y, at = live && th[e] > br.w;
                     n_ar += ar;
                     n_at += at;
                     n_both += ar && at;
-                    const bool is_cand = live && ((d2 >= br.x && !ar) || (th >= br.z && !at));
+                    const bool is_cand = live && ((d2[e] >= br.x && !ar) || (th[e] >= br.z && !at));
                     const unsigned m = __ballot_sync(0xffffffffu, is_cand);
-                    if (m) {
-                        const int slot = n_cand + __popc(m & lanemask_lt);
-                        if (is_cand && slot < SDB_OV_STAGE) {
-                            s_cand[warp][0][slot] = (uint32_t)(j0[g] + e);
-                            s_cand[warp][1][slot] = __float_as_uint(d2);
-                            s_cand[warp][2][slot] = __float_as_uint(th);
-                        }
-                        n_cand += __popc(m);
+                    const int slot = n_cand + __popc(m & lanemask_lt);
+                    if (is_cand && slot < SDB_OV_STAGE) {
+                        s_cand[warp][0][slot] = (uint32_t)(j0[g] + e);
+                        s_cand[warp][1][slot] = __float_as_uint(d2[e]);
+                        s_cand[warp][2][slot] = __float_as_uint(th[e]);
                     }
+                    n_cand += __popc(m);
                 }
-                if (track && live) {
+                if (track) {
                     const uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
-                    const bool quiet = (d2 < min_cut_d2 && th < min_cut_th && (fl & state1_bits) == 0u) ||
+                    const bool quiet = (d2[e] < min_cut_d2 && th[e] < min_cut_th && (fl & state1_bits) == 0u) ||
                                        (fl == done_pattern && !literal);
-                    if (!quiet) {
-                        const uint32_t fl_new =
-                            sdb_track(a.p, fl, d2, th, sbase + j0[g] + e, stride, org.timediff, literal);
-                        fl4_new = (fl4_new & ~(0xffu << (8 * e))) | (fl_new << (8 * e));
-                    }
+                    loud |= live && !quiet;
+                }
+            }
+            uint32_t fl4_new = fl4;
+            if (track && loud) {  // rare: some tracker of some molecule of this group may change state
+#pragma unroll 1
+                for (int e = 0; e < 4; ++e) {
+                    if (TAIL && j0[g] + e >= n) break;
+                    const uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
+                    const uint32_t fl_new =
+                        sdb_track(a.p, fl, d2[e], th[e], sbase + j0[g] + e, stride, org.timediff, literal);
+                    fl4_new = (fl4_new & ~(0xffu << (8 * e))) | (fl_new << (8 * e));
                 }
             }
             if (valid) {
@@ -372,8 +385,9 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
         }
 
         if (do_sums) {
-            // Per-lane f32 partials (8 molecules) -> fp64 across the warp through shared memory:
-            // lane (v, third) adds every third entry of row v, two shuffles combine the thirds.
+            // Per-lane f32 partials (8 molecules) are summed over a third of the warp in f32 (11 terms,
+            // pairwise) and from there on in fp64: the thirds by shuffle, the warp tiles by
+            // dyn_finalize_kernel.
             __syncwarp();
 #pragma unroll
             for (int v = 0; v < SDB_NFSUM; ++v) red[warp][v][lane] = acc[v];
@@ -381,11 +395,12 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
             double s = 0.0;
             const int v = lane % SDB_NFSUM, third = lane / SDB_NFSUM;
             if (lane < 3 * SDB_NFSUM) {
-#pragma unroll
-                for (int i = 0; i < 11; ++i) {
-                    const int idx = third + 3 * i;
-                    if (idx < 32) s += (double)red[warp][v][idx];
-                }
+                const float* row = &red[warp][v][third];
+                const float p0 = (row[0] + row[3]) + (row[6] + row[9]);
+                const float p1 = (row[12] + row[15]) + (row[18] + row[21]);
+                float p2 = (row[24] + row[27]);
+                if (third + 30 < 32) p2 += row[30];
+                s = (double)((p0 + p1) + p2);
             }
             s += __shfl_down_sync(0xffffffffu, s, SDB_NFSUM) + __shfl_down_sync(0xffffffffu, s, 2 * SDB_NFSUM);
             const int com_warp = __reduce_add_sync(0xffffffffu, com_count);
@@ -408,6 +423,19 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const St
             }
         }
     }
+}
+
+// grid = (warp tiles / 4, segments).  The partial last tile (if any) takes the bounds-checked path.
+template <bool SUMS, bool OV, bool TRACK>
+__global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const StepArgs a)
+{
+    __shared__ StepShared sh;
+    const int part = blockIdx.x * SDB_BLOCK_WARPS + (threadIdx.x >> 5);  // warp tile index
+    if (part >= a.n_parts) return;
+    if (part < a.full_parts)
+        dyn_step_tile<SUMS, OV, TRACK, false>(a, sh, part);
+    else
+        dyn_step_tile<SUMS, OV, TRACK, true>(a, sh, part);
 }
 
 // Sum the per-warp-tile partials of one origin: block = 256 threads = 16 sums x 16 strided readers.
@@ -514,8 +542,17 @@ extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, co
     if (a.ov_on) sdb_ov_layout(d_ov_ws, ov_ws_origins, p.n, &a.ov);
     else a.ov = SdbOvWorkspace{};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    dim3 grid((a.n_parts + SDB_BLOCK_WARPS - 1) / SDB_BLOCK_WARPS, n_segments);
-    dyn_step_kernel<<<grid, SDB_BLOCK_THREADS, 0, s>>>(a);
+    a.full_parts = p.n / SDB_WARP_MOLS;
+    const int variant = (p.do_sums ? 4 : 0) | (a.ov_on ? 2 : 0) | (p.n_trackers > 0 ? 1 : 0);
+    const dim3 grid((a.n_parts + SDB_BLOCK_WARPS - 1) / SDB_BLOCK_WARPS, n_segments);
+    switch (variant) {
+        case 0: dyn_step_kernel<false, false, false><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
+        case 1: dyn_step_kernel<false, false, true><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
+        case 4: dyn_step_kernel<true, false, false><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
+        case 5: dyn_step_kernel<true, false, true><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
+        case 6: dyn_step_kernel<true, true, false><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
+        default: dyn_step_kernel<true, true, true><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
+    }
     SDB_CHECK_LAUNCH("dyn_step_kernel");
     if (p.do_sums) {
         dyn_finalize_kernel<<<n_origins, 256, 0, s>>>(d_partials, a.n_parts, d_sums, a.ov_on);
