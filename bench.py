@@ -310,6 +310,9 @@ def run_gpu(args):
             kern["struct"] += e2.elapsed_time(e3)
             kern["overlap"] += e0.elapsed_time(e1) + e3.elapsed_time(e4)
         h2d, d2h = engine.h2d_bytes, engine.d2h_bytes
+        if world > 1:  # frames enter through rank 0, rows leave through rank 0
+            h2d = 28 * n if host_frames else 0
+            d2h = n_origins * 16 * 8
         del engine, sharded
         torch.cuda.empty_cache()
         return {"ms": ms, "clocks": clocks, "launches": launches, "kern": kern, "h2d": h2d, "d2h": d2h, "rows": last_rows}

@@ -13,26 +13,20 @@
 //               molecules inside a bracket to a per-warp-tile candidate list;
 //   4. resolve  one block per origin selects the exact threshold among the candidates (radix select
 //               on the key offset from lo), breaks ties by molecule index, counts the intersection;
-//   5. exact    origins whose bracket failed (all keys equal, overflow, 1e-9 events) are redone by a
-//               cooperative kernel that radix-selects over the whole array (3 digits of the f32 bit
-//               pattern).  The same kernel serves mobile_overlap() on caller-provided arrays.
+//   5. exact    origins whose bracket failed (all keys equal, overflow, rare sampling misses) are
+//               redone by a kernel that radix-selects over the whole array, one block per origin
+//               (3 digits of the f32 bit pattern).  It also serves mobile_overlap() on caller arrays.
 //
 // Keys: translation d2 = |dr|^2 = fl32(dx^2 + dy^2) -- monotone in the reference's |dr| = sqrt(d2) --
 // and rotation |dtheta|.  Members of a top-k set are the keys above the threshold plus, among keys
 // equal to it, those with the largest molecule indices (numpy's introsort leaves the choice among
 // equal keys unspecified -- parity trap T4; for all-equal arrays this rule gives identical sets for
 // both arrays, i.e. overlap = 1, like the reference).
-#include <cooperative_groups.h>
-
 #include "sdb_internal.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int OV_BINS = 2048;
-constexpr int OV_SEL = 8;  // words per (array) selection record of the exact kernel
-enum { SEL_PREFIX = 0, SEL_REMAINING = 1, SEL_COUNT_EQ = 2, SEL_IDXCUT = 3, SEL_NEED_TIE = 4 };
 
 // =================================================================================================
 // 1. sample
@@ -367,16 +361,14 @@ __global__ void __launch_bounds__(256) ov_intersect_kernel(const ResolveArgs a)
 }
 
 // =================================================================================================
-// 5. exact selection over the whole array (cooperative kernel, one origin of the list at a time)
+// 5. exact selection over the whole array: one block per origin of the list
 // =================================================================================================
 struct ExactArgs {
     const SdbOrigin* origins;
     const uint32_t* list;  // [0] = count, [1..] = origin indices
-    uint32_t* scratch;     // hist[2][2048], sel[2][8], tie[2][n_parts256]
     double* sums;
     int n;
     long stride;
-    int n_parts;  // 256-molecule parts
     uint32_t k;
     int key_mode;  // 0: keys from the (dx, dy, dtheta) planes; 1: plane 0 = displacement, plane 2 = rotation
 };
@@ -393,186 +385,91 @@ __device__ __forceinline__ void ex_keys4(const float* d, long stride, int j, uin
     }
 }
 
-__global__ void __launch_bounds__(256) ov_exact_kernel(const ExactArgs a)
+// Visit (key_r, key_t, index) of every molecule of one origin with the whole block.
+template <class F>
+__device__ __forceinline__ void ex_for_each(const ExactArgs& a, const float* d, F f)
 {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ uint32_t sh[2][OV_BINS];
-    __shared__ uint32_t scratch[256];
-    __shared__ int warp_counts[8];
-    __shared__ int found_part;
-    __shared__ uint32_t found_rem;
-    const uint32_t n_list = a.list[0];
-    uint32_t* hist = a.scratch;
-    uint32_t* sel = hist + 2 * OV_BINS;
-    uint32_t* tie = sel + 2 * OV_SEL;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    for (int j = threadIdx.x * 4; j < a.n; j += blockDim.x * 4) {
+        uint32_t kr[4], kt[4];
+        ex_keys4(d, a.stride, j, kr, kt, a.key_mode);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (j + e < a.n) f(kr[e], kt[e], (uint32_t)(j + e));
+    }
+}
 
-    for (uint32_t li = 0; li < n_list; ++li) {
+// Radix select (most significant digit first, 11 bits per pass) entirely inside one block: the
+// k-th largest f32 bit pattern of each array, then -- if several keys equal it -- the index cut that
+// keeps the largest molecule indices, then the intersection count.  Rare path: it serves origins
+// whose sampled bracket failed (e.g. all keys equal) and mobile_overlap() on caller arrays.
+__global__ void __launch_bounds__(1024) ov_exact_kernel(const ExactArgs a)
+{
+    __shared__ uint32_t hist[2][OV_BINS];
+    __shared__ uint32_t scratch[1024];
+    __shared__ uint32_t total;
+    const uint32_t n_list = a.list[0];
+    for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
         const int o = (int)a.list[1 + li];
         const float* d = a.origins[o].d_delta;
-        for (int i = gtid; i < 2 * OV_BINS + 2 * OV_SEL; i += gsize) hist[i] = 0;
-        if (gtid == 0) a.sums[(long)o * SDB_NSUM + SDB_S_OVERLAP] = 0.0;
-        grid.sync();
-        if (gtid < 2) sel[gtid * OV_SEL + SEL_REMAINING] = a.k;
-        grid.sync();
-
+        uint32_t thr[2] = {0u, 0u}, rem[2] = {a.k, a.k}, eq[2] = {0u, 0u};
         for (int pass = 0; pass < 3; ++pass) {
             const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
             const int upper = pass == 0 ? 31 : (pass == 1 ? 20 : 9);
             const uint32_t mask = pass == 2 ? 511u : 2047u;
-            for (int i = threadIdx.x; i < 2 * OV_BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
+            for (int i = threadIdx.x; i < 2 * OV_BINS; i += blockDim.x) (&hist[0][0])[i] = 0;
             __syncthreads();
-            const uint32_t prefix[2] = {sel[SEL_PREFIX], sel[OV_SEL + SEL_PREFIX]};
-            for (int j = gtid * 4; j < a.n; j += gsize * 4) {
-                uint32_t kr[4], kt[4];
-                ex_keys4(d, a.stride, j, kr, kt, a.key_mode);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (j + e >= a.n) break;
-                    const uint32_t keys[2] = {kr[e], kt[e]};
-#pragma unroll
-                    for (int arr = 0; arr < 2; ++arr)
-                        if (upper >= 31 || (keys[arr] >> upper) == (prefix[arr] >> upper))
-                            atomicAdd(&sh[arr][(keys[arr] >> shift) & mask], 1u);
-                }
-            }
+            ex_for_each(a, d, [&](uint32_t kr, uint32_t kt, uint32_t) {
+                if (upper >= 31 || (kr >> upper) == (thr[0] >> upper)) atomicAdd(&hist[0][(kr >> shift) & mask], 1u);
+                if (upper >= 31 || (kt >> upper) == (thr[1] >> upper)) atomicAdd(&hist[1][(kt >> shift) & mask], 1u);
+            });
             __syncthreads();
-            for (int i = threadIdx.x; i < 2 * OV_BINS; i += blockDim.x) {
-                const uint32_t c = (&sh[0][0])[i];
-                if (c) atomicAdd(hist + i, c);
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                uint32_t bin, above, at_bin;
+                block_pick(hist[x], OV_BINS, rem[x], scratch, bin, above, at_bin);
+                thr[x] |= bin << shift;
+                rem[x] -= above;
+                eq[x] = at_bin;
             }
-            grid.sync();
-            if (blockIdx.x < 2) {  // one block per array picks the digit
-                const int arr = blockIdx.x;
-                uint32_t* s = sel + arr * OV_SEL;
-                for (int i = threadIdx.x; i < OV_BINS; i += blockDim.x) sh[0][i] = hist[arr * OV_BINS + i];
+        }
+        // ties across the cut: keep the rem largest molecule indices (radix select on the index)
+        uint32_t cut[2] = {0u, 0u};
+        const int idx_bits = 32 - __clz(max(a.n - 1, 1));
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            if (eq[x] <= rem[x]) continue;  // block-uniform
+            uint32_t r = rem[x];
+            for (int done = 0; done < idx_bits;) {
+                const int nb = min(11, idx_bits - done), shift = idx_bits - done - nb;
+                for (int i = threadIdx.x; i < OV_BINS; i += blockDim.x) hist[0][i] = 0;
+                __syncthreads();
+                ex_for_each(a, d, [&](uint32_t kr, uint32_t kt, uint32_t idx) {
+                    if ((x == 0 ? kr : kt) != thr[x]) return;
+                    if (done > 0 && (idx >> (shift + nb)) != (cut[x] >> (shift + nb))) return;
+                    atomicAdd(&hist[0][(idx >> shift) & ((1u << nb) - 1u)], 1u);
+                });
                 __syncthreads();
                 uint32_t bin, above, at_bin;
-                const uint32_t remaining = s[SEL_REMAINING];
-                block_pick(sh[0], OV_BINS, remaining, scratch, bin, above, at_bin);
-                if (threadIdx.x == 0) {
-                    s[SEL_PREFIX] |= bin << shift;
-                    s[SEL_REMAINING] = remaining - above;
-                    s[SEL_COUNT_EQ] = at_bin;
-                    if (pass == 2) {
-                        s[SEL_NEED_TIE] = at_bin > remaining - above;
-                        s[SEL_IDXCUT] = 0;
-                    }
-                }
-                for (int i = threadIdx.x; i < OV_BINS; i += blockDim.x) hist[arr * OV_BINS + i] = 0;
-            }
-            grid.sync();
-        }
-
-        // ---- ties across the cut: per-part counts, then the smallest index still inside ----------
-        const bool need[2] = {sel[SEL_NEED_TIE] != 0, sel[OV_SEL + SEL_NEED_TIE] != 0};
-        const uint32_t thr[2] = {sel[SEL_PREFIX], sel[OV_SEL + SEL_PREFIX]};
-        if (need[0] || need[1]) {  // uniform across the grid
-            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-            for (int part = blockIdx.x * 8 + warp; part < a.n_parts; part += gridDim.x * 8) {
-                int c[2] = {0, 0};
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int j = part * 256 + g * 128 + lane * 4;
-                    if (j < a.n) {
-                        uint32_t kr[4], kt[4];
-                        ex_keys4(d, a.stride, j, kr, kt, a.key_mode);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (j + e < a.n) {
-                                c[0] += kr[e] == thr[0];
-                                c[1] += kt[e] == thr[1];
-                            }
-                        }
-                    }
-                }
-                c[0] = __reduce_add_sync(0xffffffffu, c[0]);
-                c[1] = __reduce_add_sync(0xffffffffu, c[1]);
-                if (lane == 0) {
-                    tie[part] = c[0];
-                    tie[a.n_parts + part] = c[1];
-                }
-            }
-            grid.sync();
-            if (blockIdx.x < 2 && need[blockIdx.x]) {
-                const int arr = blockIdx.x;
-                uint32_t* s = sel + arr * OV_SEL;
-                const uint32_t* tcount = tie + arr * a.n_parts;
-                const uint32_t remaining = s[SEL_REMAINING];
-                if (threadIdx.x == 0) found_part = -1;
-                __syncthreads();
-                uint32_t carried = 0;
-                // walk the parts from the end in chunks of 256, carrying the count found so far
-                for (int hi = a.n_parts; hi > 0 && found_part < 0; hi -= 256) {
-                    const int p = hi - 1 - threadIdx.x;  // thread 0 owns the last part of the chunk
-                    const uint32_t mine = p >= 0 ? tcount[p] : 0;
-                    scratch[threadIdx.x] = mine;
-                    __syncthreads();
-                    for (int off = 1; off < 256; off <<= 1) {
-                        const uint32_t add = threadIdx.x >= off ? scratch[threadIdx.x - off] : 0;
-                        __syncthreads();
-                        scratch[threadIdx.x] += add;
-                        __syncthreads();
-                    }
-                    const uint32_t incl = carried + scratch[threadIdx.x], excl = incl - mine;
-                    if (p >= 0 && excl < remaining && incl >= remaining) {
-                        found_part = p;
-                        found_rem = remaining - excl;
-                    }
-                    carried += scratch[255];
-                    __syncthreads();
-                }
-                if (threadIdx.x == 0) {
-                    uint32_t idxcut = 0;
-                    if (found_part >= 0) {
-                        uint32_t want = found_rem;
-                        const int lo = found_part * 256;
-                        const int hi = min(lo + 255, a.n - 1);
-                        for (int j = hi; j >= lo; --j) {
-                            uint32_t key;
-                            if (arr == 0) {
-                                const float dx = d[j], dy = d[a.stride + j];
-                                key = a.key_mode ? __float_as_uint(dx)
-                                                 : __float_as_uint(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-                            } else {
-                                key = __float_as_uint(fabsf(d[2 * a.stride + j]));
-                            }
-                            if (key == thr[arr] && --want == 0) {
-                                idxcut = (uint32_t)j;
-                                break;
-                            }
-                        }
-                    }
-                    s[SEL_IDXCUT] = idxcut;
-                }
-            }
-            grid.sync();
-        }
-
-        // ---- intersection count -------------------------------------------------------------------
-        const uint32_t cut[2] = {sel[SEL_IDXCUT], sel[OV_SEL + SEL_IDXCUT]};
-        int count = 0;
-        for (int j = gtid * 4; j < a.n; j += gsize * 4) {
-            uint32_t kr[4], kt[4];
-            ex_keys4(d, a.stride, j, kr, kt, a.key_mode);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint32_t idx = (uint32_t)(j + e);
-                const bool in_r = kr[e] > thr[0] || (kr[e] == thr[0] && idx >= cut[0]);
-                const bool in_t = kt[e] > thr[1] || (kt[e] == thr[1] && idx >= cut[1]);
-                count += (j + e < a.n) && in_r && in_t;
+                block_pick(hist[0], 1 << nb, r, scratch, bin, above, at_bin);
+                cut[x] |= bin << shift;
+                r -= above;
+                done += nb;
             }
         }
-        count = __reduce_add_sync(0xffffffffu, count);
-        if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = count;
+        // intersection
+        if (threadIdx.x == 0) total = 0;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int total = 0;
-            for (int w = 0; w < 8; ++w) total += warp_counts[w];
-            // integer-valued doubles: exact and independent of the arrival order
-            if (total) atomicAdd(a.sums + (long)o * SDB_NSUM + SDB_S_OVERLAP, (double)total);
-        }
-        grid.sync();
+        uint32_t both = 0;
+        ex_for_each(a, d, [&](uint32_t kr, uint32_t kt, uint32_t idx) {
+            const bool in_r = kr > thr[0] || (kr == thr[0] && idx >= cut[0]);
+            const bool in_t = kt > thr[1] || (kt == thr[1] && idx >= cut[1]);
+            both += in_r && in_t;
+        });
+        both = __reduce_add_sync(0xffffffffu, both);
+        if ((threadIdx.x & 31) == 0 && both) atomicAdd(&total, both);
+        __syncthreads();
+        if (threadIdx.x == 0) a.sums[(long)o * SDB_NSUM + SDB_S_OVERLAP] = (double)total;
+        __syncthreads();
     }
 }
 
@@ -583,38 +480,21 @@ __global__ void ov_fill_list_kernel(uint32_t* list, int n)
     if (i < n) list[1 + i] = (uint32_t)i;
 }
 
-int exact_grid_blocks()
-{
-    static int cached[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && cached[dev]) return cached[dev];
-    int sms = 0, per_sm = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ov_exact_kernel, 256, 0);
-    const int blocks = sms * (per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm));
-    if (dev < 64) cached[dev] = blocks;
-    return blocks;
-}
-
-int launch_exact(const SdbOrigin* d_origins, const uint32_t* d_list, uint32_t* d_scratch, double* d_sums, int n,
-                 int stride, int k, int key_mode, cudaStream_t s)
+int launch_exact(const SdbOrigin* d_origins, const uint32_t* d_list, double* d_sums, int n, int stride, int k,
+                 int key_mode, int max_list, cudaStream_t s)
 {
     ExactArgs a;
     a.origins = d_origins;
     a.list = d_list;
-    a.scratch = d_scratch;
     a.sums = d_sums;
     a.n = n;
     a.stride = stride;
-    a.n_parts = (n + 255) / 256;
     a.k = (uint32_t)k;
     a.key_mode = key_mode;
-    void* args[] = {&a};
-    const int blocks = exact_grid_blocks();
-    sdb_count_launch();
-    return sdb_check_cuda(cudaLaunchCooperativeKernel((void*)ov_exact_kernel, dim3(blocks), dim3(256), args, 0, s),
-                          "ov_exact_kernel");
+    const int blocks = max_list < 148 ? (max_list < 1 ? 1 : max_list) : 148;
+    ov_exact_kernel<<<blocks, 1024, 0, s>>>(a);
+    SDB_CHECK_LAUNCH("ov_exact_kernel");
+    return SDB_OK;
 }
 
 }  // namespace
@@ -708,13 +588,14 @@ extern "C" int sdb_overlap_resolve(const SdbOrigin* d_origins, int32_t n_origins
     ov_intersect_kernel<<<dim3(8, n_origins), 256, 0, s>>>(ra);
     SDB_CHECK_LAUNCH("ov_intersect_kernel");
     // origins whose bracket failed: exact selection over the whole array (no-op when the list is empty)
-    return launch_exact(d_origins, ra.w.fail, ra.w.exact, d_sums, n, stride, k, 0, s);
+    return launch_exact(d_origins, ra.w.fail, d_sums, n, stride, k, 0, n_origins, s);
 }
 
 extern "C" size_t sdb_overlap_scratch_bytes(int32_t n_origins, int32_t n)
 {
     if (n_origins <= 0 || n <= 0) return 0;
-    return sizeof(uint32_t) * (sdb_ov_exact_words(n) + 1 + (size_t)n_origins + 64);
+    (void)n;
+    return sizeof(uint32_t) * (1 + (size_t)n_origins + 64);
 }
 
 extern "C" int sdb_overlap(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride, int32_t key_mode,
@@ -727,8 +608,7 @@ extern "C" int sdb_overlap(const SdbOrigin* d_origins, int32_t n_origins, int32_
     if (n_origins <= 0) return SDB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     uint32_t* list = static_cast<uint32_t*>(d_scratch);
-    uint32_t* scratch = list + ((1 + n_origins + 63) / 64) * 64;
     ov_fill_list_kernel<<<(n_origins + 255) / 256, 256, 0, s>>>(list, n_origins);
     SDB_CHECK_LAUNCH("ov_fill_list_kernel");
-    return launch_exact(d_origins, list, scratch, d_sums, n, stride, k, key_mode, s);
+    return launch_exact(d_origins, list, d_sums, n, stride, k, key_mode, n_origins, s);
 }

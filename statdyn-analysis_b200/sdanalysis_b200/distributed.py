@@ -20,7 +20,6 @@ import numpy as np
 from . import _lib
 
 SDB_NSUM = _lib.SDB_NSUM
-ROW = SDB_NSUM + 2  # gathered rows carry (key, timediff) behind the sums
 
 
 def owner_of(key, world):
@@ -45,7 +44,7 @@ class ShardedDynamics:
     in tests, a stub).  ``max_local`` bounds the number of local origins active in one frame.
     """
 
-    def __init__(self, num_mols, step_fn, max_local, *, device, group=None, depth=2):
+    def __init__(self, num_mols, step_fn, max_local, *, device, group=None, depth=3):
         import torch
         import torch.distributed as dist
 
@@ -60,12 +59,28 @@ class ShardedDynamics:
         self.qoff = (3 * self.n + 3) // 4 * 4
         self.frames = [torch.zeros(frame_floats(self.n), dtype=torch.float32, device=self.device) for _ in range(depth)]
         self._slot = 0
-        # gather buffers: one row block per rank, padded to max_local (+1 header row: count)
-        self._send = torch.zeros((self.max_local + 1, ROW), dtype=torch.float64, device=self.device)
+        # gather buffers: one block of max_local rows per rank; rank 0 keeps `depth` receive sets so a
+        # result can be read while later frames are in flight
+        self._send = [torch.zeros((self.max_local, SDB_NSUM), dtype=torch.float64, device=self.device) for _ in range(depth)]
         self._recv = (
-            [torch.zeros_like(self._send) for _ in range(self.world)] if self.rank == 0 else None
+            [[torch.zeros_like(self._send[0]) for _ in range(self.world)] for _ in range(depth)]
+            if self.rank == 0
+            else None
         )
-        self._pending = None
+        self._start = {}  # origin key -> timestep of its first frame (known to every rank)
+        # frame uploads and broadcasts run on a side stream so that they overlap the kernels of the
+        # previous frame; `_consumed[slot]` marks the end of the kernels that read a frame buffer
+        import os
+
+        self._cuda = self.device.type == "cuda"
+        # Measured on 2 x B200 (round 1): issuing the NCCL broadcast from a side stream so that it
+        # overlaps the kernels of the previous frame slows those kernels down 1.5-8x (independent of
+        # NCCL_MAX_NCHANNELS), so the exchange is issued in-stream by default.
+        self._use_side = self._cuda and os.environ.get("SDB_SHARD_SIDE", "0") == "1"
+        self._async_gather = os.environ.get("SDB_SHARD_ASYNC_GATHER", "1") == "1"
+        self._side = torch.cuda.Stream(device=self.device) if self._use_side else None
+        self._consumed = [None] * depth
+        self._gathers = [None] * depth
 
     # -- frame exchange ---------------------------------------------------------------------------
     def post_frame(self, position=None, orientation=None):
@@ -76,17 +91,31 @@ class ShardedDynamics:
         torch = self.torch
         self._slot = (self._slot + 1) % len(self.frames)
         buf = self.frames[self._slot]
-        if self.rank == 0:
-            if position is None:
-                raise ValueError("rank 0 is the reader rank and must supply the frame")
-            pos = torch.as_tensor(position)
-            quat = torch.as_tensor(orientation)
-            buf[: 3 * self.n].view(self.n, 3).copy_(pos, non_blocking=True)
-            buf[self.qoff : self.qoff + 4 * self.n].view(self.n, 4).copy_(quat, non_blocking=True)
-        work = None
-        if self.world > 1:
-            work = self.dist.broadcast(buf, src=0, group=self.group, async_op=True)
-        return (self._slot, work)
+
+        def exchange():
+            if self.rank == 0:
+                if position is None:
+                    raise ValueError("rank 0 is the reader rank and must supply the frame")
+                pos = torch.as_tensor(position)
+                quat = torch.as_tensor(orientation)
+                buf[: 3 * self.n].view(self.n, 3).copy_(pos, non_blocking=True)
+                buf[self.qoff : self.qoff + 4 * self.n].view(self.n, 4).copy_(quat, non_blocking=True)
+            if self.world > 1:
+                return self.dist.broadcast(buf, src=0, group=self.group, async_op=True)
+            return None
+
+        if not self._use_side:
+            return (self._slot, exchange(), None)
+        with torch.cuda.stream(self._side):
+            consumed = self._consumed[self._slot]
+            if consumed is not None:
+                self._side.wait_event(consumed)  # the kernels that read this buffer have finished
+            work = exchange()
+            if work is not None:
+                work.wait()  # orders the side stream after the broadcast
+            ready = torch.cuda.Event()
+            ready.record(self._side)
+        return (self._slot, None, ready)
 
     def _frame_views(self, slot):
         buf = self.frames[slot]
@@ -102,38 +131,54 @@ class ShardedDynamics:
         origins in the order of ``active``; on the other ranks (or without ``gather``) the local
         triple."""
         torch, dist = self.torch, self.dist
-        slot, work = handle
+        slot, work, ready = handle
         if work is not None:
-            work.wait()  # orders the current stream after the broadcast
+            work.wait()
+        if ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(ready)  # frame uploaded and broadcast
         pos, quat = self._frame_views(slot)
         local = partition(active, self.rank, self.world)
         if len(local) > self.max_local:
             raise ValueError(f"{len(local)} local origins exceed max_local={self.max_local}")
+        for k in active:
+            self._start.setdefault(k, int(timestep))
         keys, timediffs, sums = self.step_fn(timestep, pos, quat, local) if local else ([], [], None)
+        if keys != local:
+            # the engine may reorder origins (grouping by previous sample): restore `local` order
+            order = [keys.index(k) for k in local]
+            sums = sums[torch.tensor(order, device=sums.device)] if sums is not None else None
+            keys, timediffs = [keys[i] for i in order], [timediffs[i] for i in order]
+        if self._use_side:
+            done = torch.cuda.Event()
+            done.record()
+            self._consumed[slot] = done
         if not gather or self.world == 1:
             return lambda: (keys, timediffs, None if sums is None else sums.cpu().numpy())
-        send = self._send
-        send.zero_()
-        send[0, 0] = len(keys)
+        send = self._send[slot % len(self._send)]
+        previous = self._gathers[slot % len(self._send)]
+        if previous is not None:
+            previous.wait()  # the gather that last used these buffers (long finished) is ordered first
         if keys:
-            send[1 : 1 + len(keys), :SDB_NSUM] = sums
-            meta = torch.tensor([[k, t] for k, t in zip(keys, timediffs)], dtype=torch.float64, device=self.device)
-            send[1 : 1 + len(keys), SDB_NSUM:] = meta
-        dist.gather(send, self._recv if self.rank == 0 else None, dst=0, group=self.group)
+            send[: len(keys)].copy_(sums, non_blocking=True)
+        recv = self._recv[slot % len(self._send)] if self.rank == 0 else None
+        gathered = dist.gather(send, recv, dst=0, group=self.group, async_op=True)
+        if not self._async_gather:
+            gathered.wait()
+        self._gathers[slot % len(self._send)] = gathered
         if self.rank != 0:
-            return lambda: (keys, timediffs, None)
-        recv = [r.clone() for r in self._recv]
+            return lambda: (gathered.wait(), (keys, timediffs, None))[1]
+        world, start = self.world, self._start
 
         def collect():
+            gathered.wait()
             rows = {}
-            for block in recv:
-                host = block.cpu().numpy()
-                count = int(host[0, 0])
-                for row in host[1 : 1 + count]:
-                    rows[int(row[SDB_NSUM])] = (int(row[SDB_NSUM + 1]), row[:SDB_NSUM].copy())
-            out_keys = [k for k in active if k in rows]
-            out_td = [rows[k][0] for k in out_keys]
-            out = np.stack([rows[k][1] for k in out_keys]) if out_keys else np.zeros((0, SDB_NSUM))
-            return out_keys, out_td, out
+            for r, block in enumerate(recv):
+                mine = partition(active, r, world)
+                if mine:
+                    host = block[: len(mine)].cpu().numpy()
+                    for k, row in zip(mine, host):
+                        rows[k] = row
+            out = np.stack([rows[k] for k in active]) if active else np.zeros((0, SDB_NSUM))
+            return list(active), [int(timestep) - start[k] for k in active], out
 
         return collect

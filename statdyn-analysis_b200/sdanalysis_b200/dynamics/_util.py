@@ -130,6 +130,7 @@ class TrackedMotion:
     def _to_general(self):
         """Move a planar state into the general layout (first non-planar quaternion seen)."""
         eng = self._engine
+        eng._flush_plan()
         org = eng.origins[0]
         trans, rot = eng.delta_arrays(0)
         prev = org.prev.planes[:, : self.num_particles].cpu().numpy()

@@ -201,7 +201,7 @@ class _PoolFrame:
 
 
 class _Origin:
-    __slots__ = ("key", "timestep", "delta", "flags", "status", "prev", "max_timediff", "updates")
+    __slots__ = ("key", "timestep", "delta", "flags", "status", "prev", "max_timediff", "updates", "ptrs")
 
     def __init__(self, key, timestep):
         self.key = key
@@ -210,6 +210,7 @@ class _Origin:
         self.prev = None
         self.max_timediff = -1
         self.updates = 0
+        self.ptrs = (0, 0, 0)  # raw device pointers of delta / flags / status (cached: data_ptr() is slow)
 
 
 class _Ring:
@@ -229,9 +230,10 @@ class _Ring:
         return self.i, self.bufs[self.i]
 
     def release(self, i):
-        ev = self.torch.cuda.Event()
+        ev = self.events[i]
+        if ev is None:
+            ev = self.events[i] = self.torch.cuda.Event()
         ev.record()
-        self.events[i] = ev
         return ev
 
 
@@ -318,6 +320,7 @@ class DynamicsEngine:
         self._frame_i = 0
         self._staged_slot = None
         self.h2d_bytes = self.d2h_bytes = 0
+        self._plan = None
         self.profile = None  # set to a list to collect (name, start_event, end_event) per kernel group
         self._sites_c = None if self.mol_sites is None else _lib.float_array(self.mol_sites.reshape(-1))
         self.frames_seen = 0
@@ -435,6 +438,7 @@ class DynamicsEngine:
         if self.trackers:
             org.flags = torch.empty(self.stride, dtype=torch.uint8, device=dev)
             org.status = torch.empty((len(self.trackers), self.stride), dtype=torch.int32, device=dev)
+        org.ptrs = (org.delta.data_ptr(), _lib.ptr(org.flags), _lib.ptr(org.status))
 
     def set_trackers(self, definitions):
         """Replace the tracker set; every origin's passage state starts afresh while its accumulated
@@ -458,8 +462,29 @@ class DynamicsEngine:
                 org.status = torch.full((len(self.trackers), self.stride), -1, dtype=torch.int32, device=dev)
             else:
                 org.flags = org.status = None
+            org.ptrs = (org.delta.data_ptr(), _lib.ptr(org.flags), _lib.ptr(org.status))
+        self._plan = None
+
+    def _release_many(self, frame, count):
+        if frame is None:
+            return
+        frame.refs -= count
+        if frame.refs == 0:
+            self._free_frames.append(frame)
+
+    def _flush_plan(self):
+        """Bring the per-origin records up to date after a run of steady-state steps."""
+        plan, self._plan = self._plan, None
+        if plan is None or plan["steps"] == 0:
+            return
+        last = plan["timestep"]
+        for org in plan["ordered"]:
+            org.prev = plan["prev"]
+            org.updates += plan["steps"]
+            org.max_timediff = max(org.max_timediff, last - org.timestep)
 
     def drop_origin(self, key):
+        self._flush_plan()
         org = self.origins.pop(key)
         self._release(org.prev)
 
@@ -485,63 +510,85 @@ class DynamicsEngine:
             else:
                 pos, quat = self._stage_frame(position, orientation)
 
-            # ---- group the active origins by previous sample --------------------------------
-            groups = OrderedDict()
-            fresh = []
-            for key in active:
-                org = self.origins.get(key)
-                if org is None:
-                    org = _Origin(key, timestep)
-                    self._alloc_origin(org)
-                    self.origins[key] = org
-                    fresh.append(org)
-                else:
-                    groups.setdefault(id(org.prev), (org.prev, []))[1].append(org)
-            if zero_step and fresh:
-                raise RuntimeError("zero_step on an origin that does not exist")
+            # ---- descriptors: origins grouped into segments by previous sample ------------------
+            plan = self._plan
+            if (
+                plan is not None
+                and not zero_step
+                and plan["active"] == active
+                and plan["has_quat"] == (quat is not None)
+                and int(timestep) >= plan["timestep"]
+                and chunk is None
+            ):
+                # steady state of the dense schedule: same origins, all sharing the previous frame --
+                # only the time differences and the previous-sample pointer change
+                ordered = plan["ordered"]
+                odesc = plan["odesc"]
+                odesc["timediff"] = int(timestep) - plan["t0"]
+                odesc["flags"] = 0
+                timediffs = odesc["timediff"].tolist()
+                if timediffs and max(timediffs) >= MAX_STATUS:
+                    raise OverflowError("time difference outside [0, 2**32-1): passage times are 32-bit on the device")
+                sdesc = plan["sdesc"]
+                sdesc["d_prev"] = plan["prev"].planes.data_ptr()
+                seg_count_max = plan["seg_count_max"]
+                n_segments = len(sdesc)
+                fast = True
+            else:
+                fast = False
+                self._flush_plan()
+                groups = OrderedDict()
+                fresh = []
+                for key in active:
+                    org = self.origins.get(key)
+                    if org is None:
+                        org = _Origin(key, timestep)
+                        self._alloc_origin(org)
+                        self.origins[key] = org
+                        fresh.append(org)
+                    else:
+                        groups.setdefault(id(org.prev), (org.prev, []))[1].append(org)
+                if zero_step and fresh:
+                    raise RuntimeError("zero_step on an origin that does not exist")
 
-            target_blocks = 148 * 16
-            blocks_per_segment = (self._n_parts + 3) // 4
-            seg_rows = []  # (prev planes ptr, flags, [origins])
-            ordered = []
-            for prev, members in groups.values():
-                flags = 0
-                if zero_step:
-                    flags |= SEG_ZERO_STEP
-                elif quat is None or prev is None or not prev.has_orientation:
-                    flags |= SEG_NO_ROTATION
-                size = chunk or max(8, math.ceil(len(members) * blocks_per_segment / target_blocks))
-                for s in range(0, len(members), size):
-                    part = members[s : s + size]
-                    seg_rows.append((0 if prev is None else prev.planes.data_ptr(), flags, len(ordered), len(part)))
-                    ordered.extend(part)
-            if fresh:
-                flags = SEG_NO_ROTATION if quat is None else 0
-                seg_rows.append((0, flags, len(ordered), len(fresh)))
-                ordered.extend(fresh)
+                target_blocks = 148 * 16
+                blocks_per_segment = (self._n_parts + 3) // 4
+                seg_rows = []  # (previous planes pointer, flags, first, count)
+                ordered = []
+                for prev, members in groups.values():
+                    flags = 0
+                    if zero_step:
+                        flags |= SEG_ZERO_STEP
+                    elif quat is None or prev is None or not prev.has_orientation:
+                        flags |= SEG_NO_ROTATION
+                    size = chunk or max(8, math.ceil(len(members) * blocks_per_segment / target_blocks))
+                    for first in range(0, len(members), size):
+                        part = members[first : first + size]
+                        seg_rows.append((0 if prev is None else prev.planes.data_ptr(), flags, len(ordered), len(part)))
+                        ordered.extend(part)
+                if fresh:
+                    flags = SEG_NO_ROTATION if quat is None else 0
+                    seg_rows.append((0, flags, len(ordered), len(fresh)))
+                    ordered.extend(fresh)
 
-            odesc = np.zeros(n_active, dtype=ORIGIN_DTYPE)
-            timediffs = []
-            for i, org in enumerate(ordered):
-                td = int(timestep) - org.timestep
-                if not 0 <= td < MAX_STATUS:
+                odesc = np.zeros(n_active, dtype=ORIGIN_DTYPE)
+                t0 = np.fromiter((org.timestep for org in ordered), dtype=np.int64, count=n_active)
+                td = int(timestep) - t0
+                if td.min() < 0 or td.max() >= MAX_STATUS:
                     raise OverflowError(
-                        f"time difference {td} outside [0, 2**32-1): passage times are 32-bit on the device"
+                        f"time difference outside [0, 2**32-1): passage times are 32-bit on the device"
                     )
-                fl = 0
-                if org.updates == 0:
-                    fl |= ORIGIN_NEW
-                elif td < org.max_timediff:
-                    fl |= ORIGIN_LITERAL
-                odesc[i] = (
-                    org.delta.data_ptr(),
-                    0 if org.flags is None else org.flags.data_ptr(),
-                    0 if org.status is None else org.status.data_ptr(),
-                    td,
-                    fl,
-                )
-                timediffs.append(td)
-            sdesc = np.array([(p, f, c, fl, 0) for (p, fl, f, c) in seg_rows], dtype=SEGMENT_DTYPE)
+                ptrs = np.array([org.ptrs for org in ordered], dtype=np.uint64)
+                odesc["d_delta"], odesc["d_flags"], odesc["d_status"] = ptrs[:, 0], ptrs[:, 1], ptrs[:, 2]
+                odesc["timediff"] = td
+                odesc["flags"] = [
+                    ORIGIN_NEW if org.updates == 0 else (ORIGIN_LITERAL if t < org.max_timediff else 0)
+                    for org, t in zip(ordered, td.tolist())
+                ]
+                timediffs = td.tolist()
+                sdesc = np.array([(p, f, c, fl, 0) for (p, fl, f, c) in seg_rows], dtype=SEGMENT_DTYPE)
+                seg_count_max = max(row[3] for row in seg_rows)
+                n_segments = len(seg_rows)
 
             ri, pinned = self._desc_ring.acquire()
             ob, sb = odesc.nbytes, sdesc.nbytes
@@ -576,8 +623,8 @@ class DynamicsEngine:
                 # sample the updated keys of every origin and bracket the k-th largest of each array
                 _lib.check(
                     lib.sdb_overlap_prepare(
-                        params, _lib.ptr(pos), _lib.ptr(quat), d_origins, n_active, d_segments, len(seg_rows),
-                        max(row[3] for row in seg_rows), self.overlap_k, ov_ws, self._cap, stream,
+                        params, _lib.ptr(pos), _lib.ptr(quat), d_origins, n_active, d_segments, n_segments,
+                        seg_count_max, self.overlap_k, ov_ws, self._cap, stream,
                     )
                 )
             if prof is not None:
@@ -592,7 +639,7 @@ class DynamicsEngine:
                     d_origins,
                     n_active,
                     d_segments,
-                    len(seg_rows),
+                    n_segments,
                     self._partials.data_ptr(),
                     sums_dev.data_ptr(),
                     ov_ws,
@@ -635,14 +682,50 @@ class DynamicsEngine:
                 self.d2h_bytes = n_active * SDB_NSUM * 8
 
             # ---- bookkeeping -------------------------------------------------------------------
-            for org, td in zip(ordered, timediffs):
-                if not zero_step:
-                    self._release(org.prev)
-                    org.prev = new_prev
-                    new_prev.refs += 1
-                    org.updates += 1
-                    org.max_timediff = max(org.max_timediff, td)
             if not zero_step:
+                if fast:
+                    # the per-origin records are brought up to date lazily (_flush_plan)
+                    plan["steps"] += 1
+                    plan["timestep"] = int(timestep)
+                    new_prev.refs += n_active
+                    self._release_many(plan["prev"], n_active)
+                    plan["prev"] = new_prev
+                else:
+                    for org, td in zip(ordered, timediffs):
+                        self._release(org.prev)
+                        org.prev = new_prev
+                        org.updates += 1
+                        if td > org.max_timediff:
+                            org.max_timediff = td
+                    new_prev.refs += n_active
+                    # a plan for the next frame: valid if the same origins come again
+                    if len({id(o) for o in ordered}) == n_active:
+                        plan_odesc = odesc.copy()
+                        plan_sdesc_rows = []
+                        target_blocks = 148 * 16
+                        blocks_per_segment = (self._n_parts + 3) // 4
+                        size = max(8, math.ceil(n_active * blocks_per_segment / target_blocks))
+                        flags = 0 if quat is not None else SEG_NO_ROTATION
+                        for first in range(0, n_active, size):
+                            plan_sdesc_rows.append((0, first, min(size, n_active - first), flags, 0))
+                        by_key = {org.key: org for org in ordered}
+                        plan_order = [by_key[k] for k in active]
+                        order_ptrs = np.array([org.ptrs for org in plan_order], dtype=np.uint64)
+                        plan_odesc["d_delta"], plan_odesc["d_flags"], plan_odesc["d_status"] = (
+                            order_ptrs[:, 0], order_ptrs[:, 1], order_ptrs[:, 2],
+                        )
+                        self._plan = {
+                            "active": list(active),
+                            "ordered": plan_order,
+                            "odesc": plan_odesc,
+                            "t0": np.fromiter((org.timestep for org in plan_order), dtype=np.int64, count=n_active),
+                            "sdesc": np.array(plan_sdesc_rows, dtype=SEGMENT_DTYPE),
+                            "seg_count_max": max(r[2] for r in plan_sdesc_rows),
+                            "prev": new_prev,
+                            "has_quat": quat is not None,
+                            "timestep": int(timestep),
+                            "steps": 0,
+                        }
                 self.frames_seen += 1
                 self.updates += n_active * self.n
 
