@@ -27,8 +27,9 @@ logger = logging.getLogger(__name__)
 
 
 def _write_table(df: pandas.DataFrame, filename: Path, group: str, append: bool) -> None:
-    """HDF5 like the reference when PyTables is present (``_read.py:57-61``); otherwise the table
-    goes to ``<stem>.<group>.parquet`` / ``.csv`` next to the requested file."""
+    """HDF5 like the reference when PyTables is present (``_read.py:57-61``: one file, one group per
+    table); otherwise parquet / CSV: the ``dynamics`` table goes to ``filename`` itself, any other
+    table to ``<stem>.<group><suffix>`` next to it."""
     filename = Path(filename)
     if filename.suffix in (".h5", ".hdf5", ".hdf"):
         try:
@@ -38,11 +39,13 @@ def _write_table(df: pandas.DataFrame, filename: Path, group: str, append: bool)
             return
         except ImportError:
             logger.warning("PyTables is not installed: writing %s as parquet instead of HDF5", group)
-            filename = filename.with_suffix(f".{group}.parquet")
-    if filename.suffix == ".csv":
-        df.to_csv(filename, mode="a" if append else "w", header=not append, index=False)
+            filename = filename.with_suffix(".parquet")
+    if filename.suffix not in (".parquet", ".csv"):
+        filename = filename.with_suffix(".parquet")
+    target = filename if group == "dynamics" else filename.with_suffix(f".{group}{filename.suffix}")
+    if target.suffix == ".csv":
+        df.to_csv(target, mode="a" if append else "w", header=not append, index=False)
         return
-    target = filename if filename.suffix == ".parquet" else filename.with_suffix(f".{group}.parquet")
     if append and target.exists():
         df = pandas.concat([pandas.read_parquet(target), df], ignore_index=True)
     df.to_parquet(target, index=False)
