@@ -149,6 +149,105 @@ __global__ void __launch_bounds__(256) struct_kernel(const StructArgs a)
     }
 }
 
+// sin^2(theta / 2) through the special-function unit, |theta| <= 16: the half angle is reduced to
+// [-1/2, 1/2] revolutions (one rounding of theta / 4 pi, an exact subtraction), then sin.approx.
+// Absolute error < 2e-6, i.e. < 8e-6 on 2 (1 - cos theta) -- inside the filter margin below.
+__device__ __forceinline__ float sin2_half_fast(float theta)
+{
+    const float x = theta * 0.079577471545947668f;  // theta / (4 pi)
+    const float fr = x - rintf(x);
+    const float sn = __sinf(fr * 6.2831853071795865f);
+    return sn * sn;
+}
+
+// Fast kernel for three sites, mode 0.  Each thread owns 4 consecutive TRANSLATION molecules
+// m0..m0+3, i.e. the 12 consecutive rows i = 3 m0 .. 3 m0 + 11 (row i is translated by molecule
+// i / 3).  Row i = s n + j is site s of rotation molecule j: away from the two places where s
+// changes the 12 rotation angles are 12 consecutive floats (three 16-byte loads when n is a
+// multiple of 4).  Per row:  |e|^2 = |t|^2 + sin^2(theta/2) (4 vy^2 - 4 vy ty).
+__global__ void __launch_bounds__(256) struct3_kernel(const StructArgs a)
+{
+    const int o = blockIdx.y;
+    const float* __restrict__ d = a.origins[o].d_delta;
+    const float* __restrict__ dth = d + 2 * a.stride;
+    const unsigned n = (unsigned)a.n;
+    const float cut = (float)a.cut2;
+    int count = 0;
+    for (unsigned m0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; m0 < n; m0 += gridDim.x * blockDim.x * 4u) {
+        const float4 tx4 = sdb_ldg4(d + m0), ty4 = sdb_ldg4(d + a.stride + m0);
+        const float tx[4] = {tx4.x, tx4.y, tx4.z, tx4.w};
+        const float ty[4] = {ty4.x, ty4.y, ty4.z, ty4.w};
+        const unsigned i0 = 3u * m0;  // host guarantees 3 n < 2^32
+        const unsigned s0 = (i0 >= n) + (i0 >= 2u * n);
+        const unsigned s_last = (i0 + 11u >= n) + (i0 + 11u >= 2u * n);
+        const unsigned j0 = i0 - s0 * n;
+        if (m0 + 4u <= n && s0 == s_last && (j0 & 3u) == 0u) {
+            const float vx = s0 == 0u ? a.sx[0] : (s0 == 1u ? a.sx[1] : a.sx[2]);
+            const float vy = s0 == 0u ? a.sy[0] : (s0 == 1u ? a.sy[1] : a.sy[2]);
+            const float c4 = 4.0f * vy * vy, b4 = 4.0f * vy;
+            const float vmargin = 8e-6f * (1.0f + 8.0f * vy * vy);
+            float t2[4], mg[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                t2[e] = fmaf(tx[e], tx[e], ty[e] * ty[e]);
+                mg[e] = fmaf(8e-6f, t2[e], vmargin);
+            }
+            float th[12];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float4 v = sdb_ldg4(dth + j0 + 4 * q);
+                th[4 * q] = v.x; th[4 * q + 1] = v.y; th[4 * q + 2] = v.z; th[4 * q + 3] = v.w;
+            }
+            unsigned near = 0u;  // rows the fast filter cannot decide (within the margin, or |theta| > 16)
+#pragma unroll
+            for (int r = 0; r < 12; ++r) {
+                const int e = r / 3;
+                const float e2 = fmaf(sin2_half_fast(th[r]), fmaf(-b4, ty[e], c4), t2[e]);
+                const bool undecided = !(fabsf(e2 - cut) > mg[e]) || fabsf(th[r]) > 16.0f;
+                near |= (unsigned)undecided << r;
+                count += (e2 < cut) && !undecided;
+            }
+            while (near) {  // about one row in 1e5
+                const unsigned r = __ffs(near) - 1u;
+                near &= near - 1u;
+                const unsigned m = m0 + r / 3u;
+                const float theta = __ldg(dth + j0 + r), txm = __ldg(d + m), tym = __ldg(d + a.stride + m);
+                const float t2m = fmaf(txm, txm, tym * tym);
+                const float e2 = fmaf(two_one_minus_cos(theta), vy * (vy - tym), t2m);
+                bool inside = e2 < cut;
+                if (!(fabsf(e2 - cut) > 8e-6f * (t2m + 1.0f + 8.0f * vy * vy)))
+                    inside = struct_row_exact(theta, (double)txm, (double)tym, (double)vx, (double)vy, a.cut2);
+                count += inside;
+            }
+        } else {  // a site boundary, the last molecules, or n not a multiple of 4: row by row
+            for (unsigned r = 0; r < 12u; ++r) {
+                const unsigned i = i0 + r, m = m0 + r / 3u;
+                if (m >= n) break;
+                const unsigned s = (i >= n) + (i >= 2u * n);
+                const float theta = __ldg(dth + (i - s * n));
+                const float vx = s == 0u ? a.sx[0] : (s == 1u ? a.sx[1] : a.sx[2]);
+                const float vy = s == 0u ? a.sy[0] : (s == 1u ? a.sy[1] : a.sy[2]);
+                const float txm = __ldg(d + m), tym = __ldg(d + a.stride + m);
+                const float t2 = fmaf(txm, txm, tym * tym);
+                const float e2 = fmaf(two_one_minus_cos(theta), vy * (vy - tym), t2);
+                bool inside = e2 < cut;
+                if (!(fabsf(e2 - cut) > 8e-6f * (t2 + 1.0f + 8.0f * vy * vy)))
+                    inside = struct_row_exact(theta, (double)txm, (double)tym, (double)vx, (double)vy, a.cut2);
+                count += inside;
+            }
+        }
+    }
+    count = __reduce_add_sync(0xffffffffu, count);
+    __shared__ int warp_counts[8];
+    if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = count;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int w = 0; w < 8; ++w) total += warp_counts[w];
+        if (total) atomicAdd(a.sums + (long)o * SDB_NSUM + SDB_S_STRUCT, (double)total);
+    }
+}
+
 }  // namespace
 
 extern "C" int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride,
@@ -184,7 +283,9 @@ extern "C" int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t
     if (rc) return rc;
     const int tiles = (n + 1023) / 1024;
     dim3 grid(tiles < 48 ? tiles : 48, n_origins);
-    if (n_sites == 3)
+    if (n_sites == 3 && mode == 0)
+        struct3_kernel<<<grid, 256, 0, s>>>(a);
+    else if (n_sites == 3)
         struct_kernel<3><<<grid, 256, 0, s>>>(a);
     else
         struct_kernel<0><<<grid, 256, 0, s>>>(a);
