@@ -34,7 +34,8 @@ struct StepArgs {
 
 // cos(x) for x >= 0 with ~1e-7 absolute error: two-constant Cody-Waite reduction to [-pi, pi], then
 // cos r = 1 - 2 sin^2(r/2) with an odd polynomial for sin on [-pi/2, pi/2].  Used for the rot1/rot2
-// means only (rtol 1e-5 on a mean of N terms).
+// means only (rtol 1e-5 on a mean of N terms; the special-function unit's cos.approx is biased by
+// ~5e-8, which shows in rot2 when it is close to zero).
 __device__ __forceinline__ float sdb_cos_reduced(float x)
 {
     // |x| up to ~1e5 rad keeps the stated accuracy (k * 6.28125 is exact for k < 2^16)
@@ -60,78 +61,138 @@ __device__ __forceinline__ float sdb_sqrt_approx(float x)
 
 // Slow path of the passage trackers (something may change for this molecule):
 // MolecularRelaxation.add relaxations.py:209-218, LastMolecularRelaxation.add :238-289.
-__device__ __forceinline__ uint32_t sdb_track(const SdbDynParams& p, uint32_t fl, float d2, float th, uint32_t* status,
-                                           long stride, uint32_t timediff, bool literal)
+// Not inlined: it runs for the few molecules that are near a threshold; `tr` points into the kernel
+// parameter block (__grid_constant__).
+__device__ __noinline__ uint32_t sdb_track(const SdbTracker* __restrict__ tr, int n_trackers, uint32_t fl, float d2,
+                                           float th, uint32_t* status, long stride, uint32_t timediff, bool literal)
 {
 #pragma unroll 1
-    for (int t = 0; t < p.n_trackers; ++t) {
-        const SdbTracker tr = p.trackers[t];
-        const float val = tr.is_rotation ? th : d2;
+    for (int t = 0; t < n_trackers; ++t, ++tr) {
+        const float val = tr->is_rotation ? th : d2;
         uint32_t* st_word = status + (long)t * stride;
-        if (!tr.is_last) {
-            if (val >= tr.cut_gt) {
-                const bool fired = (fl >> tr.bit) & 1u;
+        if (!tr->is_last) {
+            if (val >= tr->cut_gt) {
+                const bool fired = (fl >> tr->bit) & 1u;
                 if (!fired || (literal && *st_word > timediff)) *st_word = timediff;
-                fl |= 1u << tr.bit;
+                fl |= 1u << tr->bit;
             }
         } else {
-            uint32_t s = (fl >> tr.bit) & 3u;
-            if (s == 0 && val >= tr.cut_gt) {
+            uint32_t s = (fl >> tr->bit) & 3u;
+            if (s == 0 && val >= tr->cut_gt) {
                 s = 1;
                 *st_word = timediff;
-            } else if (s == 1 && val < tr.cut_lt) {
+            } else if (s == 1 && val < tr->cut_lt) {
                 s = 0;
             }
-            if (s == 1 && val >= tr.cut_irr) s = 2;
-            fl = (fl & ~(3u << tr.bit)) | (s << tr.bit);
+            if (s == 1 && val >= tr->cut_irr) s = 2;
+            fl = (fl & ~(3u << tr->bit)) | (s << tr->bit);
         }
     }
     return fl;
 }
 
-struct StepShared {
-    float red[SDB_BLOCK_WARPS][SDB_NFSUM][33];
-    alignas(16) float wx[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
-    alignas(16) float wy[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
-    alignas(16) double al[SDB_BLOCK_WARPS][SDB_WARP_MOLS];
-    uint32_t cand[SDB_BLOCK_WARPS][3][SDB_OV_STAGE];  // staged overlap candidates (idx, d2, |dtheta|)
+// ---- bulk asynchronous copies (TMA, 1-D) completing on a shared-memory mbarrier ----------------------
+__device__ __forceinline__ uint32_t sdb_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sdb_mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sdb_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sdb_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sdb_smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void sdb_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sdb_smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(sdb_smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sdb_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "SDB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra SDB_DONE;\n"
+        "bra SDB_WAIT;\n"
+        "SDB_DONE:\n"
+        "}" ::"r"(sdb_smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Per-warp shared memory: a ring of state tiles filled by bulk copies (one origin per stage), the
+// reduction scratch and the staged overlap candidates.  Warps never synchronise with each other.
+constexpr int SDB_STAGES = 3;
+constexpr int SDB_PLANE_BYTES = SDB_WARP_MOLS * 4;                       // 1 KB: one f32 plane of a tile
+constexpr int SDB_STAGE_BYTES = 3 * SDB_PLANE_BYTES + SDB_WARP_MOLS;     // dx, dy, dtheta planes + flag bytes
+struct alignas(128) StepWarpShared {
+    alignas(128) unsigned char stage[SDB_STAGES][SDB_STAGE_BYTES];
+    float red[SDB_NFSUM][33];
+    uint32_t cand[3][SDB_OV_STAGE];  // staged overlap candidates (idx, d2, |dtheta|)
+    alignas(8) uint64_t bar[SDB_STAGES];
 };
 
 // One warp tile (256 molecules) of one segment.  TAIL: the tile is the partial last one (bounds checks).
 template <bool SUMS, bool OV, bool TRACK, bool TAIL>
-__device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh, const int part)
+__device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared& sh, const int part)
 {
-    auto& red = sh.red;
-    auto& s_wx = sh.wx;
-    auto& s_wy = sh.wy;
-    auto& s_al = sh.al;
-    auto& s_cand = sh.cand;
-
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const int n = a.p.n;
     const long stride = a.p.stride;
 
     const SdbSegment seg = a.segments[blockIdx.y];
     const float* prev = static_cast<const float*>(seg.d_prev);
     const bool zero_step = (seg.flags & SDB_SEG_ZERO_STEP) != 0 || a.pos == nullptr;
+    const long tile0 = (long)part * SDB_WARP_MOLS;
+    // rows of this tile inside the padded planes (a multiple of 4)
+    const uint32_t plane_bytes = 4u * (uint32_t)min((long)SDB_WARP_MOLS, stride - tile0);
+    const uint32_t flag_bytes = (TRACK && !TAIL) ? (uint32_t)SDB_WARP_MOLS : 0u;
 
-    // ---- phase 1: per-segment increments for this lane's 8 molecules, parked in shared memory -----
+    // ---- start the pipeline: bulk copies of the first origins' state tiles -----------------------
+    auto issue = [&](int oi, int slot) {  // lane 0 only
+        const SdbOrigin* od = a.origins + seg.first + oi;
+        const float* dsrc = od->d_delta + tile0;
+        uint64_t* bar = &sh.bar[slot];
+        unsigned char* dst = sh.stage[slot];
+        sdb_mbar_expect_tx(bar, 3u * plane_bytes + flag_bytes);
+        sdb_bulk_load(dst, dsrc, plane_bytes, bar);
+        sdb_bulk_load(dst + SDB_PLANE_BYTES, dsrc + stride, plane_bytes, bar);
+        sdb_bulk_load(dst + 2 * SDB_PLANE_BYTES, dsrc + 2 * stride, plane_bytes, bar);
+        if (flag_bytes) sdb_bulk_load(dst + 3 * SDB_PLANE_BYTES, od->d_flags + tile0, flag_bytes, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < SDB_STAGES; ++s) sdb_mbar_init(&sh.bar[s], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < SDB_STAGES - 1; ++s)
+            if (s < seg.count) issue(s, s);
+    }
+
+    // ---- phase 1: per-segment increments of this lane's 8 molecules, kept in registers ----------
     //   w = box.wrap(prev - cur)  (f32, freud operation order)     _util.py:149
     //   alpha = to_euler(q / q_prev)[0]  (f64)                     _util.py:150-153
     int j0[SDB_GROUPS];
+    float wx[SDB_GROUPS][4], wy[SDB_GROUPS][4];
+    double al[SDB_GROUPS][4];
     int bad = 0;
     const bool rotate = (seg.flags & SDB_SEG_NO_ROTATION) == 0 && !zero_step;
-#pragma unroll 1
+#pragma unroll
     for (int g = 0; g < SDB_GROUPS; ++g) {
         const int jg = part * SDB_WARP_MOLS + g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
+        j0[g] = jg;
         float cx[4], cy[4], cw[4], cz[4];
         if (zero_step || jg >= n) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 cx[e] = 0.f; cy[e] = 0.f; cw[e] = 1.f; cz[e] = 0.f;
             }
-        } else if (jg + SDB_LANE_MOLS <= n) {
+        } else if (!TAIL || jg + SDB_LANE_MOLS <= n) {
             const float4 p0 = sdb_ldg4(a.pos + 3L * jg);
             const float4 p1 = sdb_ldg4(a.pos + 3L * jg + 4);
             const float4 p2 = sdb_ldg4(a.pos + 3L * jg + 8);
@@ -183,33 +244,23 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
                 px[e] = cx[e]; py[e] = cy[e]; pw[e] = cw[e]; pz[e] = cz[e];
             }
         }
-        float wx[4], wy[4];
-        double al[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            sdb_wrap2d(a.p.lx, a.p.ly, a.p.xy, SDB_FSUB(px[e], cx[e]), SDB_FSUB(py[e], cy[e]), wx[e], wy[e]);
-            al[e] = 0.0;
+            sdb_wrap2d(a.p.lx, a.p.ly, a.p.xy, SDB_FSUB(px[e], cx[e]), SDB_FSUB(py[e], cy[e]), wx[g][e], wy[g][e]);
+            al[g][e] = 0.0;
             if (rotate) {
                 int b;
-                al[e] = sdb_rot_increment(cw[e], cz[e], pw[e], pz[e], a.atan_tab, b);
+                al[g][e] = sdb_rot_increment(cw[e], cz[e], pw[e], pz[e], a.atan_tab, b);
                 bad += (b != 0) & (jg + e < n);
             }
         }
-        const int base = g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
-        *reinterpret_cast<float4*>(&s_wx[warp][base]) = make_float4(wx[0], wx[1], wx[2], wx[3]);
-        *reinterpret_cast<float4*>(&s_wy[warp][base]) = make_float4(wy[0], wy[1], wy[2], wy[3]);
-        *reinterpret_cast<double2*>(&s_al[warp][base]) = make_double2(al[0], al[1]);
-        *reinterpret_cast<double2*>(&s_al[warp][base + 2]) = make_double2(al[2], al[3]);
     }
-#pragma unroll
-    for (int g = 0; g < SDB_GROUPS; ++g)
-        j0[g] = part * SDB_WARP_MOLS + g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
     const int bad_warp = __reduce_add_sync(0xffffffffu, bad);
-    __syncwarp();
 
     // ---- tracker pre-digestion (uniform across the grid) ------------------------------------------
-    // A molecule's flag byte cannot change when (a) it is below every "greater than" cut and no
-    // last-passage tracker is in state 1, or (b) every tracker has reached its final state.
+    // A group of 4 molecules cannot change its flag bytes when (a) all four are below every "greater
+    // than" cut and no last-passage tracker is in state 1, or (b) every tracker of all four has
+    // reached its final state.
     float min_cut_d2 = INFINITY, min_cut_th = INFINITY;
     uint32_t state1_bits = 0, done_pattern = 0;
     for (int t = 0; t < a.p.n_trackers; ++t) {
@@ -223,6 +274,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
             done_pattern |= 1u << tr.bit;
         }
     }
+    const uint32_t state1_x4 = state1_bits * 0x01010101u, done_x4 = done_pattern * 0x01010101u;
     constexpr bool track = TRACK, do_sums = SUMS, ov = OV && SUMS;
     int live_count = 0;
 #pragma unroll
@@ -230,15 +282,26 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
     const int live_warp = __reduce_add_sync(0xffffffffu, live_count);
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float com_cut = a.p.com_cut_lt;
+    __syncwarp();  // barrier initialisation is visible to every lane
 
     // ---- stream the per-origin state ----------------------------------------------------------
+    int slot = 0;            // stage of origin oi
+    uint32_t parity = 0;     // phase parity of that stage's barrier
+    int pf_slot = SDB_STAGES - 1;  // stage the next prefetch goes to
     for (int oi = 0; oi < seg.count; ++oi) {
         const int o = seg.first + oi;
+        // the stage consumed in the previous iteration is free: prefetch origin oi + STAGES - 1 into it
+        if (lane == 0 && oi + SDB_STAGES - 1 < seg.count) issue(oi + SDB_STAGES - 1, pf_slot);
+        pf_slot = pf_slot + 1 == SDB_STAGES ? 0 : pf_slot + 1;
         const SdbOrigin org = a.origins[o];
         float* dbase = org.d_delta;
         uint8_t* fbase = org.d_flags;
         uint32_t* sbase = org.d_status;
         double* out = a.partials + ((long)o * a.n_parts + part) * SDB_NSUM;
+        const unsigned char* st = sh.stage[slot];
+        sdb_mbar_wait(&sh.bar[slot], parity);
+        slot = slot + 1 == SDB_STAGES ? 0 : slot + 1;
+        parity ^= (slot == 0);
 
         if (org.flags & SDB_ORIGIN_NEW) {
             // Dynamics.from_frame / Relaxations.from_frame followed by the first compute_all / add with
@@ -265,6 +328,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
                 if (lane < SDB_NFSUM || lane == SDB_S_COMSTRUCT || lane == SDB_S_BADQUAT || lane >= SDB_S_OV_RABOVE)
                     out[lane] = v;
             }
+            __syncwarp();
             continue;
         }
         const bool literal = org.flags & SDB_ORIGIN_LITERAL;
@@ -284,27 +348,22 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
             float4 dx = make_float4(0.f, 0.f, 0.f, 0.f), dy = dx, dt = dx;
             uint32_t fl4 = 0;
             if (valid) {
-                dx = sdb_ld_stream4(dbase + j0[g]);
-                dy = sdb_ld_stream4(dbase + stride + j0[g]);
-                dt = sdb_ld_stream4(dbase + 2 * stride + j0[g]);
-                if (track) fl4 = __ldcs(reinterpret_cast<const uint32_t*>(fbase + j0[g]));
+                const int off = (g * 32 + lane) * 16;
+                dx = *reinterpret_cast<const float4*>(st + off);
+                dy = *reinterpret_cast<const float4*>(st + SDB_PLANE_BYTES + off);
+                dt = *reinterpret_cast<const float4*>(st + 2 * SDB_PLANE_BYTES + off);
+                if (track) {
+                    if (TAIL) fl4 = __ldcs(reinterpret_cast<const uint32_t*>(fbase + j0[g]));
+                    else fl4 = *reinterpret_cast<const uint32_t*>(st + 3 * SDB_PLANE_BYTES + (g * 32 + lane) * 4);
+                }
             }
             float ddx[4] = {dx.x, dx.y, dx.z, dx.w};
             float ddy[4] = {dy.x, dy.y, dy.z, dy.w};
             float ddt[4] = {dt.x, dt.y, dt.z, dt.w};
-            const int sbase_i = g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
-            const float4 vwx = *reinterpret_cast<const float4*>(&s_wx[warp][sbase_i]);
-            const float4 vwy = *reinterpret_cast<const float4*>(&s_wy[warp][sbase_i]);
-            const double2 va0 = *reinterpret_cast<const double2*>(&s_al[warp][sbase_i]);
-            const double2 va1 = *reinterpret_cast<const double2*>(&s_al[warp][sbase_i + 2]);
-            const float wx[4] = {vwx.x, vwx.y, vwx.z, vwx.w};
-            const float wy[4] = {vwy.x, vwy.y, vwy.z, vwy.w};
-            const double alpha[4] = {va0.x, va0.y, va1.x, va1.y};
             float d2[4], th[4];
-            bool loud = false;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                sdb_apply_increment(ddx[e], ddy[e], ddt[e], wx[e], wy[e], alpha[e], d2[e], th[e]);
+                sdb_apply_increment(ddx[e], ddy[e], ddt[e], wx[g][e], wy[g][e], al[g][e], d2[e], th[e]);
                 const bool live = !TAIL || j0[g] + e < n;
                 if (do_sums && live) {
                     const float t2 = th[e] * th[e];
@@ -315,7 +374,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
                     acc[SDB_S_ROT] += th[e];
                     acc[SDB_S_ROT2] += t2;
                     acc[SDB_S_COS] += c;
-                    acc[SDB_S_COS2] += fmaf(2.0f * c, c, -1.0f);
+                    acc[SDB_S_COS2] = fmaf(c, c, acc[SDB_S_COS2]);  // sum cos^2; 2 s - n at the end
                     acc[SDB_S_ROT4] = fmaf(t2, t2, acc[SDB_S_ROT4]);
                     acc[SDB_S_D2R2] = fmaf(d2[e], t2, acc[SDB_S_D2R2]);
                     com_count += d2[e] < com_cut;
@@ -327,30 +386,35 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
                     n_both += ar && at;
                     const bool is_cand = live && ((d2[e] >= br.x && !ar) || (th[e] >= br.z && !at));
                     const unsigned m = __ballot_sync(0xffffffffu, is_cand);
-                    const int slot = n_cand + __popc(m & lanemask_lt);
-                    if (is_cand && slot < SDB_OV_STAGE) {
-                        s_cand[warp][0][slot] = (uint32_t)(j0[g] + e);
-                        s_cand[warp][1][slot] = __float_as_uint(d2[e]);
-                        s_cand[warp][2][slot] = __float_as_uint(th[e]);
+                    if (m) {
+                        const int cs = n_cand + __popc(m & lanemask_lt);
+                        if (is_cand && cs < SDB_OV_STAGE) {
+                            sh.cand[0][cs] = (uint32_t)(j0[g] + e);
+                            sh.cand[1][cs] = __float_as_uint(d2[e]);
+                            sh.cand[2][cs] = __float_as_uint(th[e]);
+                        }
+                        n_cand += __popc(m);
                     }
-                    n_cand += __popc(m);
-                }
-                if (track) {
-                    const uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
-                    const bool quiet = (d2[e] < min_cut_d2 && th[e] < min_cut_th && (fl & state1_bits) == 0u) ||
-                                       (fl == done_pattern && !literal);
-                    loud |= live && !quiet;
                 }
             }
             uint32_t fl4_new = fl4;
-            if (track && loud) {  // rare: some tracker of some molecule of this group may change state
-#pragma unroll 1
-                for (int e = 0; e < 4; ++e) {
-                    if (TAIL && j0[g] + e >= n) break;
-                    const uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
-                    const uint32_t fl_new =
-                        sdb_track(a.p, fl, d2[e], th[e], sbase + j0[g] + e, stride, org.timediff, literal);
-                    fl4_new = (fl4_new & ~(0xffu << (8 * e))) | (fl_new << (8 * e));
+            if (track) {
+                const float m_d2 = fmaxf(fmaxf(d2[0], d2[1]), fmaxf(d2[2], d2[3]));
+                const float m_th = fmaxf(fmaxf(th[0], th[1]), fmaxf(th[2], th[3]));
+                const bool quiet = (m_d2 < min_cut_d2 && m_th < min_cut_th && (fl4 & state1_x4) == 0u) ||
+                                   (fl4 == done_x4 && !literal);
+                if (valid && !quiet) {  // rare: some tracker of some molecule of this group may change state
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (TAIL && j0[g] + e >= n) break;
+                        const uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
+                        const bool quiet_e = (d2[e] < min_cut_d2 && th[e] < min_cut_th && (fl & state1_bits) == 0u) ||
+                                             (fl == done_pattern && !literal);
+                        if (quiet_e) continue;
+                        const uint32_t fl_new = sdb_track(a.p.trackers, a.p.n_trackers, fl, d2[e], th[e],
+                                                          sbase + j0[g] + e, stride, org.timediff, literal);
+                        fl4_new = (fl4_new & ~(0xffu << (8 * e))) | (fl_new << (8 * e));
+                    }
                 }
             }
             if (valid) {
@@ -373,29 +437,27 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
                 if (base + (uint32_t)n_cand <= (uint32_t)a.ov.cand_cap) {
                     const long row = (long)o * a.ov.cand_cap + base;
                     for (int s = lane; s < n_cand; s += 32) {
-                        a.ov.cand_idx[row + s] = s_cand[warp][0][s];
-                        a.ov.cand_r[row + s] = s_cand[warp][1][s];
-                        a.ov.cand_t[row + s] = s_cand[warp][2][s];
+                        a.ov.cand_idx[row + s] = sh.cand[0][s];
+                        a.ov.cand_r[row + s] = sh.cand[1][s];
+                        a.ov.cand_t[row + s] = sh.cand[2][s];
                     }
                 } else if (lane == 0) {
                     a.ov.cand_cnt[2 * o + 1] = 1u;
                 }
             }
-            __syncwarp();
         }
 
         if (do_sums) {
             // Per-lane f32 partials (8 molecules) are summed over a third of the warp in f32 (11 terms,
             // pairwise) and from there on in fp64: the thirds by shuffle, the warp tiles by
             // dyn_finalize_kernel.
-            __syncwarp();
 #pragma unroll
-            for (int v = 0; v < SDB_NFSUM; ++v) red[warp][v][lane] = acc[v];
+            for (int v = 0; v < SDB_NFSUM; ++v) sh.red[v][lane] = acc[v];
             __syncwarp();
             double s = 0.0;
             const int v = lane % SDB_NFSUM, third = lane / SDB_NFSUM;
             if (lane < 3 * SDB_NFSUM) {
-                const float* row = &red[warp][v][third];
+                const float* row = &sh.red[v][third];
                 const float p0 = (row[0] + row[3]) + (row[6] + row[9]);
                 const float p1 = (row[12] + row[15]) + (row[18] + row[21]);
                 float p2 = (row[24] + row[27]);
@@ -403,6 +465,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
                 s = (double)((p0 + p1) + p2);
             }
             s += __shfl_down_sync(0xffffffffu, s, SDB_NFSUM) + __shfl_down_sync(0xffffffffu, s, 2 * SDB_NFSUM);
+            if (lane == SDB_S_COS2) s = 2.0 * s - (double)live_warp;  // sum (2 cos^2 - 1)
             const int com_warp = __reduce_add_sync(0xffffffffu, com_count);
             if (lane < SDB_NFSUM) {
                 out[lane] = s;
@@ -422,14 +485,16 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepShared& sh,
                 }
             }
         }
+        __syncwarp();  // every lane is done with this stage, the scratch and the candidate buffer
     }
 }
 
 // grid = (warp tiles / 4, segments).  The partial last tile (if any) takes the bounds-checked path.
 template <bool SUMS, bool OV, bool TRACK>
-__global__ void __launch_bounds__(SDB_BLOCK_THREADS, 6) dyn_step_kernel(const StepArgs a)
+__global__ void __launch_bounds__(SDB_BLOCK_THREADS, 4) dyn_step_kernel(const __grid_constant__ StepArgs a)
 {
-    __shared__ StepShared sh;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StepWarpShared& sh = reinterpret_cast<StepWarpShared*>(smem_raw)[threadIdx.x >> 5];
     const int part = blockIdx.x * SDB_BLOCK_WARPS + (threadIdx.x >> 5);  // warp tile index
     if (part >= a.n_parts) return;
     if (part < a.full_parts)
@@ -545,14 +610,30 @@ extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, co
     a.full_parts = p.n / SDB_WARP_MOLS;
     const int variant = (p.do_sums ? 4 : 0) | (a.ov_on ? 2 : 0) | (p.n_trackers > 0 ? 1 : 0);
     const dim3 grid((a.n_parts + SDB_BLOCK_WARPS - 1) / SDB_BLOCK_WARPS, n_segments);
+    constexpr size_t smem = sizeof(StepWarpShared) * SDB_BLOCK_WARPS;
+    auto launch = [&](void (*kernel)(const StepArgs)) -> int {
+        static std::atomic<bool> configured[8][64];  // [variant][device]: opt in to > 48 KB of shared memory once
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 64 || !configured[variant][dev].load(std::memory_order_acquire)) {
+            int rc = sdb_check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                    "dyn_step_kernel: shared memory size");
+            if (rc) return rc;
+            if (dev < 64) configured[variant][dev].store(true, std::memory_order_release);
+        }
+        kernel<<<grid, SDB_BLOCK_THREADS, smem, s>>>(a);
+        return SDB_OK;
+    };
+    int lrc;
     switch (variant) {
-        case 0: dyn_step_kernel<false, false, false><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
-        case 1: dyn_step_kernel<false, false, true><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
-        case 4: dyn_step_kernel<true, false, false><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
-        case 5: dyn_step_kernel<true, false, true><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
-        case 6: dyn_step_kernel<true, true, false><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
-        default: dyn_step_kernel<true, true, true><<<grid, SDB_BLOCK_THREADS, 0, s>>>(a); break;
+        case 0: lrc = launch(dyn_step_kernel<false, false, false>); break;
+        case 1: lrc = launch(dyn_step_kernel<false, false, true>); break;
+        case 4: lrc = launch(dyn_step_kernel<true, false, false>); break;
+        case 5: lrc = launch(dyn_step_kernel<true, false, true>); break;
+        case 6: lrc = launch(dyn_step_kernel<true, true, false>); break;
+        default: lrc = launch(dyn_step_kernel<true, true, true>); break;
     }
+    if (lrc) return lrc;
     SDB_CHECK_LAUNCH("dyn_step_kernel");
     if (p.do_sums) {
         dyn_finalize_kernel<<<n_origins, 256, 0, s>>>(d_partials, a.n_parts, d_sums, a.ov_on);
