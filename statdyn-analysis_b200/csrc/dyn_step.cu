@@ -97,18 +97,6 @@ __device__ __forceinline__ void sdb_mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sdb_smem_addr(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void sdb_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sdb_smem_addr(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void sdb_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     sdb_smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(sdb_smem_addr(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void sdb_mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
@@ -153,26 +141,53 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
     const uint32_t flag_bytes = (TRACK && !TAIL) ? (uint32_t)SDB_WARP_MOLS : 0u;
 
     // ---- start the pipeline: bulk copies of the first origins' state tiles -----------------------
-    auto issue = [&](int oi, int slot) {  // lane 0 only
+    // Executed by the whole (converged) warp with warp-uniform operands; one elected lane issues.
+    auto issue = [&](int oi, int slot) {
         const SdbOrigin* od = a.origins + seg.first + oi;
         const float* dsrc = od->d_delta + tile0;
-        uint64_t* bar = &sh.bar[slot];
-        unsigned char* dst = sh.stage[slot];
-        sdb_mbar_expect_tx(bar, 3u * plane_bytes + flag_bytes);
-        sdb_bulk_load(dst, dsrc, plane_bytes, bar);
-        sdb_bulk_load(dst + SDB_PLANE_BYTES, dsrc + stride, plane_bytes, bar);
-        sdb_bulk_load(dst + 2 * SDB_PLANE_BYTES, dsrc + 2 * stride, plane_bytes, bar);
-        if (flag_bytes) sdb_bulk_load(dst + 3 * SDB_PLANE_BYTES, od->d_flags + tile0, flag_bytes, bar);
+        const uint32_t bar = sdb_smem_addr(&sh.bar[slot]);
+        const uint32_t dst = sdb_smem_addr(sh.stage[slot]);
+        if (TRACK && !TAIL) {
+            const uint8_t* fsrc = od->d_flags + tile0;
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "elect.sync _|p, 0xffffffff;\n"
+                "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%6], %10, [%0];\n"
+                "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%7], %10, [%0];\n"
+                "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%8], %10, [%0];\n"
+                "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%5], [%9], %11, [%0];\n"
+                "}" ::"r"(bar),
+                "r"(3u * plane_bytes + flag_bytes), "r"(dst), "r"(dst + SDB_PLANE_BYTES), "r"(dst + 2 * SDB_PLANE_BYTES),
+                "r"(dst + 3 * SDB_PLANE_BYTES), "l"(dsrc), "l"(dsrc + stride), "l"(dsrc + 2 * stride), "l"(fsrc),
+                "r"(plane_bytes), "r"(flag_bytes)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "elect.sync _|p, 0xffffffff;\n"
+                "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+                "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %8, [%0];\n"
+                "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%6], %8, [%0];\n"
+                "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%7], %8, [%0];\n"
+                "}" ::"r"(bar),
+                "r"(3u * plane_bytes), "r"(dst), "r"(dst + SDB_PLANE_BYTES), "r"(dst + 2 * SDB_PLANE_BYTES), "l"(dsrc),
+                "l"(dsrc + stride), "l"(dsrc + 2 * stride), "r"(plane_bytes)
+                : "memory");
+        }
     };
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < SDB_STAGES; ++s) sdb_mbar_init(&sh.bar[s], 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-        for (int s = 0; s < SDB_STAGES - 1; ++s)
-            if (s < seg.count) issue(s, s);
     }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < SDB_STAGES - 1; ++s)
+        if (s < seg.count) issue(s, s);
 
     // ---- phase 1: per-segment increments of this lane's 8 molecules, kept in registers ----------
     //   w = box.wrap(prev - cur)  (f32, freud operation order)     _util.py:149
@@ -282,7 +297,6 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
     const int live_warp = __reduce_add_sync(0xffffffffu, live_count);
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const float com_cut = a.p.com_cut_lt;
-    __syncwarp();  // barrier initialisation is visible to every lane
 
     // ---- stream the per-origin state ----------------------------------------------------------
     int slot = 0;            // stage of origin oi
@@ -291,7 +305,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
     for (int oi = 0; oi < seg.count; ++oi) {
         const int o = seg.first + oi;
         // the stage consumed in the previous iteration is free: prefetch origin oi + STAGES - 1 into it
-        if (lane == 0 && oi + SDB_STAGES - 1 < seg.count) issue(oi + SDB_STAGES - 1, pf_slot);
+        if (oi + SDB_STAGES - 1 < seg.count) issue(oi + SDB_STAGES - 1, pf_slot);
         pf_slot = pf_slot + 1 == SDB_STAGES ? 0 : pf_slot + 1;
         const SdbOrigin org = a.origins[o];
         float* dbase = org.d_delta;
@@ -340,6 +354,9 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
         // overlap: keys above the bracket of each array, and molecules inside a bracket (candidates)
         float4 br = make_float4(0.f, INFINITY, 0.f, INFINITY);  // lo_r, hi_r, lo_t, hi_t
         if (ov) br = __ldg(reinterpret_cast<const float4*>(a.ov.brackets) + o);
+        const int lo_r = __float_as_int(br.x), hi_r = __float_as_int(br.y);
+        const int lo_t = __float_as_int(br.z), hi_t = __float_as_int(br.w);
+        const uint32_t span_r = (uint32_t)(hi_r - lo_r), span_t = (uint32_t)(hi_t - lo_t);
         int n_ar = 0, n_at = 0, n_both = 0, n_cand = 0;
 
 #pragma unroll
@@ -380,21 +397,25 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
                     com_count += d2[e] < com_cut;
                 }
                 if (ov) {
-                    const bool ar = live && d2[e] > br.y, at = live && th[e] > br.w;
-                    n_ar += ar;
-                    n_at += at;
-                    n_both += ar && at;
-                    const bool is_cand = live && ((d2[e] >= br.x && !ar) || (th[e] >= br.z && !at));
-                    const unsigned m = __ballot_sync(0xffffffffu, is_cand);
-                    if (m) {
-                        const int cs = n_cand + __popc(m & lanemask_lt);
-                        if (is_cand && cs < SDB_OV_STAGE) {
-                            sh.cand[0][cs] = (uint32_t)(j0[g] + e);
-                            sh.cand[1][cs] = __float_as_uint(d2[e]);
-                            sh.cand[2][cs] = __float_as_uint(th[e]);
-                        }
-                        n_cand += __popc(m);
+                    // keys are non-negative floats: their bit patterns order like the values (and like the
+                    // exact kernel's radix select), so "key > hi" is the sign of an integer difference
+                    const int kr = __float_as_int(d2[e]), kt = __float_as_int(th[e]);
+                    const int ar = hi_r - kr, at = hi_t - kt;  // negative <=> above the bracket
+                    const bool in_r = (uint32_t)(kr - lo_r) <= span_r, in_t = (uint32_t)(kt - lo_t) <= span_t;
+                    const bool is_cand = live && (in_r || in_t);
+                    if (live) {
+                        n_ar += (uint32_t)ar >> 31;
+                        n_at += (uint32_t)at >> 31;
+                        n_both += (uint32_t)(ar & at) >> 31;
                     }
+                    const unsigned m = __ballot_sync(0xffffffffu, is_cand);
+                    const int cs = n_cand + __popc(m & lanemask_lt);
+                    if (is_cand && cs < SDB_OV_STAGE) {
+                        sh.cand[0][cs] = (uint32_t)(j0[g] + e);
+                        sh.cand[1][cs] = (uint32_t)kr;
+                        sh.cand[2][cs] = (uint32_t)kt;
+                    }
+                    n_cand += __popc(m);
                 }
             }
             uint32_t fl4_new = fl4;
