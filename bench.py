@@ -267,14 +267,14 @@ def run_gpu(args):
                 results.append(engine.step(ts, pos, quat, all_keys))
             if len(results) > 2:
                 r = results.pop(0)
-                r() if callable(r) else r.rows()
+                r() if callable(r) else r.table()
 
         for i in range(warmup):
             one_step(i, timestep)
             timestep += 1
         while results:
             r = results.pop(0)
-            r() if callable(r) else r.rows()
+            r() if callable(r) else r.table()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -290,7 +290,7 @@ def run_gpu(args):
         last_rows = None
         while results:
             r = results.pop(0)
-            last_rows = r() if callable(r) else r.rows()
+            last_rows = r() if callable(r) else r.table()
         t_end.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -376,8 +376,8 @@ def run_gpu(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": dev["clocks"],
-        "check": {k: dev["rows"][0][k] for k in ("time", "msd", "alpha", "rot1", "overlap", "struct")}
-        if isinstance(dev["rows"], list) and dev["rows"] else None,
+        "check": {k: float(dev["rows"][k][0]) for k in ("time", "msd", "alpha", "rot1", "overlap", "struct")}
+        if isinstance(dev["rows"], dict) else None,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -95,6 +95,12 @@ typedef struct {
                                  (Dynamics.from_frame + first compute_all, read/_read.py:135-152) */
 #define SDB_ORIGIN_LITERAL 2u /* timediff is not larger than every earlier one of this origin: use
                                  the literal read-modify-write of relaxations.py:215-218 */
+#define SDB_ORIGIN_HISTORY 4u /* d_delta is followed by SDB_HISTORY_WORDS 32-bit words (at
+                                 d_delta + 3 * stride, zero-initialised by the caller when the origin is
+                                 created) in which the `overlap` selection keeps the exact thresholds of
+                                 the origin's last two frames; they predict the next bracket, so the
+                                 sampling pass is skipped and ~10x fewer candidates are collected */
+#define SDB_HISTORY_WORDS 16
 
 /* A run of active origins that share the same previous sample (TrackedMotion.previous_position /
  * previous_orientation, _util.py:155-156).  The minimum-image step and the rotation increment are
@@ -167,6 +173,11 @@ int sdb_overlap_prepare(const SdbDynParams* h_params, const float* d_pos, const 
                         int32_t ws_origins, void* stream);
 int sdb_overlap_resolve(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride,
                         int32_t k, void* d_ws, int32_t ws_origins, double* d_sums, void* stream);
+/* Diagnostics of the last sdb_overlap_resolve on this workspace (synchronises the stream): h_out[0] =
+ * origins that needed the exact kernel, h_out[1 + o] = candidates collected for origin o. */
+int sdb_overlap_stats(void* d_ws, int32_t ws_origins, int32_t n, int32_t n_origins, uint32_t* h_out,
+                      void* stream);
+
 /* Stand-alone exact selection over the whole arrays (radix select, cooperative kernel).
  * key_mode 0: keys are computed from the (dx, dy, dtheta) planes of each origin's d_delta
  * (|dr|^2 and |dtheta|); key_mode 1: plane 0 holds non-negative displacement keys and plane 2

@@ -92,8 +92,12 @@ __global__ void __launch_bounds__(128) ov_sample_kernel(const SampleArgs a)
     const int o = seg.first + blockIdx.y;
     const SdbOrigin org = a.origins[o];
     if (org.flags & SDB_ORIGIN_NEW) return;
-    const long j = (long)g * 4 * a.w.sample_stride;
     const long stride = a.p.stride;
+    if (a.w.sample_stride > 1) {  // the bracket of this origin is predicted from its history: no sample needed
+        float lo, hi;
+        if (sdb_predict_bracket(sdb_history(org, stride), org.timediff, 0, rsqrtf((float)a.p.n), lo, hi)) return;
+    }
+    const long j = (long)g * 4 * a.w.sample_stride;
     const float4 vx = sdb_ldg4(org.d_delta + j), vy = sdb_ldg4(org.d_delta + stride + j), vt = sdb_ldg4(org.d_delta + 2 * stride + j);
     float dx[4] = {vx.x, vx.y, vx.z, vx.w}, dy[4] = {vy.x, vy.y, vy.z, vy.w}, dt[4] = {vt.x, vt.y, vt.z, vt.w};
     const float4* incs = reinterpret_cast<const float4*>(a.w.increments) + (long)blockIdx.z * a.w.n_samples + 4 * g;
@@ -157,6 +161,7 @@ __device__ void block_pick(const uint32_t* hist, int nbins, uint32_t remaining, 
 // =================================================================================================
 struct BracketArgs {
     const SdbOrigin* origins;
+    long stride;
     SdbOvWorkspace w;
     uint32_t rank_hi, rank_lo;  // ranks counted from the largest sample value (1 = maximum)
 };
@@ -166,7 +171,25 @@ __global__ void __launch_bounds__(512) ov_bracket_kernel(const BracketArgs a)
     __shared__ uint32_t hist[2][OV_BINS];
     __shared__ uint32_t scratch[512];
     const int arr = blockIdx.x, o = blockIdx.y;
-    if (a.origins[o].flags & SDB_ORIGIN_NEW) return;
+    const SdbOrigin org = a.origins[o];
+    if (org.flags & SDB_ORIGIN_NEW) return;
+    if (a.w.sample_stride > 1) {
+        // both arrays are predicted or neither (the sample kernel tests array 0 only)
+        float lo, hi, lo0, hi0;
+        const uint32_t* hist = sdb_history(org, a.stride);
+        const float inv_sqrt_n = rsqrtf((float)(a.w.n_parts * SDB_WARP_MOLS));
+        if (sdb_predict_bracket(hist, org.timediff, 0, inv_sqrt_n, lo0, hi0)) {
+            if (arr == 0 || !sdb_predict_bracket(hist, org.timediff, 1, inv_sqrt_n, lo, hi)) {
+                if (arr == 0) { lo = lo0; hi = hi0; }
+                else { lo = 0.0f; hi = __uint_as_float(0x7f7fffffu); }  // open bracket: overflow -> exact path
+            }
+            if (threadIdx.x == 0) {
+                a.w.brackets[o * 4 + 2 * arr + 0] = lo;
+                a.w.brackets[o * 4 + 2 * arr + 1] = hi;
+            }
+            return;
+        }
+    }
     const uint32_t* keys = reinterpret_cast<const uint32_t*>(a.w.samples + ((long)o * 2 + arr) * a.w.n_samples);
     const int ns = a.w.n_samples;
     uint32_t prefix[2] = {0u, 0u};
@@ -212,7 +235,35 @@ struct ResolveArgs {
     SdbOvWorkspace w;
     double* sums;
     uint32_t k;
+    long stride;
 };
+
+// Record this frame's exact thresholds in the origin's history (one thread).  `cause`: 0 = the bracket
+// held, 1 = it was too wide (candidate overflow), 2 = it missed the threshold (-> widen the next ones).
+__device__ void ov_record_history(const SdbOrigin& org, long stride, uint32_t cause, uint32_t thr_r, uint32_t thr_t)
+{
+    uint32_t* h = sdb_history(org, stride);
+    if (h == nullptr) return;
+    if (org.flags & SDB_ORIGIN_NEW) {
+        h[SDB_H_VALID] = 0u;
+        h[SDB_H_WIDEN] = 0u;
+        return;
+    }
+    if (cause & 2u) h[SDB_H_WIDEN] = min(h[SDB_H_WIDEN] + 1u, 6u);
+    else if (cause == 1u && h[SDB_H_WIDEN] > 0u) h[SDB_H_WIDEN] -= 1u;
+    const uint32_t valid = h[SDB_H_VALID];
+    if (valid >= 1u && org.timediff > h[SDB_H_TD1]) {
+        h[SDB_H_R0] = h[SDB_H_R1];
+        h[SDB_H_T0] = h[SDB_H_T1];
+        h[SDB_H_TD0] = h[SDB_H_TD1];
+        h[SDB_H_VALID] = 2u;
+    } else if (valid == 0u || org.timediff < h[SDB_H_TD1]) {
+        h[SDB_H_VALID] = 1u;  // first record, or time moved backwards: start afresh
+    }  // same time difference again (zero step): overwrite the last record
+    h[SDB_H_R1] = thr_r;
+    h[SDB_H_T1] = thr_t;
+    h[SDB_H_TD1] = org.timediff;
+}
 
 // Strided walk over an array with 8 independent loads in flight per thread (the walks are latency
 // bound otherwise: ~80k candidates per origin, 512 threads).
@@ -263,7 +314,7 @@ __global__ void __launch_bounds__(512) ov_select_kernel(const ResolveArgs a)
     __syncthreads();
     const uint32_t total = tot;
     if (overflow || need < 1 || need > (long)total) {
-        if (threadIdx.x == 0) sel[RS_FAIL + x] = 1u;
+        if (threadIdx.x == 0) sel[RS_FAIL + x] = overflow ? 1u : 2u;
         return;
     }
 
@@ -325,19 +376,24 @@ __global__ void __launch_bounds__(256) ov_intersect_kernel(const ResolveArgs a)
     const int o = blockIdx.y;
     double* sums = a.sums + (long)o * SDB_NSUM;
     const uint32_t* sel = a.w.select + 8L * o;
-    if (a.origins[o].flags & SDB_ORIGIN_NEW) {
+    const SdbOrigin org = a.origins[o];
+    if (org.flags & SDB_ORIGIN_NEW) {
         // all keys are zero: ties are broken by index for both arrays -> identical sets
-        if (blockIdx.x == 0 && threadIdx.x == 0) sums[SDB_S_OVERLAP] = (double)a.k;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            sums[SDB_S_OVERLAP] = (double)a.k;
+            ov_record_history(org, a.stride, 0u, 0u, 0u);
+        }
         return;
     }
     if (sel[RS_FAIL] | sel[RS_FAIL + 1]) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             const uint32_t slot = atomicAdd(a.w.fail, 1u);
-            a.w.fail[1 + slot] = (uint32_t)o;
+            a.w.fail[1 + slot] = (uint32_t)o;  // the exact kernel records the thresholds
         }
         return;
     }
     const uint32_t thr_r = sel[RS_THR], cut_r = sel[RS_CUT], thr_t = sel[2 + RS_THR], cut_t = sel[2 + RS_CUT];
+    if (blockIdx.x == 0 && threadIdx.x == 0) ov_record_history(org, a.stride, 0u, thr_r, thr_t);
     const uint32_t n_cand = a.w.cand_cnt[2 * o];
     const long row = (long)o * a.w.cand_cap;
     uint32_t both = 0;
@@ -366,6 +422,7 @@ __global__ void __launch_bounds__(256) ov_intersect_kernel(const ResolveArgs a)
 struct ExactArgs {
     const SdbOrigin* origins;
     const uint32_t* list;  // [0] = count, [1..] = origin indices
+    const uint32_t* select;  // select records of the bracketed path (failure causes) or nullptr
     double* sums;
     int n;
     long stride;
@@ -468,7 +525,12 @@ __global__ void __launch_bounds__(1024) ov_exact_kernel(const ExactArgs a)
         both = __reduce_add_sync(0xffffffffu, both);
         if ((threadIdx.x & 31) == 0 && both) atomicAdd(&total, both);
         __syncthreads();
-        if (threadIdx.x == 0) a.sums[(long)o * SDB_NSUM + SDB_S_OVERLAP] = (double)total;
+        if (threadIdx.x == 0) {
+            a.sums[(long)o * SDB_NSUM + SDB_S_OVERLAP] = (double)total;
+            if (a.select && a.key_mode == 0)
+                ov_record_history(a.origins[o], a.stride, a.select[8L * o + RS_FAIL] | a.select[8L * o + RS_FAIL + 1],
+                                  thr[0], thr[1]);
+        }
         __syncthreads();
     }
 }
@@ -480,12 +542,13 @@ __global__ void ov_fill_list_kernel(uint32_t* list, int n)
     if (i < n) list[1 + i] = (uint32_t)i;
 }
 
-int launch_exact(const SdbOrigin* d_origins, const uint32_t* d_list, double* d_sums, int n, int stride, int k,
-                 int key_mode, int max_list, cudaStream_t s)
+int launch_exact(const SdbOrigin* d_origins, const uint32_t* d_list, const uint32_t* d_select, double* d_sums, int n,
+                 int stride, int k, int key_mode, int max_list, cudaStream_t s)
 {
     ExactArgs a;
     a.origins = d_origins;
     a.list = d_list;
+    a.select = d_select;
     a.sums = d_sums;
     a.n = n;
     a.stride = stride;
@@ -548,6 +611,7 @@ extern "C" int sdb_overlap_prepare(const SdbDynParams* h_params, const float* d_
     // ranks (from the top) of the two sample order statistics that bracket the k-th largest key
     BracketArgs ba;
     ba.origins = d_origins;
+    ba.stride = h_params->stride;
     ba.w = sa.w;
     const double n = h_params->n, ns = sa.w.n_samples, p = k / n;
     if (sa.w.sample_stride == 1) {
@@ -578,6 +642,7 @@ extern "C" int sdb_overlap_resolve(const SdbOrigin* d_origins, int32_t n_origins
     ra.origins = d_origins;
     ra.sums = d_sums;
     ra.k = (uint32_t)k;
+    ra.stride = stride;
     sdb_ov_layout(d_ws, ws_origins, n, &ra.w);
     int rc = sdb_check_cuda(cudaMemset2DAsync(d_sums + SDB_S_OVERLAP, SDB_NSUM * sizeof(double), 0, sizeof(double),
                                               (size_t)n_origins, s),
@@ -588,7 +653,28 @@ extern "C" int sdb_overlap_resolve(const SdbOrigin* d_origins, int32_t n_origins
     ov_intersect_kernel<<<dim3(8, n_origins), 256, 0, s>>>(ra);
     SDB_CHECK_LAUNCH("ov_intersect_kernel");
     // origins whose bracket failed: exact selection over the whole array (no-op when the list is empty)
-    return launch_exact(d_origins, ra.w.fail, d_sums, n, stride, k, 0, n_origins, s);
+    return launch_exact(d_origins, ra.w.fail, ra.w.select, d_sums, n, stride, k, 0, n_origins, s);
+}
+
+// Diagnostics of the last sdb_overlap_resolve on this workspace (synchronises the stream):
+// h_out[0] = number of origins that took the exact path, h_out[1 + o] = candidates collected for origin o.
+extern "C" int sdb_overlap_stats(void* d_ws, int32_t ws_origins, int32_t n, int32_t n_origins, uint32_t* h_out,
+                                 void* stream)
+{
+    if (!d_ws || !h_out || n_origins > ws_origins || n <= 0) {
+        sdb_set_error("sdb_overlap_stats: bad argument");
+        return SDB_EINVAL;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SdbOvWorkspace w;
+    sdb_ov_layout(d_ws, ws_origins, n, &w);
+    int rc = sdb_check_cuda(cudaMemcpyAsync(h_out, w.fail, sizeof(uint32_t), cudaMemcpyDeviceToHost, s), "stats: fail");
+    if (rc) return rc;
+    rc = sdb_check_cuda(cudaMemcpy2DAsync(h_out + 1, sizeof(uint32_t), w.cand_cnt, 2 * sizeof(uint32_t), sizeof(uint32_t),
+                                          (size_t)n_origins, cudaMemcpyDeviceToHost, s),
+                        "stats: candidates");
+    if (rc) return rc;
+    return sdb_check_cuda(cudaStreamSynchronize(s), "stats: sync");
 }
 
 extern "C" size_t sdb_overlap_scratch_bytes(int32_t n_origins, int32_t n)
@@ -610,5 +696,5 @@ extern "C" int sdb_overlap(const SdbOrigin* d_origins, int32_t n_origins, int32_
     uint32_t* list = static_cast<uint32_t*>(d_scratch);
     ov_fill_list_kernel<<<(n_origins + 255) / 256, 256, 0, s>>>(list, n_origins);
     SDB_CHECK_LAUNCH("ov_fill_list_kernel");
-    return launch_exact(d_origins, list, d_sums, n, stride, k, key_mode, n_origins, s);
+    return launch_exact(d_origins, list, nullptr, d_sums, n, stride, k, key_mode, n_origins, s);
 }

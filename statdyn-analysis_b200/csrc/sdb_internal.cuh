@@ -79,6 +79,40 @@ struct SdbOvWorkspace {
     int n_samples, sample_stride, n_parts, cand_cap;
 };
 
+// ---- threshold history of one origin (SDB_ORIGIN_HISTORY): words after the three delta planes -------
+//   [0] thr_r1  [1] thr_t1  [2] td1   exact thresholds (f32 bits) and time difference of the last frame
+//   [3] thr_r0  [4] thr_t0  [5] td0   ... of the frame before
+//   [6] valid   number of consecutive successful selections recorded (0, 1, 2)
+//   [7] widen   log2 of the bracket widening factor (grows when a predicted bracket misses the threshold)
+enum { SDB_H_R1 = 0, SDB_H_T1 = 1, SDB_H_TD1 = 2, SDB_H_R0 = 3, SDB_H_T0 = 4, SDB_H_TD0 = 5, SDB_H_VALID = 6, SDB_H_WIDEN = 7 };
+
+__device__ __forceinline__ uint32_t* sdb_history(const SdbOrigin& org, long stride)
+{
+    return (org.flags & SDB_ORIGIN_HISTORY) ? reinterpret_cast<uint32_t*>(org.d_delta + 3 * stride) : nullptr;
+}
+
+// Bracket predicted by linear extrapolation (in time) of the last two exact thresholds of one key
+// array: [lo, hi] = extrapolation +- 2^widen max(|step| / 2, 8 thr / sqrt(n)).  Any bracket is safe --
+// the selection verifies that the k-th largest key lies inside and falls back to the exact kernel
+// otherwise; the width covers the observed prediction error (<= 0.24 |step| for young origins, threshold
+// jitter <= 4 / sqrt(n) relative for old ones) twice, and `widen` grows whenever a bracket misses.
+// About 0.4 % of the molecules become candidates instead of ~5 % with the sampled bracket.
+__device__ __forceinline__ bool sdb_predict_bracket(const uint32_t* hist, uint32_t td, int arr, float inv_sqrt_n,
+                                                    float& lo, float& hi)
+{
+    if (hist == nullptr || hist[SDB_H_VALID] < 2u) return false;
+    const uint32_t td1 = hist[SDB_H_TD1], td0 = hist[SDB_H_TD0];
+    if (!(td > td1 && td1 > td0)) return false;
+    const float t1 = __uint_as_float(hist[arr ? SDB_H_T1 : SDB_H_R1]), t0 = __uint_as_float(hist[arr ? SDB_H_T0 : SDB_H_R0]);
+    if (!(t1 > 0.0f) || !(t0 > 0.0f) || !(t1 < INFINITY)) return false;
+    const float step = (t1 - t0) * ((float)(td - td1) / (float)(td1 - td0));
+    const float centre = t1 + step;
+    const float w = fmaxf(0.5f * fabsf(step), 8.0f * inv_sqrt_n * t1) * (float)(1u << min(hist[SDB_H_WIDEN], 6u));
+    lo = fmaxf(centre - w, 0.0f);
+    hi = centre + w;
+    return hi > lo && hi < INFINITY;
+}
+
 inline size_t sdb_ov_exact_words(int n) { return 2 * 2048 + 2 * 8 + 2 * (size_t)((n + 255) / 256) + 64; }
 
 inline size_t sdb_ov_layout(void* base, int max_origins, int n, SdbOvWorkspace* w)

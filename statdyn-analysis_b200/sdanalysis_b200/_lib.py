@@ -19,7 +19,8 @@ SDB_MAX_K = 16
 S_DISP, S_DISP2, S_DISP4, S_COMSTRUCT, S_ROT, S_ROT2, S_COS, S_COS2, S_ROT4, S_D2R2 = range(10)
 S_STRUCT, S_OVERLAP, S_BADQUAT = 10, 11, 12
 
-ORIGIN_NEW, ORIGIN_LITERAL = 1, 2
+ORIGIN_NEW, ORIGIN_LITERAL, ORIGIN_HISTORY = 1, 2, 4
+HISTORY_WORDS = 16
 SEG_NO_ROTATION, SEG_ZERO_STEP = 1, 2
 
 # Every symbol include/sdb200.h declares; tests check that the library exports all of them.
@@ -34,6 +35,7 @@ EXPORTS = (
     "sdb_overlap_ws_bytes",
     "sdb_overlap_prepare",
     "sdb_overlap_resolve",
+    "sdb_overlap_stats",
     "sdb_first_passage",
     "sdb_last_passage",
     "sdb_motion_general",
@@ -130,6 +132,7 @@ def load():
         "sdb_overlap_ws_bytes": (c_size_t, [c_int32, c_int32]),
         "sdb_overlap_prepare": (c_int32, [POINTER(SdbDynParams), P, P, P, c_int32, P, c_int32, c_int32, c_int32, P, c_int32, P]),
         "sdb_overlap_resolve": (c_int32, [P, c_int32, c_int32, c_int32, c_int32, P, c_int32, P, P]),
+        "sdb_overlap_stats": (c_int32, [P, c_int32, c_int32, c_int32, P, P]),
         "sdb_first_passage": (c_int32, [P, c_int32, c_int32, c_double, c_int64, P, P]),
         "sdb_last_passage": (c_int32, [P, c_int32, c_int32, c_double, c_double, c_int64, P, P, P]),
         "sdb_motion_general": (c_int32, [POINTER(c_float), c_int32, c_int32, P, P, P, P, c_int32, P, P, P, P]),

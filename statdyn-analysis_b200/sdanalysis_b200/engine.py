@@ -27,7 +27,9 @@ import numpy as np
 
 from . import _lib
 from ._lib import (
+    HISTORY_WORDS,
     ORIGIN_DTYPE,
+    ORIGIN_HISTORY,
     ORIGIN_LITERAL,
     ORIGIN_NEW,
     S_BADQUAT,
@@ -190,6 +192,41 @@ def finalize_row(s, td, n, *, distance=None, overlap_k=None, n_sites=None, stric
     return row
 
 
+def finalize_table(sums, timediffs, n, *, distance=None, overlap_k=None, n_sites=None, strict=True):
+    """Vectorised :func:`finalize_row`: ``sums`` is ``(A, SDB_NSUM)``; returns ``{quantity: (A,) array}``
+    with the same closed forms and the same NaN conventions (0/0 -> NaN, SURVEY trap T3)."""
+    s = np.asarray(sums, dtype=np.float64).reshape(-1, SDB_NSUM)
+    a = s.shape[0]
+    n = float(n)
+    nan = np.full(a, np.nan)
+    msd, mfd = s[:, S_DISP2] / n, s[:, S_DISP4] / n
+    msr, mfr = s[:, S_ROT2] / n, s[:, S_ROT4] / n
+    table = {key: nan for key in ALL_QUANTITIES}
+    table["time"] = np.asarray(timediffs, dtype=np.int64)
+    table["mean_displacement"] = s[:, S_DISP] / n
+    table["msd"] = msd
+    table["mfd"] = mfd
+    with np.errstate(divide="ignore", invalid="ignore"):
+        table["alpha"] = np.where(msd > 0, mfd / (2 * msd * msd) - 1, np.nan)
+        table["alpha_rot"] = np.where(msr > 0, mfr / (3 * msr * msr) - 1, np.nan)
+        table["gamma"] = np.where((msd > 0) & (msr > 0), (s[:, S_D2R2] / n) / (msd * msr) - 1, np.nan)
+    if distance is not None:
+        table["com_struct"] = s[:, S_COMSTRUCT] / n
+    table["mean_rotation"] = s[:, S_ROT] / n
+    table["msr"] = msr
+    table["rot1"] = s[:, S_COS] / n
+    table["rot2"] = s[:, S_COS2] / n
+    if overlap_k is not None:
+        if overlap_k == 0:
+            if strict and a:
+                raise ZeroDivisionError("division by zero")  # dynamics.py:445 with N < 10
+        else:
+            table["overlap"] = s[:, S_OVERLAP] / overlap_k
+    if n_sites is not None:
+        table["struct"] = s[:, S_STRUCT] / (n * n_sites)
+    return table
+
+
 # ----------------------------------------------------------------------------------------------
 class _PoolFrame:
     __slots__ = ("planes", "refs", "has_orientation")
@@ -258,6 +295,13 @@ class StepResult:
         ``strict``: raise ZeroDivisionError for N < 10 like ``mobile_overlap`` does in compute_all."""
         return self.engine.finalize_rows(self.sums(), self.timediffs, check=check, strict=strict)
 
+    def table(self, check=True, strict=True):
+        """The same quantities as columns: ``{quantity: (A,) array}`` plus ``keyframe`` (vectorised over
+        the active origins; this is what the ``dynamics`` table of ``process_file`` is assembled from)."""
+        table = self.engine.finalize_table(self.sums(), self.timediffs, check=check, strict=strict)
+        table["keyframe"] = list(self.keys)
+        return table
+
 
 class DynamicsEngine:
     def __init__(
@@ -321,6 +365,10 @@ class DynamicsEngine:
         self._staged_slot = None
         self.h2d_bytes = self.d2h_bytes = 0
         self._plan = None
+        # SDB_OV_PREDICT=0 disables the history-predicted overlap brackets (sampled brackets every frame)
+        import os
+
+        self._origin_flags = ORIGIN_HISTORY if os.environ.get("SDB_OV_PREDICT", "1") != "0" else 0
         self.profile = None  # set to a list to collect (name, start_event, end_event) per kernel group
         self._sites_c = None if self.mol_sites is None else _lib.float_array(self.mol_sites.reshape(-1))
         self.frames_seen = 0
@@ -434,7 +482,10 @@ class DynamicsEngine:
 
     def _alloc_origin(self, org):
         torch, dev = self.torch, self.device
-        org.delta = torch.empty((3, self.stride), dtype=torch.float32, device=dev)
+        # three planes followed by the threshold history of the overlap selection (SDB_ORIGIN_HISTORY)
+        buf = torch.empty(3 * self.stride + HISTORY_WORDS, dtype=torch.float32, device=dev)
+        buf[3 * self.stride :].zero_()
+        org.delta = buf[: 3 * self.stride].view(3, self.stride)
         if self.trackers:
             org.flags = torch.empty(self.stride, dtype=torch.uint8, device=dev)
             org.status = torch.empty((len(self.trackers), self.stride), dtype=torch.int32, device=dev)
@@ -525,7 +576,7 @@ class DynamicsEngine:
                 ordered = plan["ordered"]
                 odesc = plan["odesc"]
                 odesc["timediff"] = int(timestep) - plan["t0"]
-                odesc["flags"] = 0
+                odesc["flags"] = self._origin_flags
                 timediffs = odesc["timediff"].tolist()
                 if timediffs and max(timediffs) >= MAX_STATUS:
                     raise OverflowError("time difference outside [0, 2**32-1): passage times are 32-bit on the device")
@@ -582,7 +633,8 @@ class DynamicsEngine:
                 odesc["d_delta"], odesc["d_flags"], odesc["d_status"] = ptrs[:, 0], ptrs[:, 1], ptrs[:, 2]
                 odesc["timediff"] = td
                 odesc["flags"] = [
-                    ORIGIN_NEW if org.updates == 0 else (ORIGIN_LITERAL if t < org.max_timediff else 0)
+                    self._origin_flags
+                    | (ORIGIN_NEW if org.updates == 0 else (ORIGIN_LITERAL if t < org.max_timediff else 0))
                     for org, t in zip(ordered, td.tolist())
                 ]
                 timediffs = td.tolist()
@@ -757,6 +809,21 @@ class DynamicsEngine:
             )
         return rows
 
+    def finalize_table(self, sums, timediffs, check=True, strict=True):
+        """Column form of :meth:`finalize_rows` (one numpy expression per quantity)."""
+        sums = np.asarray(sums).reshape(-1, SDB_NSUM)
+        if check and sums.shape[0] and (sums[:, S_BADQUAT] > 0).any():
+            raise ValueError("Arguments must be unit quaternions (planar, rotation about z)")
+        return finalize_table(
+            sums,
+            timediffs,
+            self.n,
+            distance=self.distance,
+            overlap_k=self.overlap_k if self.compute_overlap else None,
+            n_sites=len(self.mol_sites) if self.compute_struct else None,
+            strict=strict,
+        )
+
     # ------------------------------------------------------------------------------------------
     def delta_arrays(self, key):
         """(delta_translation (N,3), delta_rotation (N,3)) of one origin as host arrays."""
@@ -802,6 +869,17 @@ class DynamicsEngine:
                 col[state != 2] = MAX_STATUS
             out[spec.name] = col
         return out
+
+    def overlap_stats(self, n_active):
+        """(origins that needed the exact kernel, candidates per origin) of the last step (diagnostics)."""
+        out = np.zeros(1 + n_active, dtype=np.uint32)
+        with self.torch.cuda.device(self.device):
+            _lib.check(
+                self.lib.sdb_overlap_stats(
+                    self._ov_ws.data_ptr(), self._cap, self.n, n_active, out.ctypes.data, _lib.stream_ptr(self.device)
+                )
+            )
+        return int(out[0]), out[1:]
 
     def synchronize(self):
         self.torch.cuda.synchronize(self.device)

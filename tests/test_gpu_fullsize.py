@@ -159,3 +159,35 @@ def test_periodic_image_leaves_everything_unchanged():
     # wrap maps the image back: the displacement is the f32 rounding of the shift (<= 1 ulp of L)
     assert row["msd"] < (2 * np.spacing(np.float32(walk.box[0]))) ** 2 * 2
     assert row["msr"] == 0.0 and row["rot1"] == 1.0
+
+
+def test_predicted_overlap_brackets_match_sampled_ones(monkeypatch):
+    """The history-predicted brackets of the `overlap` selection (csrc/overlap.cu) give exactly the
+    counts of the sampled brackets, engage after two frames of history, never fall back to the exact
+    kernel on a smooth trajectory and collect far fewer candidates."""
+    import torch
+
+    from sdanalysis_b200.engine import DynamicsEngine
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    dev = torch.device("cuda", 0)
+    n = 300_000
+    walk = SyntheticTrimer(n, seed=12, sigma_r=0.01, sigma_theta=0.02, device=dev)
+    monkeypatch.setenv("SDB_OV_PREDICT", "1")
+    predicted = DynamicsEngine(n, walk.box, WAVE, device=dev, trackers=None)
+    monkeypatch.setenv("SDB_OV_PREDICT", "0")
+    sampled = DynamicsEngine(n, walk.box, WAVE, device=dev, trackers=None)
+    cands = []
+    for t in range(40):
+        pos, quat = walk.frame()
+        active = [0] if t < 7 else [0, 1]  # a second origin joins with no history
+        a = predicted.step(walk.timestep, pos, quat, active).table()
+        fails_p, cand_p = predicted.overlap_stats(len(active))
+        b = sampled.step(walk.timestep, pos, quat, active).table()
+        fails_s, cand_s = sampled.overlap_stats(len(active))
+        assert np.array_equal(a["overlap"], b["overlap"]), t
+        assert fails_p == 0 and fails_s == 0, t
+        cands.append((int(cand_p[0]), int(cand_s[0])))
+        walk.advance(1)
+    assert cands[1][0] == cands[1][1] > 0  # no history yet: both engines sample
+    assert all(p < s / 3 for p, s in cands[25:])  # old origin: predicted brackets are much tighter
