@@ -225,7 +225,7 @@ def run_gpu(args):
             def step_fn(ts, pos, quat, keys):
                 return engine.step(ts, pos, quat, keys, to_host=False)
 
-            sharded = ShardedDynamics(n, step_fn, max_local=len(local_keys) + 1, device=device)
+            sharded = ShardedDynamics(n, step_fn, max_local=len(local_keys) + 1, device=device, batch=steps + warmup + 1)
         # origin creation: origin k starts at frame k (linear schedule, keyframe_interval = 1)
         timestep = 0
         # frames: a random walk generated on rank 0's GPU
@@ -258,23 +258,40 @@ def run_gpu(args):
 
         results = []
 
+        posted = {}
+
         def one_step(i, ts):
-            pos, quat = frames[i]
             if world > 1:
-                h = sharded.post_frame(pos, quat)
-                results.append(sharded.step(ts, all_keys, h, gather=True))
-            else:
-                results.append(engine.step(ts, pos, quat, all_keys))
+                # software pipeline: the exchange of frame i + 1 is enqueued (side stream) before the
+                # kernels of frame i, so it overlaps them
+                if i not in posted:
+                    posted[i] = sharded.post_frame(*frames[i])
+                if i + 1 < n_frames:
+                    posted[i + 1] = sharded.post_frame(*frames[i + 1])
+                # rows stay on the device; one gather per batch of frames (and at the end of the region)
+                sharded.step(ts, all_keys, posted.pop(i), gather="batch")
+                return
+            pos, quat = frames[i]
+            results.append(engine.step(ts, pos, quat, all_keys))
             if len(results) > 2:
-                r = results.pop(0)
-                r() if callable(r) else r.table()
+                results.pop(0).table()
+
+        def drain():
+            last = None
+            if world > 1:
+                flushed = sharded.flush()
+                if flushed:
+                    keys, timediffs, sums = flushed[-1]
+                    last = engine.finalize_table(sums, timediffs)
+                return last
+            while results:
+                last = results.pop(0).table()
+            return last
 
         for i in range(warmup):
             one_step(i, timestep)
             timestep += 1
-        while results:
-            r = results.pop(0)
-            r() if callable(r) else r.table()
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -284,13 +301,12 @@ def run_gpu(args):
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         t_start.record()
+        host_t0 = time.perf_counter()
         for i in range(steps):
             one_step(warmup + i, timestep)
             timestep += 1
-        last_rows = None
-        while results:
-            r = results.pop(0)
-            last_rows = r() if callable(r) else r.table()
+        host_ms = 1e3 * (time.perf_counter() - host_t0) / steps
+        last_rows = drain()
         t_end.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -309,12 +325,20 @@ def run_gpu(args):
             kern["dyn"] += e1.elapsed_time(e2)
             kern["struct"] += e2.elapsed_time(e3)
             kern["overlap"] += e0.elapsed_time(e1) + e3.elapsed_time(e4)
+        if sharded is not None and sharded.stalls:
+            import time as _t
+            st = [a.elapsed_time(b) for a, b in sharded.stalls[-steps:]]
+            xt = [a.elapsed_time(b) for a, b in sharded.exchange_times[-steps:]]
+            print(f"[rank {rank}] host_frames={host_frames} frame-wait stall per step: mean {sum(st)/len(st):.3f} ms max {max(st):.3f} ms; "
+                  f"exchange (side stream) mean {sum(xt)/max(len(xt),1):.3f} ms max {max(xt):.3f}\n", file=sys.stderr, flush=True)
         h2d, d2h = engine.h2d_bytes, engine.d2h_bytes
         if world > 1:  # frames enter through rank 0, rows leave through rank 0
             h2d = 28 * n if host_frames else 0
             d2h = n_origins * 16 * 8
         del engine, sharded
         torch.cuda.empty_cache()
+        if os.environ.get("SDB_SHARD_PROFILE") == "1":
+            print(f"[rank {rank}] host enqueue time per step {host_ms:.3f} ms", file=sys.stderr, flush=True)
         return {"ms": ms, "clocks": clocks, "launches": launches, "kern": kern, "h2d": h2d, "d2h": d2h, "rows": last_rows}
 
     dev = phase(host_frames=False)
@@ -365,7 +389,10 @@ def run_gpu(args):
         "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": WORKLOAD, "molecules": n, "origins": n_origins, "origins_per_gpu": len(local_keys),
-            "parallelism": f"origin-sharded x{world}, NCCL frame broadcast" if world > 1 else "single GPU",
+            "parallelism": (
+                f"origin-sharded x{world}, frame pushed to every rank by multicast stores over NVSwitch, rows gathered once per batch (NCCL)"
+                if world > 1 else "single GPU"
+            ),
             "l2": "inputs larger than L2 (>= 25 MB of state per origin and step)",
         },
         "e2e": {

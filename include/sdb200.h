@@ -239,6 +239,13 @@ uint64_t sdb_launch_count(void);
 double sdb_test_rot_increment(float w, float z, float pw, float pz, int32_t* bad);
 void sdb_test_wrap2d(float lx, float ly, float xy, float vx, float vy, float* ox, float* oy);
 
+/* ---- multi-GPU frame exchange (origin-sharded path; the reference is single-process) -------------
+ * Copy `bytes` (a multiple of 16) from local device memory to an NVSwitch multicast address with
+ * multimem.st stores: one pass on the reader rank delivers the frame to the same offset of every
+ * rank's symmetric buffer.  d_multicast_dst is the multicast virtual address of the destination
+ * (torch symmetric memory: handle.multicast_ptr + offset).  blocks <= 0 picks a default grid. */
+int sdb_multicast_copy(const void* d_src, void* d_multicast_dst, size_t bytes, int32_t blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,11 +6,12 @@ origin, hence
 
 * origin ``k`` lives on rank ``k % world`` (round-robin keeps the progressively activated origins of
   the linear schedule balanced) and never moves;
-* the only shared input is the current frame: the reader rank (0) uploads it and broadcasts the
-  28 B/molecule over NVLink; the broadcast of frame t+1 is issued before the kernels of frame t are
-  waited for, so it overlaps with compute;
-* the per-(frame, origin) rows (16 doubles) are gathered to rank 0, which assembles the ``dynamics``
-  table in the reference's row order; passage-time tables stay sharded.
+* the only shared input is the current frame: the reader rank (0) uploads it and pushes the
+  28 B/molecule into every rank's frame ring over NVLink with multicast stores (``csrc/exchange.cu``)
+  on a side stream, so the exchange of frame t+1 overlaps the kernels of frame t;
+* the per-(frame, origin) rows (16 doubles) are gathered to rank 0 -- per frame or once per batch of
+  frames -- which assembles the ``dynamics`` table in the reference's row order; passage-time tables
+  stay sharded.
 
 The compute step is injected (``step_fn``) so the plumbing can be exercised on CPU tensors.
 """
@@ -42,9 +43,26 @@ class ShardedDynamics:
     ``step_fn(timestep, pos, quat, local_keys) -> (keys, timediffs, sums)`` advances the local
     origins and returns a ``(len(keys), SDB_NSUM)`` float64 tensor on ``device`` (the CUDA engine or,
     in tests, a stub).  ``max_local`` bounds the number of local origins active in one frame.
+
+    Frame exchange (``exchange``):
+
+    ``"multicast"``  (CUDA, default) every rank holds a ring of frame slots in torch symmetric memory.
+        The reader rank pushes frame t into slot t % depth of *every* rank with one pass of
+        ``multimem.st`` stores through the NVSwitch multicast address (``csrc/exchange.cu``), on a side
+        stream, followed by a device-side barrier; compute waits on an event.  The reader's NVLink
+        egress is 28 B per molecule whatever the number of ranks, and no collective kernel competes
+        with the compute kernels.  Without multicast support the peers pull the slot from the reader
+        with copy-engine peer copies instead.
+    ``"collective"`` ``torch.distributed.broadcast`` (NCCL on GPUs, gloo in the CPU tests).
+
+    Rows: ``step(..., gather=True)`` gathers every frame's rows to rank 0 with a collective (CPU tests,
+    small runs); ``gather="batch"`` keeps them in a device buffer that :meth:`flush` gathers once per
+    ``batch`` frames -- nothing but the frame exchange happens per frame.
     """
 
-    def __init__(self, num_mols, step_fn, max_local, *, device, group=None, depth=3):
+    def __init__(self, num_mols, step_fn, max_local, *, device, group=None, depth=3, exchange=None, batch=64):
+        import os
+
         import torch
         import torch.distributed as dist
 
@@ -56,66 +74,157 @@ class ShardedDynamics:
         self.device = torch.device(device)
         self.step_fn = step_fn
         self.max_local = int(max_local)
+        self.depth = int(depth)
         self.qoff = (3 * self.n + 3) // 4 * 4
-        self.frames = [torch.zeros(frame_floats(self.n), dtype=torch.float32, device=self.device) for _ in range(depth)]
-        self._slot = 0
-        # gather buffers: one block of max_local rows per rank; rank 0 keeps `depth` receive sets so a
-        # result can be read while later frames are in flight
-        self._send = [torch.zeros((self.max_local, SDB_NSUM), dtype=torch.float64, device=self.device) for _ in range(depth)]
-        self._recv = (
-            [[torch.zeros_like(self._send[0]) for _ in range(self.world)] for _ in range(depth)]
-            if self.rank == 0
-            else None
-        )
-        self._start = {}  # origin key -> timestep of its first frame (known to every rank)
-        # frame uploads and broadcasts run on a side stream so that they overlap the kernels of the
-        # previous frame; `_consumed[slot]` marks the end of the kernels that read a frame buffer
-        import os
-
+        self.slot_floats = (frame_floats(self.n) + 3) // 4 * 4  # 16-byte multiple
         self._cuda = self.device.type == "cuda"
+        self._slot = 0
+        self._start = {}  # origin key -> timestep of its first frame (known to every rank)
+        self._consumed = [None] * self.depth
+        self.stalls = [] if os.environ.get("SDB_SHARD_PROFILE") == "1" else None
+        self.exchange_times = []
+
+        if exchange is None:
+            exchange = os.environ.get("SDB_SHARD_EXCHANGE", "multicast" if self._cuda and self.world > 1 else "collective")
+        self.exchange = exchange
+        self._hdl = None
+        if exchange == "multicast":
+            try:
+                self._setup_symmetric()
+            except Exception as exc:  # no symmetric memory on this system: collectives still work
+                import warnings
+
+                warnings.warn(f"symmetric-memory frame exchange unavailable ({exc}); using collectives")
+                self.exchange = "collective"
+        if self.exchange == "collective":
+            self.frames = [
+                torch.zeros(self.slot_floats, dtype=torch.float32, device=self.device) for _ in range(self.depth)
+            ]
         # Measured on 2 x B200 (round 1): issuing the NCCL broadcast from a side stream so that it
         # overlaps the kernels of the previous frame slows those kernels down 1.5-8x (independent of
-        # NCCL_MAX_NCHANNELS), so the exchange is issued in-stream by default.
-        self._use_side = self._cuda and os.environ.get("SDB_SHARD_SIDE", "0") == "1"
+        # NCCL_MAX_NCHANNELS), so the collective exchange is issued in-stream by default.
+        self._use_side = self._cuda and (self.exchange != "collective" or os.environ.get("SDB_SHARD_SIDE", "0") == "1")
+        self._side = torch.cuda.Stream(device=self.device, priority=-1) if self._use_side else None
+
+        # per-frame gather (gather=True): one block of max_local rows per rank; rank 0 keeps `depth`
+        # receive sets so a result can be read while later frames are in flight
         self._async_gather = os.environ.get("SDB_SHARD_ASYNC_GATHER", "1") == "1"
-        self._side = torch.cuda.Stream(device=self.device) if self._use_side else None
-        self._consumed = [None] * depth
-        self._gathers = [None] * depth
+        self._send = self._recv = None
+        self._gathers = [None] * self.depth
+        # batched gather (gather="batch")
+        self.batch = int(batch)
+        self._batch_buf = None
+        self._batch_meta = []
+
+    # -- symmetric-memory ring ------------------------------------------------------------------------
+    def _setup_symmetric(self):
+        torch, dist = self.torch, self.dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = self.group if self.group is not None else dist.group.WORLD
+        self._ring = symm_mem.empty(self.depth * self.slot_floats, dtype=torch.float32, device=self.device)
+        self._hdl = symm_mem.rendezvous(self._ring, group.group_name)
+        self._ring.zero_()
+        self.frames = [self._ring[i * self.slot_floats : (i + 1) * self.slot_floats] for i in range(self.depth)]
+        self._mc_ptr = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+        if self.rank == 0:
+            # the reader stages a frame here (H2D or D2D) before pushing it to every rank
+            self._stage = [torch.zeros(self.slot_floats, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._stage_i = 0
+            self._stage_free = [None, None]
+        else:
+            self._reader_ring = self._hdl.get_buffer(0, (self.depth * self.slot_floats,), torch.float32)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
+    def _ensure_gather_buffers(self):
+        if self._send is None:
+            torch = self.torch
+            self._send = [
+                torch.zeros((self.max_local, SDB_NSUM), dtype=torch.float64, device=self.device) for _ in range(self.depth)
+            ]
+            if self.rank == 0:
+                self._recv = [[torch.zeros_like(self._send[0]) for _ in range(self.world)] for _ in range(self.depth)]
 
     # -- frame exchange ---------------------------------------------------------------------------
+    def _fill(self, buf, position, orientation):
+        torch = self.torch
+        if position is None:
+            raise ValueError("rank 0 is the reader rank and must supply the frame")
+        pos = torch.as_tensor(position)
+        quat = torch.as_tensor(orientation)
+        buf[: 3 * self.n].view(self.n, 3).copy_(pos, non_blocking=True)
+        buf[self.qoff : self.qoff + 4 * self.n].view(self.n, 4).copy_(quat, non_blocking=True)
+
     def post_frame(self, position=None, orientation=None):
-        """Start the broadcast of the next frame (rank 0 supplies it; others pass nothing).
+        """Start the exchange of the next frame (rank 0 supplies it; others pass nothing).
 
         ``position`` (n,3) / ``orientation`` (n,4) may be host arrays, pinned CPU tensors or tensors
         on ``device``.  Returns a handle for :meth:`step`."""
         torch = self.torch
-        self._slot = (self._slot + 1) % len(self.frames)
-        buf = self.frames[self._slot]
+        self._slot = (self._slot + 1) % self.depth
+        slot = self._slot
+        buf = self.frames[slot]
 
-        def exchange():
-            if self.rank == 0:
-                if position is None:
-                    raise ValueError("rank 0 is the reader rank and must supply the frame")
-                pos = torch.as_tensor(position)
-                quat = torch.as_tensor(orientation)
-                buf[: 3 * self.n].view(self.n, 3).copy_(pos, non_blocking=True)
-                buf[self.qoff : self.qoff + 4 * self.n].view(self.n, 4).copy_(quat, non_blocking=True)
-            if self.world > 1:
-                return self.dist.broadcast(buf, src=0, group=self.group, async_op=True)
-            return None
+        if self.exchange == "collective":
+            def exchange():
+                if self.rank == 0:
+                    self._fill(buf, position, orientation)
+                if self.world > 1:
+                    return self.dist.broadcast(buf, src=0, group=self.group, async_op=True)
+                return None
 
-        if not self._use_side:
-            return (self._slot, exchange(), None)
+            if not self._use_side:
+                return (slot, exchange(), None)
+            with torch.cuda.stream(self._side):
+                consumed = self._consumed[slot]
+                if consumed is not None:
+                    self._side.wait_event(consumed)  # the kernels that read this buffer have finished
+                work = exchange()
+                if work is not None:
+                    work.wait()  # orders the side stream after the broadcast
+                ready = torch.cuda.Event()
+                ready.record(self._side)
+            return (slot, None, ready)
+
+        # symmetric-memory ring: see the class docstring.  Slot reuse: before arriving at the barrier of
+        # frame u every rank waits for its own kernels on the slot of frame u + 1; the reader writes that
+        # slot only after the barrier, so nobody is still reading it.
+        main = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self._side):
-            consumed = self._consumed[self._slot]
-            if consumed is not None:
-                self._side.wait_event(consumed)  # the kernels that read this buffer have finished
-            work = exchange()
-            if work is not None:
-                work.wait()  # orders the side stream after the broadcast
-            ready = torch.cuda.Event()
+            nxt = self._consumed[(slot + 1) % self.depth]
+            if nxt is not None:
+                self._side.wait_event(nxt)
+            if self.stalls is not None:
+                x0 = torch.cuda.Event(enable_timing=True)
+                x0.record(self._side)
+            if self.rank == 0:
+                self._stage_i ^= 1
+                stage = self._stage[self._stage_i]
+                free = self._stage_free[self._stage_i]
+                if free is not None:
+                    self._side.wait_event(free)
+                self._side.wait_event(main.record_event())  # the caller's frame tensors are complete
+                self._fill(stage, position, orientation)
+                if self._mc_ptr:
+                    _lib.check(
+                        _lib.load().sdb_multicast_copy(
+                            stage.data_ptr(), self._mc_ptr + 4 * slot * self.slot_floats, 4 * self.slot_floats, 0,
+                            self._side.cuda_stream,
+                        )
+                    )
+                else:
+                    buf.copy_(stage, non_blocking=True)
+                self._stage_free[self._stage_i] = self._side.record_event()
+            self._hdl.barrier(channel=0)
+            if self.rank != 0 and not self._mc_ptr:
+                lo = slot * self.slot_floats
+                buf.copy_(self._reader_ring[lo : lo + self.slot_floats], non_blocking=True)
+            ready = torch.cuda.Event(enable_timing=self.stalls is not None)
             ready.record(self._side)
-        return (self._slot, None, ready)
+            if self.stalls is not None:
+                self.exchange_times.append((x0, ready))
+        return (slot, None, ready)
 
     def _frame_views(self, slot):
         buf = self.frames[slot]
@@ -127,15 +236,24 @@ class ShardedDynamics:
     def step(self, timestep, active, handle, gather=True):
         """Advance the local share of ``active`` with the frame behind ``handle``.
 
-        Returns, on rank 0 with ``gather``, a callable producing ``(keys, timediffs, sums)`` for *all*
-        origins in the order of ``active``; on the other ranks (or without ``gather``) the local
-        triple."""
+        ``gather=True``: returns, on rank 0, a callable producing ``(keys, timediffs, sums)`` for *all*
+        origins in the order of ``active`` (on the other ranks the local triple).  ``gather="batch"``:
+        the rows stay on the device until :meth:`flush`; returns None.  ``gather=False``: a callable
+        producing the local triple."""
         torch, dist = self.torch, self.dist
         slot, work, ready = handle
         if work is not None:
             work.wait()
         if ready is not None:
-            torch.cuda.current_stream(self.device).wait_event(ready)  # frame uploaded and broadcast
+            main = torch.cuda.current_stream(self.device)
+            if self.stalls is not None:  # diagnostics: time the compute stream spends waiting for the frame
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(main)
+                main.wait_event(ready)
+                e1.record(main)
+                self.stalls.append((e0, e1))
+            else:
+                main.wait_event(ready)  # frame uploaded and delivered
         pos, quat = self._frame_views(slot)
         local = partition(active, self.rank, self.world)
         if len(local) > self.max_local:
@@ -152,8 +270,22 @@ class ShardedDynamics:
             done = torch.cuda.Event()
             done.record()
             self._consumed[slot] = done
+        if gather == "batch" and self.world > 1:
+            if self._batch_buf is None:
+                self._batch_buf = torch.zeros(
+                    (self.batch, self.max_local, SDB_NSUM), dtype=torch.float64, device=self.device
+                )
+            i = len(self._batch_meta)
+            if keys and sums is not None:
+                self._batch_buf[i, : len(keys)].copy_(sums, non_blocking=True)
+            self._batch_meta.append((int(timestep), list(active)))
+            if len(self._batch_meta) == self.batch:
+                self._flushed = self.flush()
+                return self._flushed
+            return None
         if not gather or self.world == 1:
             return lambda: (keys, timediffs, None if sums is None else sums.cpu().numpy())
+        self._ensure_gather_buffers()
         send = self._send[slot % len(self._send)]
         previous = self._gathers[slot % len(self._send)]
         if previous is not None:
@@ -182,3 +314,34 @@ class ShardedDynamics:
             return list(active), [int(timestep) - start[k] for k in active], out
 
         return collect
+
+    def flush(self):
+        """Gather the rows of the frames stepped with ``gather="batch"`` since the last flush.
+
+        Returns, on rank 0, a list of ``(keys, timediffs, sums)`` per frame (all origins, in the order
+        of ``active``); an empty list on the other ranks.  One collective for up to ``batch`` frames."""
+        torch, dist = self.torch, self.dist
+        meta, self._batch_meta = self._batch_meta, []
+        if not meta or self._batch_buf is None:
+            return []
+        count = len(meta)
+        send = self._batch_buf[:count].contiguous()
+        recv = [torch.empty_like(send) for _ in range(self.world)] if self.rank == 0 else None
+        dist.gather(send, recv, dst=0, group=self.group)
+        if self.rank != 0:
+            return []
+        host = [block.cpu().numpy() for block in recv]
+        out = []
+        cached_active, places, t0 = None, None, None
+        for i, (timestep, active) in enumerate(meta):
+            if active != cached_active:  # the scatter pattern only depends on the active list
+                cached_active = active
+                index = {k: j for j, k in enumerate(active)}
+                places = [np.array([index[k] for k in partition(active, r, self.world)], dtype=np.int64) for r in range(self.world)]
+                t0 = np.array([self._start[k] for k in active], dtype=np.int64)
+            sums = np.zeros((len(active), SDB_NSUM))
+            for r in range(self.world):
+                if len(places[r]):
+                    sums[places[r]] = host[r][i, : len(places[r])]
+            out.append((list(active), (timestep - t0).tolist(), sums))
+        return out
