@@ -295,7 +295,9 @@ def run_gpu(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        engine.profile = []
+        lib = _lib.load()
+        lib.sdb_profile_collect(None, None, None)  # drop anything collected so far
+        lib.sdb_profile_enable(1)  # per-kernel-group CUDA-event times of every sdb_frame_step call
         launches0 = _lib.launch_count()
         sampler = ClockSampler(local_rank) if rank == 0 else None
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -318,13 +320,17 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         launches = _lib.launch_count() - launches0
-        prof = engine.profile
-        engine.profile = None
-        kern = {"dyn": 0.0, "struct": 0.0, "overlap": 0.0, "count": len(prof), "origins": prof[0][0] if prof else 0}
-        for _, e0, e1, e2, e3, e4 in prof:
-            kern["dyn"] += e1.elapsed_time(e2)
-            kern["struct"] += e2.elapsed_time(e3)
-            kern["overlap"] += e0.elapsed_time(e1) + e3.elapsed_time(e4)
+        import ctypes
+
+        group_ms = (ctypes.c_double * 4)()
+        n_steps, n_origin_steps = ctypes.c_int64(0), ctypes.c_int64(0)
+        lib.sdb_profile_enable(0)
+        _lib.check(lib.sdb_profile_collect(group_ms, ctypes.byref(n_steps), ctypes.byref(n_origin_steps)))
+        count = max(int(n_steps.value), 1)
+        kern = {
+            "dyn": group_ms[1], "struct": group_ms[2], "overlap": group_ms[0] + group_ms[3], "count": count,
+            "origins": int(n_origin_steps.value) // count,
+        }
         if sharded is not None and sharded.stalls:
             import time as _t
             st = [a.elapsed_time(b) for a, b in sharded.stalls[-steps:]]

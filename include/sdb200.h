@@ -239,6 +239,28 @@ uint64_t sdb_launch_count(void);
 double sdb_test_rot_increment(float w, float z, float pw, float pz, int32_t* bad);
 void sdb_test_wrap2d(float lx, float ly, float xy, float vx, float vy, float* ox, float* oy);
 
+/* ---- one call per frame -------------------------------------------------------------------------
+ * The body of the reference hot loop (read/_read.py:134-153) for every active origin, enqueued from
+ * native code: upload of the descriptor block (h_desc, pinned: n_origins SdbOrigin records, then at
+ * byte segments_offset the n_segments SdbSegment records; desc_bytes in total) to d_desc, then
+ * sdb_overlap_prepare -> sdb_dyn_step -> sdb_struct -> sdb_overlap_resolve with the same meaning of
+ * the arguments as those calls (overlap_k <= 0 or d_ov_ws NULL: no `overlap`; h_sites_xy NULL: no
+ * `struct`), then the download of d_sums[n_origins][SDB_NSUM] to h_sums (pinned; NULL: stay on the
+ * device).  Asynchronous on `stream`. */
+int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
+                   float* d_cur_compact, const void* h_desc, void* d_desc, int32_t desc_bytes,
+                   int32_t segments_offset, int32_t n_origins, int32_t n_segments,
+                   int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
+                   void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy,
+                   int32_t n_sites, double struct_dist, int32_t struct_mode, void* stream);
+
+/* Per-kernel-group device times of sdb_frame_step (CUDA events on the launching stream), for
+ * bench.py's roofline: groups 0 overlap prepare, 1 dyn_step + finalize, 2 struct, 3 overlap resolve.
+ * sdb_profile_collect waits for the recorded events, returns the summed times in ms (h_ms[4]), the
+ * number of steps and of origin-steps, and clears the collection. */
+void sdb_profile_enable(int32_t on);
+int sdb_profile_collect(double* h_ms, int64_t* h_steps, int64_t* h_origin_steps);
+
 /* ---- multi-GPU frame exchange (origin-sharded path; the reference is single-process) -------------
  * Copy `bytes` (a multiple of 16) from local device memory to an NVSwitch multicast address with
  * multimem.st stores: one pass on the reader rank delivers the frame to the same offset of every

@@ -1,0 +1,125 @@
+// frame_step.cu -- one call per frame: the whole device-side sequence of the hot loop body
+// (reference read/_read.py:134-153 for every active origin) enqueued from native code, so the host
+// spends one FFI call per frame instead of one per kernel group plus tensor copies.
+#include <mutex>
+#include <vector>
+
+#include "sdb_internal.cuh"
+
+// ---- optional per-kernel-group timing (CUDA events on the launching stream) --------------------------
+// Groups: 0 overlap prepare, 1 dyn_step + finalize, 2 struct, 3 overlap resolve.
+namespace {
+struct StepEvents {
+    cudaEvent_t ev[5];
+    int n_origins;
+};
+std::mutex g_prof_mutex;
+bool g_prof_on = false;
+std::vector<StepEvents> g_prof_steps;
+std::vector<StepEvents> g_prof_free;
+
+StepEvents* prof_begin(int n_origins)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (!g_prof_on) return nullptr;
+    StepEvents se;
+    if (!g_prof_free.empty()) {
+        se = g_prof_free.back();
+        g_prof_free.pop_back();
+    } else {
+        for (auto& e : se.ev)
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    }
+    se.n_origins = n_origins;
+    g_prof_steps.push_back(se);
+    return &g_prof_steps.back();
+}
+}  // namespace
+
+// Start (on != 0) or stop collecting per-group kernel times of sdb_frame_step calls made by this process.
+extern "C" void sdb_profile_enable(int32_t on)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof_on = on != 0;
+}
+
+// Sum of the collected group times in ms (h_ms[4]), number of steps and of origin-steps; synchronises
+// on the recorded events and clears the collection.
+extern "C" int sdb_profile_collect(double* h_ms, int64_t* h_steps, int64_t* h_origin_steps)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (h_ms) h_ms[0] = h_ms[1] = h_ms[2] = h_ms[3] = 0.0;
+    int64_t steps = 0, origin_steps = 0;
+    for (auto& se : g_prof_steps) {
+        if (sdb_check_cuda(cudaEventSynchronize(se.ev[4]), "sdb_profile_collect")) return SDB_ECUDA;
+        for (int g = 0; g < 4; ++g) {
+            float ms = 0.f;
+            if (sdb_check_cuda(cudaEventElapsedTime(&ms, se.ev[g], se.ev[g + 1]), "sdb_profile_collect")) return SDB_ECUDA;
+            if (h_ms) h_ms[g] += ms;
+        }
+        ++steps;
+        origin_steps += se.n_origins;
+        g_prof_free.push_back(se);
+    }
+    g_prof_steps.clear();
+    if (h_steps) *h_steps = steps;
+    if (h_origin_steps) *h_origin_steps = origin_steps;
+    return SDB_OK;
+}
+
+extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
+                              float* d_cur_compact, const void* h_desc, void* d_desc, int32_t desc_bytes,
+                              int32_t segments_offset, int32_t n_origins, int32_t n_segments,
+                              int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
+                              void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy,
+                              int32_t n_sites, double struct_dist, int32_t struct_mode, void* stream)
+{
+    if (!h_params || !h_desc || !d_desc || desc_bytes <= 0 || segments_offset <= 0 || segments_offset >= desc_bytes) {
+        sdb_set_error("sdb_frame_step: bad descriptor arguments");
+        return SDB_EINVAL;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = sdb_check_cuda(cudaMemcpyAsync(d_desc, h_desc, (size_t)desc_bytes, cudaMemcpyHostToDevice, s),
+                            "sdb_frame_step: descriptor upload");
+    if (rc) return rc;
+    const SdbOrigin* d_origins = static_cast<const SdbOrigin*>(d_desc);
+    const SdbSegment* d_segments =
+        reinterpret_cast<const SdbSegment*>(static_cast<const char*>(d_desc) + segments_offset);
+    const bool sums = h_params->do_sums != 0;
+    const bool use_ov = sums && d_ov_ws != nullptr && overlap_k > 0;
+    StepEvents* prof = prof_begin(n_origins);
+    StepEvents prof_copy;
+    if (prof) {
+        prof_copy = *prof;  // the vector may grow under another thread; the handles stay valid
+        cudaEventRecord(prof_copy.ev[0], s);
+    }
+    if (use_ov) {
+        rc = sdb_overlap_prepare(h_params, d_pos, d_quat, d_origins, n_origins, d_segments, n_segments,
+                                 max_segment_count, overlap_k, d_ov_ws, ov_ws_origins, stream);
+        if (rc) return rc;
+    }
+    if (prof) cudaEventRecord(prof_copy.ev[1], s);
+    rc = sdb_dyn_step(h_params, d_pos, d_quat, d_cur_compact, d_origins, n_origins, d_segments, n_segments, d_partials,
+                      d_sums, use_ov ? d_ov_ws : nullptr, ov_ws_origins, stream);
+    if (rc) return rc;
+    if (prof) cudaEventRecord(prof_copy.ev[2], s);
+    if (sums && h_sites_xy && n_sites > 0) {
+        rc = sdb_struct(d_origins, n_origins, h_params->n, h_params->stride, h_sites_xy, n_sites, struct_dist, struct_mode,
+                        d_sums, stream);
+        if (rc) return rc;
+    }
+    if (prof) cudaEventRecord(prof_copy.ev[3], s);
+    if (use_ov) {
+        rc = sdb_overlap_resolve(d_origins, n_origins, h_params->n, h_params->stride, overlap_k, d_ov_ws, ov_ws_origins,
+                                 d_sums, stream);
+        if (rc) return rc;
+    }
+    if (prof) cudaEventRecord(prof_copy.ev[4], s);
+    if (sums && h_sums) {
+        rc = sdb_check_cuda(cudaMemcpyAsync(h_sums, d_sums, sizeof(double) * SDB_NSUM * (size_t)n_origins,
+                                            cudaMemcpyDeviceToHost, s),
+                            "sdb_frame_step: sums download");
+        if (rc) return rc;
+    }
+    return SDB_OK;
+}

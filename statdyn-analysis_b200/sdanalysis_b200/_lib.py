@@ -37,6 +37,9 @@ EXPORTS = (
     "sdb_overlap_resolve",
     "sdb_overlap_stats",
     "sdb_multicast_copy",
+    "sdb_frame_step",
+    "sdb_profile_enable",
+    "sdb_profile_collect",
     "sdb_first_passage",
     "sdb_last_passage",
     "sdb_motion_general",
@@ -135,6 +138,13 @@ def load():
         "sdb_overlap_resolve": (c_int32, [P, c_int32, c_int32, c_int32, c_int32, P, c_int32, P, P]),
         "sdb_overlap_stats": (c_int32, [P, c_int32, c_int32, c_int32, P, P]),
         "sdb_multicast_copy": (c_int32, [P, P, ctypes.c_size_t, c_int32, P]),
+        "sdb_frame_step": (
+            c_int32,
+            [POINTER(SdbDynParams), P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int32, P, P, P, P, c_int32,
+             c_int32, POINTER(c_float), c_int32, ctypes.c_double, c_int32, P],
+        ),
+        "sdb_profile_enable": (None, [c_int32]),
+        "sdb_profile_collect": (c_int32, [POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
         "sdb_first_passage": (c_int32, [P, c_int32, c_int32, c_double, c_int64, P, P]),
         "sdb_last_passage": (c_int32, [P, c_int32, c_int32, c_double, c_double, c_int64, P, P, P]),
         "sdb_motion_general": (c_int32, [POINTER(c_float), c_int32, c_int32, P, P, P, P, c_int32, P, P, P, P]),

@@ -81,6 +81,8 @@ class ShardedDynamics:
         self._slot = 0
         self._start = {}  # origin key -> timestep of its first frame (known to every rank)
         self._consumed = [None] * self.depth
+        self._view_cache = {}
+        self._last_active, self._last_local = None, None
         self.stalls = [] if os.environ.get("SDB_SHARD_PROFILE") == "1" else None
         self.exchange_times = []
 
@@ -127,6 +129,9 @@ class ShardedDynamics:
         self._ring.zero_()
         self.frames = [self._ring[i * self.slot_floats : (i + 1) * self.slot_floats] for i in range(self.depth)]
         self._mc_ptr = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+        import os
+
+        self._mc_blocks = int(os.environ.get("SDB_MC_BLOCKS", "32"))
         if self.rank == 0:
             # the reader stages a frame here (H2D or D2D) before pushing it to every rank
             self._stage = [torch.zeros(self.slot_floats, dtype=torch.float32, device=self.device) for _ in range(2)]
@@ -147,14 +152,22 @@ class ShardedDynamics:
                 self._recv = [[torch.zeros_like(self._send[0]) for _ in range(self.world)] for _ in range(self.depth)]
 
     # -- frame exchange ---------------------------------------------------------------------------
+    def _views(self, buf):
+        """(pos (n,3), quat (n,4)) views of a frame buffer, cached (slicing tensors is slow)."""
+        key = buf.data_ptr()
+        views = self._view_cache.get(key)
+        if views is None:
+            views = (buf[: 3 * self.n].view(self.n, 3), buf[self.qoff : self.qoff + 4 * self.n].view(self.n, 4))
+            self._view_cache[key] = views
+        return views
+
     def _fill(self, buf, position, orientation):
         torch = self.torch
         if position is None:
             raise ValueError("rank 0 is the reader rank and must supply the frame")
-        pos = torch.as_tensor(position)
-        quat = torch.as_tensor(orientation)
-        buf[: 3 * self.n].view(self.n, 3).copy_(pos, non_blocking=True)
-        buf[self.qoff : self.qoff + 4 * self.n].view(self.n, 4).copy_(quat, non_blocking=True)
+        pos_view, quat_view = self._views(buf)
+        pos_view.copy_(torch.as_tensor(position), non_blocking=True)
+        quat_view.copy_(torch.as_tensor(orientation), non_blocking=True)
 
     def post_frame(self, position=None, orientation=None):
         """Start the exchange of the next frame (rank 0 supplies it; others pass nothing).
@@ -199,23 +212,34 @@ class ShardedDynamics:
                 x0 = torch.cuda.Event(enable_timing=True)
                 x0.record(self._side)
             if self.rank == 0:
-                self._stage_i ^= 1
-                stage = self._stage[self._stage_i]
-                free = self._stage_free[self._stage_i]
-                if free is not None:
-                    self._side.wait_event(free)
                 self._side.wait_event(main.record_event())  # the caller's frame tensors are complete
-                self._fill(stage, position, orientation)
-                if self._mc_ptr:
-                    _lib.check(
-                        _lib.load().sdb_multicast_copy(
-                            stage.data_ptr(), self._mc_ptr + 4 * slot * self.slot_floats, 4 * self.slot_floats, 0,
-                            self._side.cuda_stream,
-                        )
-                    )
+                pos_t, quat_t = torch.as_tensor(position), torch.as_tensor(orientation)
+                direct = (
+                    self._mc_ptr
+                    and pos_t.is_cuda and quat_t.is_cuda
+                    and pos_t.dtype == torch.float32 and quat_t.dtype == torch.float32
+                    and pos_t.is_contiguous() and quat_t.is_contiguous()
+                    and (12 * self.n) % 16 == 0 and pos_t.data_ptr() % 16 == 0 and quat_t.data_ptr() % 16 == 0
+                )
+                lib = _lib.load()
+                base = self._mc_ptr + 4 * slot * self.slot_floats
+                if direct:
+                    # device-resident frame: multicast straight from the caller's tensors (the caller keeps
+                    # them alive and unchanged until the step that consumes this frame has been enqueued)
+                    _lib.check(lib.sdb_multicast_copy(pos_t.data_ptr(), base, 12 * self.n, self._mc_blocks, self._side.cuda_stream))
+                    _lib.check(lib.sdb_multicast_copy(quat_t.data_ptr(), base + 4 * self.qoff, 16 * self.n, self._mc_blocks, self._side.cuda_stream))
                 else:
-                    buf.copy_(stage, non_blocking=True)
-                self._stage_free[self._stage_i] = self._side.record_event()
+                    self._stage_i ^= 1
+                    stage = self._stage[self._stage_i]
+                    free = self._stage_free[self._stage_i]
+                    if free is not None:
+                        self._side.wait_event(free)
+                    self._fill(stage, pos_t, quat_t)
+                    if self._mc_ptr:
+                        _lib.check(lib.sdb_multicast_copy(stage.data_ptr(), base, 4 * self.slot_floats, self._mc_blocks, self._side.cuda_stream))
+                    else:
+                        buf.copy_(stage, non_blocking=True)
+                    self._stage_free[self._stage_i] = self._side.record_event()
             self._hdl.barrier(channel=0)
             if self.rank != 0 and not self._mc_ptr:
                 lo = slot * self.slot_floats
@@ -227,10 +251,7 @@ class ShardedDynamics:
         return (slot, None, ready)
 
     def _frame_views(self, slot):
-        buf = self.frames[slot]
-        pos = buf[: 3 * self.n].view(self.n, 3)
-        quat = buf[self.qoff : self.qoff + 4 * self.n].view(self.n, 4)
-        return pos, quat
+        return self._views(self.frames[slot])
 
     # -- one frame ------------------------------------------------------------------------------------
     def step(self, timestep, active, handle, gather=True):
@@ -255,11 +276,15 @@ class ShardedDynamics:
             else:
                 main.wait_event(ready)  # frame uploaded and delivered
         pos, quat = self._frame_views(slot)
-        local = partition(active, self.rank, self.world)
-        if len(local) > self.max_local:
-            raise ValueError(f"{len(local)} local origins exceed max_local={self.max_local}")
-        for k in active:
-            self._start.setdefault(k, int(timestep))
+        if active == self._last_active:  # steady state: the same origins as in the previous frame
+            local = self._last_local
+        else:
+            local = partition(active, self.rank, self.world)
+            if len(local) > self.max_local:
+                raise ValueError(f"{len(local)} local origins exceed max_local={self.max_local}")
+            for k in active:
+                self._start.setdefault(k, int(timestep))
+            self._last_active, self._last_local = list(active), local
         keys, timediffs, sums = self.step_fn(timestep, pos, quat, local) if local else ([], [], None)
         if keys != local:
             # the engine may reorder origins (grouping by previous sample): restore `local` order

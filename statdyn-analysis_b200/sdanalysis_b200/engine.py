@@ -229,10 +229,11 @@ def finalize_table(sums, timediffs, n, *, distance=None, overlap_k=None, n_sites
 
 # ----------------------------------------------------------------------------------------------
 class _PoolFrame:
-    __slots__ = ("planes", "refs", "has_orientation")
+    __slots__ = ("planes", "refs", "has_orientation", "ptr")
 
     def __init__(self, planes):
         self.planes = planes
+        self.ptr = planes.data_ptr()
         self.refs = 0
         self.has_orientation = True
 
@@ -369,7 +370,6 @@ class DynamicsEngine:
         import os
 
         self._origin_flags = ORIGIN_HISTORY if os.environ.get("SDB_OV_PREDICT", "1") != "0" else 0
-        self.profile = None  # set to a list to collect (name, start_event, end_event) per kernel group
         self._sites_c = None if self.mol_sites is None else _lib.float_array(self.mol_sites.reshape(-1))
         self.frames_seen = 0
         self.updates = 0  # molecule x origin updates performed
@@ -390,9 +390,18 @@ class DynamicsEngine:
         )
         self._sums_dev = [torch.zeros((cap, SDB_NSUM), dtype=torch.float64, device=dev) for _ in range(self._ring_depth)]
         self._partials = torch.empty((cap, self._n_parts, SDB_NSUM), dtype=torch.float64, device=dev)
+        self._ov_ws_ptr = 0
         if self.compute_overlap and self.overlap_k > 0:
             nbytes = int(self.lib.sdb_overlap_ws_bytes(cap, self.n))
             self._ov_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._ov_ws_ptr = self._ov_ws.data_ptr()
+        # raw pointers / numpy views used every frame (tensor.data_ptr() and .numpy() are slow)
+        self._desc_host = [t.numpy() for t in self._desc_ring.bufs]
+        self._desc_host_ptr = [t.data_ptr() for t in self._desc_ring.bufs]
+        self._desc_dev_ptr = [t.data_ptr() for t in self._desc_dev]
+        self._sums_host_ptr = [t.data_ptr() for t in self._sums_ring.bufs]
+        self._sums_dev_ptr = [t.data_ptr() for t in self._sums_dev]
+        self._partials_ptr = self._partials.data_ptr()
 
     def _stage_frame(self, position, orientation):
         """Return device tensors (pos (N,3) f32, quat (N,4) f32 or None).
@@ -581,7 +590,7 @@ class DynamicsEngine:
                 if timediffs and max(timediffs) >= MAX_STATUS:
                     raise OverflowError("time difference outside [0, 2**32-1): passage times are 32-bit on the device")
                 sdesc = plan["sdesc"]
-                sdesc["d_prev"] = plan["prev"].planes.data_ptr()
+                sdesc["d_prev"] = plan["prev"].ptr
                 seg_count_max = plan["seg_count_max"]
                 n_segments = len(sdesc)
                 fast = True
@@ -615,7 +624,7 @@ class DynamicsEngine:
                     size = chunk or max(8, math.ceil(len(members) * blocks_per_segment / target_blocks))
                     for first in range(0, len(members), size):
                         part = members[first : first + size]
-                        seg_rows.append((0 if prev is None else prev.planes.data_ptr(), flags, len(ordered), len(part)))
+                        seg_rows.append((0 if prev is None else prev.ptr, flags, len(ordered), len(part)))
                         ordered.extend(part)
                 if fresh:
                     flags = SEG_NO_ROTATION if quat is None else 0
@@ -645,14 +654,9 @@ class DynamicsEngine:
             ri, pinned = self._desc_ring.acquire()
             ob, sb = odesc.nbytes, sdesc.nbytes
             seg_off = (ob + 15) // 16 * 16
-            host = pinned.numpy()
+            host = self._desc_host[ri]
             host[:ob] = odesc.view(np.uint8)
             host[seg_off : seg_off + sb] = sdesc.view(np.uint8)
-            ddev = self._desc_dev[ri]
-            ddev[: seg_off + sb].copy_(pinned[: seg_off + sb], non_blocking=True)
-            self._desc_ring.release(ri)
-            d_origins = ddev.data_ptr()
-            d_segments = d_origins + seg_off
 
             # ---- the frame that becomes everybody's previous sample ---------------------------
             new_prev = None
@@ -662,74 +666,45 @@ class DynamicsEngine:
 
             si, sums_pinned = self._sums_ring.acquire()
             sums_dev = self._sums_dev[si]
-            stream = _lib.stream_ptr(self.device)
             params = self.params
             params.do_sums = int(do_sums)
-            prof = self.profile
-            if prof is not None:
-                ev0 = torch.cuda.Event(enable_timing=True)
-                ev0.record()
             use_ov = do_sums and self.compute_overlap and self.overlap_k > 0
-            ov_ws = self._ov_ws.data_ptr() if use_ov else 0
-            if use_ov:
-                # sample the updated keys of every origin and bracket the k-th largest of each array
-                _lib.check(
-                    lib.sdb_overlap_prepare(
-                        params, _lib.ptr(pos), _lib.ptr(quat), d_origins, n_active, d_segments, n_segments,
-                        seg_count_max, self.overlap_k, ov_ws, self._cap, stream,
-                    )
-                )
-            if prof is not None:
-                ev1 = torch.cuda.Event(enable_timing=True)
-                ev1.record()
+            want_host = do_sums and to_host
+            # one native call enqueues the whole frame: descriptor upload, overlap sampling/brackets, the
+            # fused dynamics kernel, struct, overlap resolve, download of the sums (csrc/frame_step.cu)
             _lib.check(
-                lib.sdb_dyn_step(
+                lib.sdb_frame_step(
                     params,
                     _lib.ptr(pos),
                     _lib.ptr(quat),
-                    0 if new_prev is None else new_prev.planes.data_ptr(),
-                    d_origins,
+                    0 if new_prev is None else new_prev.ptr,
+                    self._desc_host_ptr[ri],
+                    self._desc_dev_ptr[ri],
+                    seg_off + sb,
+                    seg_off,
                     n_active,
-                    d_segments,
                     n_segments,
-                    self._partials.data_ptr(),
-                    sums_dev.data_ptr(),
-                    ov_ws,
+                    seg_count_max,
+                    self._partials_ptr,
+                    self._sums_dev_ptr[si],
+                    self._sums_host_ptr[si] if want_host else 0,
+                    self._ov_ws_ptr if use_ov else 0,
                     self._cap,
-                    stream,
+                    self.overlap_k if use_ov else 0,
+                    self._sites_c if (do_sums and self.compute_struct) else None,
+                    len(self.mol_sites) if (do_sums and self.compute_struct) else 0,
+                    float(self.distance) if self.distance is not None else 0.0,
+                    self.struct_mode,
+                    _lib.stream_ptr(self.device),
                 )
             )
-            if prof is not None:
-                ev2 = torch.cuda.Event(enable_timing=True)
-                ev2.record()
-            if do_sums and self.compute_struct:
-                _lib.check(
-                    lib.sdb_struct(
-                        d_origins, n_active, self.n, self.stride, self._sites_c, len(self.mol_sites),
-                        float(self.distance), self.struct_mode, sums_dev.data_ptr(), stream,
-                    )
-                )
-            if prof is not None:
-                ev3 = torch.cuda.Event(enable_timing=True)
-                ev3.record()
-            if use_ov:
-                _lib.check(
-                    lib.sdb_overlap_resolve(
-                        d_origins, n_active, self.n, self.stride, self.overlap_k, ov_ws, self._cap,
-                        sums_dev.data_ptr(), stream,
-                    )
-                )
-            if prof is not None:
-                ev4 = torch.cuda.Event(enable_timing=True)
-                ev4.record()
-                prof.append((n_active, ev0, ev1, ev2, ev3, ev4))
+            self._desc_ring.release(ri)
             if self._staged_slot is not None:
                 consumed = torch.cuda.Event()
                 consumed.record()
                 self._dev_consumed[self._staged_slot] = consumed
             event = None
-            if do_sums and to_host:
-                sums_pinned[:n_active].copy_(sums_dev[:n_active], non_blocking=True)
+            if want_host:
                 event = self._sums_ring.release(si)
                 self.d2h_bytes = n_active * SDB_NSUM * 8
 

@@ -65,7 +65,20 @@ def _worker(rank, world, port, out):
             if rank == 0:
                 want = float(pos.astype(np.float64).sum() + 3 * quat.astype(np.float64).sum())
                 results.append((keys, timediffs, sums.tolist(), want, active))
-        out.put((rank, calls, results))
+        # the same frames again with batched gathering: rows stay local until flush()
+        batched = ShardedDynamics(N_MOLS, step_fn, max_local=8, device="cpu", batch=4)
+        rng = np.random.default_rng(5)
+        flushed = []
+        for t in range(6):
+            pos = rng.normal(size=(N_MOLS, 3)).astype(np.float32)
+            quat = rng.normal(size=(N_MOLS, 4)).astype(np.float32)
+            active = list(range(min(t + 1, 5)))
+            handle = batched.post_frame(pos, quat) if rank == 0 else batched.post_frame()
+            got = batched.step(100 + t, active, handle, gather="batch")
+            if got:  # the batch filled up: step() flushed it
+                flushed.extend(got)
+        flushed.extend(batched.flush())
+        out.put((rank, calls, results, [(k, td, s.tolist()) for k, td, s in flushed]))
     finally:
         dist.destroy_process_group()
 
@@ -81,13 +94,13 @@ def test_sharded_step_broadcasts_frames_and_gathers_rows():
         p.start()
     got = {}
     for _ in procs:
-        rank, calls, results = out.get(timeout=100)
-        got[rank] = (calls, results)
+        rank, calls, results, flushed = out.get(timeout=100)
+        got[rank] = (calls, results, flushed)
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
     # each rank only ever advances the origins it owns
-    for rank, (calls, _) in got.items():
+    for rank, (calls, _, _) in got.items():
         assert all(owner_of(k, world) == rank for _, keys in calls for k in keys)
     # rank 0 sees every origin of every frame, in the order of `active`, with the right payload
     for t, (keys, timediffs, sums, want, active) in enumerate(got[0][1]):
@@ -98,3 +111,9 @@ def test_sharded_step_broadcasts_frames_and_gathers_rows():
         # every rank computed from the frame that rank 0 supplied
         assert np.allclose(sums[:, 2], want, rtol=1e-12)
         assert np.array_equal(sums[:, 3], [owner_of(k, world) for k in active])
+    # batched gathering returns the same rows, frame by frame, on rank 0 only
+    assert got[1][2] == []
+    assert len(got[0][2]) == len(got[0][1])
+    for (keys, timediffs, sums, _, _), (bkeys, btd, bsums) in zip(got[0][1], got[0][2]):
+        assert keys == bkeys and timediffs == btd
+        assert np.array_equal(np.array(sums), np.array(bsums))
