@@ -124,9 +124,33 @@ struct alignas(128) StepWarpShared {
     alignas(8) uint64_t bar[SDB_STAGES];
 };
 
+// Per flag byte: the interval of each key in which NO tracker of the molecule changes state,
+//   quiet  <=>  lo_d2 <= d2 < hi_d2  &&  lo_th <= |dtheta| < hi_th
+// (first passage, not fired: key < cut_gt; last passage: state 0 key < cut_gt, state 1 cut_lt <= key <
+// cut_irr, state 2 anything).  Built once per CTA; lets molecules that sit between two thresholds for
+// many frames skip the tracker slow path.
+__device__ __forceinline__ float4 sdb_quiet_interval(const SdbTracker* tr, int n_trackers, uint32_t fl)
+{
+    float4 q = make_float4(INFINITY, 0.0f, INFINITY, 0.0f);  // hi_d2, lo_d2, hi_th, lo_th
+    for (int t = 0; t < n_trackers; ++t) {
+        float hi = INFINITY, lo = 0.0f;
+        if (!tr[t].is_last) {
+            if (!((fl >> tr[t].bit) & 1u)) hi = tr[t].cut_gt;
+        } else {
+            const uint32_t st = (fl >> tr[t].bit) & 3u;
+            if (st == 0u) hi = tr[t].cut_gt;
+            else if (st == 1u) { hi = tr[t].cut_irr; lo = tr[t].cut_lt; }
+        }
+        if (tr[t].is_rotation) { q.z = fminf(q.z, hi); q.w = fmaxf(q.w, lo); }
+        else { q.x = fminf(q.x, hi); q.y = fmaxf(q.y, lo); }
+    }
+    return q;
+}
+
 // One warp tile (256 molecules) of one segment.  TAIL: the tile is the partial last one (bounds checks).
 template <bool SUMS, bool OV, bool TRACK, bool TAIL>
-__device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared& sh, const int part)
+__device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared& sh, const float4* quiet_tab,
+                                              const int part)
 {
     const int lane = threadIdx.x & 31;
     const int n = a.p.n;
@@ -409,13 +433,15 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
                         n_both += (uint32_t)(ar & at) >> 31;
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, is_cand);
-                    const int cs = n_cand + __popc(m & lanemask_lt);
-                    if (is_cand && cs < SDB_OV_STAGE) {
-                        sh.cand[0][cs] = (uint32_t)(j0[g] + e);
-                        sh.cand[1][cs] = (uint32_t)kr;
-                        sh.cand[2][cs] = (uint32_t)kt;
+                    if (m) {  // warp-uniform; with history-predicted brackets ~1 % of the molecules qualify
+                        const int cs = n_cand + __popc(m & lanemask_lt);
+                        if (is_cand && cs < SDB_OV_STAGE) {
+                            sh.cand[0][cs] = (uint32_t)(j0[g] + e);
+                            sh.cand[1][cs] = (uint32_t)kr;
+                            sh.cand[2][cs] = (uint32_t)kt;
+                        }
+                        n_cand += __popc(m);
                     }
-                    n_cand += __popc(m);
                 }
             }
             uint32_t fl4_new = fl4;
@@ -424,13 +450,13 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
                 const float m_th = fmaxf(fmaxf(th[0], th[1]), fmaxf(th[2], th[3]));
                 const bool quiet = (m_d2 < min_cut_d2 && m_th < min_cut_th && (fl4 & state1_x4) == 0u) ||
                                    (fl4 == done_x4 && !literal);
-                if (valid && !quiet) {  // rare: some tracker of some molecule of this group may change state
+                if (valid && !quiet) {  // some molecule of this group is above a cut or in an intermediate state
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (TAIL && j0[g] + e >= n) break;
                         const uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
-                        const bool quiet_e = (d2[e] < min_cut_d2 && th[e] < min_cut_th && (fl & state1_bits) == 0u) ||
-                                             (fl == done_pattern && !literal);
+                        const float4 q = quiet_tab[fl];
+                        const bool quiet_e = d2[e] < q.x && d2[e] >= q.y && th[e] < q.z && th[e] >= q.w && !literal;
                         if (quiet_e) continue;
                         const uint32_t fl_new = sdb_track(a.p.trackers, a.p.n_trackers, fl, d2[e], th[e],
                                                           sbase + j0[g] + e, stride, org.timediff, literal);
@@ -516,12 +542,18 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 4) dyn_step_kernel(const __
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StepWarpShared& sh = reinterpret_cast<StepWarpShared*>(smem_raw)[threadIdx.x >> 5];
+    float4* quiet_tab = reinterpret_cast<float4*>(smem_raw + sizeof(StepWarpShared) * SDB_BLOCK_WARPS);
+    if (TRACK) {
+        for (uint32_t fl = threadIdx.x; fl < 256u; fl += SDB_BLOCK_THREADS)
+            quiet_tab[fl] = sdb_quiet_interval(a.p.trackers, a.p.n_trackers, fl);
+        __syncthreads();
+    }
     const int part = blockIdx.x * SDB_BLOCK_WARPS + (threadIdx.x >> 5);  // warp tile index
     if (part >= a.n_parts) return;
     if (part < a.full_parts)
-        dyn_step_tile<SUMS, OV, TRACK, false>(a, sh, part);
+        dyn_step_tile<SUMS, OV, TRACK, false>(a, sh, quiet_tab, part);
     else
-        dyn_step_tile<SUMS, OV, TRACK, true>(a, sh, part);
+        dyn_step_tile<SUMS, OV, TRACK, true>(a, sh, quiet_tab, part);
 }
 
 // Sum the per-warp-tile partials of one origin: block = 256 threads = 16 sums x 16 strided readers.
@@ -631,7 +663,7 @@ extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, co
     a.full_parts = p.n / SDB_WARP_MOLS;
     const int variant = (p.do_sums ? 4 : 0) | (a.ov_on ? 2 : 0) | (p.n_trackers > 0 ? 1 : 0);
     const dim3 grid((a.n_parts + SDB_BLOCK_WARPS - 1) / SDB_BLOCK_WARPS, n_segments);
-    constexpr size_t smem = sizeof(StepWarpShared) * SDB_BLOCK_WARPS;
+    constexpr size_t smem = sizeof(StepWarpShared) * SDB_BLOCK_WARPS + 256 * sizeof(float4);
     auto launch = [&](void (*kernel)(const StepArgs)) -> int {
         static std::atomic<bool> configured[8][64];  // [variant][device]: opt in to > 48 KB of shared memory once
         int dev = 0;
