@@ -121,6 +121,10 @@ struct alignas(128) StepWarpShared {
     alignas(128) unsigned char stage[SDB_STAGES][SDB_STAGE_BYTES];
     float red[SDB_NFSUM][33];
     uint32_t cand[3][SDB_OV_STAGE];  // staged overlap candidates (idx, d2, |dtheta|)
+    // descriptors of the next origins (SdbOrigin + overlap bracket), fetched with cp.async three
+    // iterations ahead: with ~220 KB of shared memory per SM there is hardly any L1 left, so a plain load
+    // of a descriptor costs an L2 round trip at the top of every iteration
+    alignas(16) uint32_t desc[4][12];
     alignas(8) uint64_t bar[SDB_STAGES];
 };
 
@@ -167,7 +171,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
     // ---- start the pipeline: bulk copies of the first origins' state tiles -----------------------
     // Executed by the whole (converged) warp with warp-uniform operands; one elected lane issues.
     auto issue = [&](int oi, int slot) {
-        const SdbOrigin* od = a.origins + seg.first + oi;
+        const SdbOrigin* od = reinterpret_cast<const SdbOrigin*>(sh.desc[oi & 3]);
         const float* dsrc = od->d_delta + tile0;
         const uint32_t bar = sdb_smem_addr(&sh.bar[slot]);
         const uint32_t dst = sdb_smem_addr(sh.stage[slot]);
@@ -202,12 +206,26 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
                 : "memory");
         }
     };
+    // lanes 0, 1: the two halves of the SdbOrigin record; lane 2: the overlap bracket of that origin
+    auto fetch_desc = [&](int oi) {
+        if (lane < (OV && SUMS ? 3 : 2)) {
+            const char* src = lane < 2 ? reinterpret_cast<const char*>(a.origins + seg.first + oi) + 16 * lane
+                                       : reinterpret_cast<const char*>(a.ov.brackets + 4L * (seg.first + oi));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdb_smem_addr(&sh.desc[oi & 3][4 * lane])), "l"(src)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < SDB_STAGES; ++s) sdb_mbar_init(&sh.bar[s], 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+#pragma unroll
+    for (int s = 0; s < SDB_STAGES; ++s)
+        if (s < seg.count) fetch_desc(s);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < SDB_STAGES - 1; ++s)
@@ -329,9 +347,13 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
     for (int oi = 0; oi < seg.count; ++oi) {
         const int o = seg.first + oi;
         // the stage consumed in the previous iteration is free: prefetch origin oi + STAGES - 1 into it
+        // (its descriptor was fetched during the previous iteration), then fetch the next descriptor
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
         if (oi + SDB_STAGES - 1 < seg.count) issue(oi + SDB_STAGES - 1, pf_slot);
         pf_slot = pf_slot + 1 == SDB_STAGES ? 0 : pf_slot + 1;
-        const SdbOrigin org = a.origins[o];
+        if (oi + SDB_STAGES < seg.count) fetch_desc(oi + SDB_STAGES);
+        const SdbOrigin org = *reinterpret_cast<const SdbOrigin*>(sh.desc[oi & 3]);
         float* dbase = org.d_delta;
         uint8_t* fbase = org.d_flags;
         uint32_t* sbase = org.d_status;
@@ -377,7 +399,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
         int com_count = 0;
         // overlap: keys above the bracket of each array, and molecules inside a bracket (candidates)
         float4 br = make_float4(0.f, INFINITY, 0.f, INFINITY);  // lo_r, hi_r, lo_t, hi_t
-        if (ov) br = __ldg(reinterpret_cast<const float4*>(a.ov.brackets) + o);
+        if (ov) br = *reinterpret_cast<const float4*>(&sh.desc[oi & 3][8]);
         const int lo_r = __float_as_int(br.x), hi_r = __float_as_int(br.y);
         const int lo_t = __float_as_int(br.z), hi_t = __float_as_int(br.w);
         const uint32_t span_r = (uint32_t)(hi_r - lo_r), span_t = (uint32_t)(hi_t - lo_t);
@@ -471,27 +493,13 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
                 if (track && fl4_new != fl4) *reinterpret_cast<uint32_t*>(fbase + j0[g]) = fl4_new;
             }
         }
-        if (ov && n_cand > 0) {  // warp-uniform: append the staged candidates to the origin's dense list
-            uint32_t base = 0;
-            const bool fits = n_cand <= SDB_OV_STAGE;
-            if (lane == 0) {
-                if (fits) base = atomicAdd(a.ov.cand_cnt + 2 * o, (uint32_t)n_cand);
-                else a.ov.cand_cnt[2 * o + 1] = 1u;  // staging overflow: this origin takes the exact path
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            __syncwarp();
-            if (fits) {
-                if (base + (uint32_t)n_cand <= (uint32_t)a.ov.cand_cap) {
-                    const long row = (long)o * a.ov.cand_cap + base;
-                    for (int s = lane; s < n_cand; s += 32) {
-                        a.ov.cand_idx[row + s] = sh.cand[0][s];
-                        a.ov.cand_r[row + s] = sh.cand[1][s];
-                        a.ov.cand_t[row + s] = sh.cand[2][s];
-                    }
-                } else if (lane == 0) {
-                    a.ov.cand_cnt[2 * o + 1] = 1u;
-                }
-            }
+        // Append the staged candidates to the origin's dense list: the slot reservation (one atomic per
+        // warp tile) is issued here and its result is only consumed after the reduction below.
+        uint32_t cand_base = 0;
+        const bool cand_fits = n_cand <= SDB_OV_STAGE;
+        if (ov && n_cand > 0 && lane == 0) {
+            if (cand_fits) cand_base = atomicAdd(a.ov.cand_cnt + 2 * o, (uint32_t)n_cand);
+            else a.ov.cand_cnt[2 * o + 1] = 1u;  // staging overflow: this origin takes the exact path
         }
 
         if (do_sums) {
@@ -530,6 +538,19 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
                     out[SDB_S_OV_TABOVE] = (double)w_at;
                     out[SDB_S_OV_BOTH] = (double)w_both;
                 }
+            }
+        }
+        if (ov && n_cand > 0 && cand_fits) {  // warp-uniform
+            const uint32_t base = __shfl_sync(0xffffffffu, cand_base, 0);
+            if (base + (uint32_t)n_cand <= (uint32_t)a.ov.cand_cap) {
+                const long row = (long)o * a.ov.cand_cap + base;
+                for (int s = lane; s < n_cand; s += 32) {
+                    a.ov.cand_idx[row + s] = sh.cand[0][s];
+                    a.ov.cand_r[row + s] = sh.cand[1][s];
+                    a.ov.cand_t[row + s] = sh.cand[2][s];
+                }
+            } else if (lane == 0) {
+                a.ov.cand_cnt[2 * o + 1] = 1u;
             }
         }
         __syncwarp();  // every lane is done with this stage, the scratch and the candidate buffer
