@@ -52,6 +52,25 @@ __device__ __forceinline__ float sdb_cos_reduced(float x)
     return fmaf(-2.0f * sn, sn, 1.0f);
 }
 
+// The same polynomial on two molecules at once with Blackwell's packed f32x2 arithmetic
+// (FMUL2 / FFMA2: one issue slot for both lanes of the pair).
+__device__ __forceinline__ float2 sdb_cos_reduced2(float2 x)
+{
+    const float2 q = __fmul2_rn(x, make_float2(0.15915494309189535f, 0.15915494309189535f));
+    const float2 k = make_float2(rintf(q.x), rintf(q.y));
+    float2 r = __ffma2_rn(k, make_float2(-6.28125f, -6.28125f), x);
+    r = __ffma2_rn(k, make_float2(-1.9353071795864769e-3f, -1.9353071795864769e-3f), r);
+    const float2 h = __fmul2_rn(r, make_float2(0.5f, 0.5f)), h2 = __fmul2_rn(h, h);
+    float2 p = __ffma2_rn(h2, make_float2(1.6059043836821613e-10f, 1.6059043836821613e-10f),
+                          make_float2(-2.5052108385441720e-8f, -2.5052108385441720e-8f));
+    p = __ffma2_rn(h2, p, make_float2(2.7557319223985893e-6f, 2.7557319223985893e-6f));
+    p = __ffma2_rn(h2, p, make_float2(-1.9841269841269841e-4f, -1.9841269841269841e-4f));
+    p = __ffma2_rn(h2, p, make_float2(8.3333333333333332e-3f, 8.3333333333333332e-3f));
+    p = __ffma2_rn(h2, p, make_float2(-1.6666666666666666e-1f, -1.6666666666666666e-1f));
+    const float2 sn = __ffma2_rn(__fmul2_rn(h, h2), p, h);
+    return __ffma2_rn(__fmul2_rn(sn, make_float2(-2.0f, -2.0f)), sn, make_float2(1.0f, 1.0f));
+}
+
 __device__ __forceinline__ float sdb_sqrt_approx(float x)
 {
     float r;
@@ -394,8 +413,12 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
         const bool literal = org.flags & SDB_ORIGIN_LITERAL;
 
         float acc[SDB_NFSUM];
+        float2 acc2[SDB_NFSUM];  // full tiles: one partial sum per half of the molecule pairs
 #pragma unroll
-        for (int v = 0; v < SDB_NFSUM; ++v) acc[v] = 0.f;
+        for (int v = 0; v < SDB_NFSUM; ++v) {
+            acc[v] = 0.f;
+            acc2[v] = make_float2(0.f, 0.f);
+        }
         int com_count = 0;
         // overlap: keys above the bracket of each array, and molecules inside a bracket (candidates)
         float4 br = make_float4(0.f, INFINITY, 0.f, INFINITY);  // lo_r, hi_r, lo_t, hi_t
@@ -424,23 +447,56 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
             float ddy[4] = {dy.x, dy.y, dy.z, dy.w};
             float ddt[4] = {dt.x, dt.y, dt.z, dt.w};
             float d2[4], th[4];
+            if (!TAIL && do_sums) {
+                // full tile: molecules in pairs, packed f32x2 arithmetic (same roundings as the scalar path:
+                // every packed operation rounds each half to nearest like its scalar counterpart)
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const int e0 = 2 * p, e1 = 2 * p + 1;
+                    const float2 x = __fadd2_rn(make_float2(ddx[e0], ddx[e1]), make_float2(-wx[g][e0], -wx[g][e1]));
+                    const float2 y = __fadd2_rn(make_float2(ddy[e0], ddy[e1]), make_float2(-wy[g][e0], -wy[g][e1]));
+                    const float2 dd = __fadd2_rn(__fmul2_rn(x, x), __fmul2_rn(y, y));
+                    ddx[e0] = x.x; ddx[e1] = x.y;
+                    ddy[e0] = y.x; ddy[e1] = y.y;
+                    ddt[e0] = (float)((double)ddt[e0] + al[g][e0]);
+                    ddt[e1] = (float)((double)ddt[e1] + al[g][e1]);
+                    d2[e0] = dd.x; d2[e1] = dd.y;
+                    th[e0] = fabsf(ddt[e0]); th[e1] = fabsf(ddt[e1]);
+                    const float2 tt = make_float2(th[e0], th[e1]);
+                    const float2 t2 = __fmul2_rn(tt, tt);
+                    const float2 c = sdb_cos_reduced2(tt);
+                    const float2 sq = make_float2(sdb_sqrt_approx(dd.x), sdb_sqrt_approx(dd.y));
+                    acc2[SDB_S_DISP] = __fadd2_rn(acc2[SDB_S_DISP], sq);
+                    acc2[SDB_S_DISP2] = __fadd2_rn(acc2[SDB_S_DISP2], dd);
+                    acc2[SDB_S_DISP4] = __ffma2_rn(dd, dd, acc2[SDB_S_DISP4]);
+                    acc2[SDB_S_ROT] = __fadd2_rn(acc2[SDB_S_ROT], tt);
+                    acc2[SDB_S_ROT2] = __fadd2_rn(acc2[SDB_S_ROT2], t2);
+                    acc2[SDB_S_COS] = __fadd2_rn(acc2[SDB_S_COS], c);
+                    acc2[SDB_S_COS2] = __ffma2_rn(c, c, acc2[SDB_S_COS2]);  // sum cos^2; 2 s - n at the end
+                    acc2[SDB_S_ROT4] = __ffma2_rn(t2, t2, acc2[SDB_S_ROT4]);
+                    acc2[SDB_S_D2R2] = __ffma2_rn(dd, t2, acc2[SDB_S_D2R2]);
+                    com_count += (dd.x < com_cut) + (dd.y < com_cut);
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                sdb_apply_increment(ddx[e], ddy[e], ddt[e], wx[g][e], wy[g][e], al[g][e], d2[e], th[e]);
                 const bool live = !TAIL || j0[g] + e < n;
-                if (do_sums && live) {
-                    const float t2 = th[e] * th[e];
-                    const float c = sdb_cos_reduced(th[e]);
-                    acc[SDB_S_DISP] += sdb_sqrt_approx(d2[e]);
-                    acc[SDB_S_DISP2] += d2[e];
-                    acc[SDB_S_DISP4] = fmaf(d2[e], d2[e], acc[SDB_S_DISP4]);
-                    acc[SDB_S_ROT] += th[e];
-                    acc[SDB_S_ROT2] += t2;
-                    acc[SDB_S_COS] += c;
-                    acc[SDB_S_COS2] = fmaf(c, c, acc[SDB_S_COS2]);  // sum cos^2; 2 s - n at the end
-                    acc[SDB_S_ROT4] = fmaf(t2, t2, acc[SDB_S_ROT4]);
-                    acc[SDB_S_D2R2] = fmaf(d2[e], t2, acc[SDB_S_D2R2]);
-                    com_count += d2[e] < com_cut;
+                if (TAIL || !do_sums) {
+                    sdb_apply_increment(ddx[e], ddy[e], ddt[e], wx[g][e], wy[g][e], al[g][e], d2[e], th[e]);
+                    if (do_sums && live) {
+                        const float t2 = th[e] * th[e];
+                        const float c = sdb_cos_reduced(th[e]);
+                        acc[SDB_S_DISP] += sdb_sqrt_approx(d2[e]);
+                        acc[SDB_S_DISP2] += d2[e];
+                        acc[SDB_S_DISP4] = fmaf(d2[e], d2[e], acc[SDB_S_DISP4]);
+                        acc[SDB_S_ROT] += th[e];
+                        acc[SDB_S_ROT2] += t2;
+                        acc[SDB_S_COS] += c;
+                        acc[SDB_S_COS2] = fmaf(c, c, acc[SDB_S_COS2]);  // sum cos^2; 2 s - n at the end
+                        acc[SDB_S_ROT4] = fmaf(t2, t2, acc[SDB_S_ROT4]);
+                        acc[SDB_S_D2R2] = fmaf(d2[e], t2, acc[SDB_S_D2R2]);
+                        com_count += d2[e] < com_cut;
+                    }
                 }
                 if (ov) {
                     // keys are non-negative floats: their bit patterns order like the values (and like the
@@ -507,7 +563,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
             // pairwise) and from there on in fp64: the thirds by shuffle, the warp tiles by
             // dyn_finalize_kernel.
 #pragma unroll
-            for (int v = 0; v < SDB_NFSUM; ++v) sh.red[v][lane] = acc[v];
+            for (int v = 0; v < SDB_NFSUM; ++v) sh.red[v][lane] = TAIL ? acc[v] : acc2[v].x + acc2[v].y;
             __syncwarp();
             double s = 0.0;
             const int v = lane % SDB_NFSUM, third = lane / SDB_NFSUM;
