@@ -37,6 +37,7 @@ UNIT = "updates/s"
 N_MOLS = 1_000_000
 N_ORIGINS = 200
 WAVE_NUMBER = 2.9
+PIPELINE = int(os.environ.get("SDB_BENCH_PIPELINE", "2"))  # frames in flight before the oldest result is read
 SIGMA_R, SIGMA_T = 0.01, 0.02
 WORKLOAD = (
     "configs[3]: synthetic 2D Trimer liquid, 1M molecules, 200 time-origins, dense linear schedule "
@@ -213,7 +214,7 @@ def run_gpu(args):
     from sdanalysis_b200.synthetic import box_for
 
     def make_engine():
-        return DynamicsEngine(n, box_for(n), WAVE_NUMBER, mol_sites=Trimer().positions, device=device, ring_depth=4)
+        return DynamicsEngine(n, box_for(n), WAVE_NUMBER, mol_sites=Trimer().positions, device=device, ring_depth=PIPELINE + 2)
 
     n_frames = warmup + steps
 
@@ -244,7 +245,29 @@ def run_gpu(args):
         torch.cuda.synchronize()
         # the frames of the measured steps
         frames = []
-        if rank == 0:
+        shared_host = host_frames and world > 1
+        if shared_host:
+            # e2e with several GPUs: the frames sit in page-locked HOST memory that every rank can read
+            # (a shared mapping, like a memory-mapped trajectory file); each rank uploads its 1/R slice
+            # over its own PCIe link inside the timed region and multicasts it to all ranks over NVLink
+            path = f"/dev/shm/sdb_bench_{os.environ.get('MASTER_PORT', '0')}.bin"
+            per_frame = 7 * n
+            if rank == 0:
+                mm = np.lib.format.open_memmap(path, mode="w+", dtype=np.float32, shape=(n_frames, per_frame))
+                for i in range(n_frames):
+                    pos, quat = walk.frame()
+                    walk.advance(1)
+                    mm[i, : 3 * n] = pos.cpu().numpy().reshape(-1)
+                    mm[i, 3 * n :] = quat.cpu().numpy().reshape(-1)
+                mm.flush()
+                del mm
+            dist.barrier()
+            mm = np.load(path, mmap_mode="r+")
+            shared = torch.from_numpy(mm)
+            rc = torch.cuda.cudart().cudaHostRegister(shared.data_ptr(), shared.numel() * 4, 0)
+            assert int(rc) == 0, f"cudaHostRegister failed: {rc}"
+            frames = [(shared[i, : 3 * n].view(n, 3), shared[i, 3 * n :].view(n, 4)) for i in range(n_frames)]
+        elif rank == 0:
             for _ in range(n_frames):
                 pos, quat = walk.frame()
                 walk.advance(1)
@@ -264,16 +287,17 @@ def run_gpu(args):
             if world > 1:
                 # software pipeline: the exchange of frame i + 1 is enqueued (side stream) before the
                 # kernels of frame i, so it overlaps them
+                post = sharded.post_frame_sliced if shared_host else sharded.post_frame
                 if i not in posted:
-                    posted[i] = sharded.post_frame(*frames[i])
+                    posted[i] = post(*frames[i])
                 if i + 1 < n_frames:
-                    posted[i + 1] = sharded.post_frame(*frames[i + 1])
+                    posted[i + 1] = post(*frames[i + 1])
                 # rows stay on the device; one gather per batch of frames (and at the end of the region)
                 sharded.step(ts, all_keys, posted.pop(i), gather="batch")
                 return
             pos, quat = frames[i]
             results.append(engine.step(ts, pos, quat, all_keys))
-            if len(results) > 2:
+            if len(results) > PIPELINE:
                 results.pop(0).table()
 
         def drain():
@@ -338,9 +362,16 @@ def run_gpu(args):
             print(f"[rank {rank}] host_frames={host_frames} frame-wait stall per step: mean {sum(st)/len(st):.3f} ms max {max(st):.3f} ms; "
                   f"exchange (side stream) mean {sum(xt)/max(len(xt),1):.3f} ms max {max(xt):.3f}\n", file=sys.stderr, flush=True)
         h2d, d2h = engine.h2d_bytes, engine.d2h_bytes
-        if world > 1:  # frames enter through rank 0, rows leave through rank 0
+        if world > 1:  # every rank uploads its slice of the frame (28 B per molecule in total); rows leave through rank 0
             h2d = 28 * n if host_frames else 0
             d2h = n_origins * 16 * 8
+        if shared_host:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaHostUnregister(shared.data_ptr())
+            del frames, shared, mm
+            dist.barrier()
+            if rank == 0:
+                os.unlink(path)
         del engine, sharded
         torch.cuda.empty_cache()
         if os.environ.get("SDB_SHARD_PROFILE") == "1":
@@ -411,6 +442,11 @@ def run_gpu(args):
         "clocks": dev["clocks"],
         "check": {k: float(dev["rows"][k][0]) for k in ("time", "msd", "alpha", "rot1", "overlap", "struct")}
         if isinstance(dev["rows"], dict) else None,
+        # the end-to-end phase replays the same frames from host memory: its rows must be identical
+        "e2e_rows_identical": bool(
+            isinstance(dev["rows"], dict) and isinstance(e2e["rows"], dict)
+            and all(np.array_equal(dev["rows"][k], e2e["rows"][k], equal_nan=True) for k in dev["rows"] if k != "keyframe")
+        ),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

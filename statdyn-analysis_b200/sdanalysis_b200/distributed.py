@@ -82,6 +82,8 @@ class ShardedDynamics:
         self._start = {}  # origin key -> timestep of its first frame (known to every rank)
         self._consumed = [None] * self.depth
         self._view_cache = {}
+        self._slice_stage = None
+        self.h2d_bytes = 0
         self._last_active, self._last_local = None, None
         self.stalls = [] if os.environ.get("SDB_SHARD_PROFILE") == "1" else None
         self.exchange_times = []
@@ -168,6 +170,61 @@ class ShardedDynamics:
         pos_view, quat_view = self._views(buf)
         pos_view.copy_(torch.as_tensor(position), non_blocking=True)
         quat_view.copy_(torch.as_tensor(orientation), non_blocking=True)
+
+    def slice_bounds(self, rank=None):
+        """Rows ``[lo, hi)`` of a frame that ``rank`` uploads in the sliced exchange (multiples of 4)."""
+        r = self.rank if rank is None else rank
+        per = (self.n // self.world) // 4 * 4
+        lo = r * per
+        hi = self.n if r == self.world - 1 else lo + per
+        return lo, hi
+
+    def post_frame_sliced(self, position, orientation):
+        """Exchange of a frame that EVERY rank can read in host memory (e.g. the same memory-mapped GSD
+        file, or a shared pinned buffer): rank r uploads only rows ``slice_bounds(r)`` over its own PCIe
+        link and multicasts that slice into the frame slot of every rank, so no single host link carries
+        the whole frame.  Called by all ranks with the same frame; returns a handle for :meth:`step`."""
+        torch = self.torch
+        if self.exchange != "multicast" or not self._mc_ptr:
+            return self.post_frame(position if self.rank == 0 else None, orientation if self.rank == 0 else None)
+        self._slot = (self._slot + 1) % self.depth
+        slot = self._slot
+        lo, hi = self.slice_bounds()
+        pos_t, quat_t = torch.as_tensor(position), torch.as_tensor(orientation)
+        if self._slice_stage is None:
+            self._slice_stage = [
+                (torch.empty((hi - lo, 3), dtype=torch.float32, device=self.device),
+                 torch.empty((hi - lo, 4), dtype=torch.float32, device=self.device))
+                for _ in range(2)
+            ]
+            self._slice_free = [None, None]
+            self._slice_i = 0
+        with torch.cuda.stream(self._side):
+            nxt = self._consumed[(slot + 1) % self.depth]
+            if nxt is not None:
+                self._side.wait_event(nxt)
+            if self.stalls is not None:
+                x0 = torch.cuda.Event(enable_timing=True)
+                x0.record(self._side)
+            self._slice_i ^= 1
+            spos, squat = self._slice_stage[self._slice_i]
+            free = self._slice_free[self._slice_i]
+            if free is not None:
+                self._side.wait_event(free)
+            spos.copy_(pos_t[lo:hi], non_blocking=True)
+            squat.copy_(quat_t[lo:hi], non_blocking=True)
+            lib = _lib.load()
+            base = self._mc_ptr + 4 * slot * self.slot_floats
+            _lib.check(lib.sdb_multicast_copy(spos.data_ptr(), base + 12 * lo, 12 * (hi - lo), self._mc_blocks, self._side.cuda_stream))
+            _lib.check(lib.sdb_multicast_copy(squat.data_ptr(), base + 4 * self.qoff + 16 * lo, 16 * (hi - lo), self._mc_blocks, self._side.cuda_stream))
+            self._slice_free[self._slice_i] = self._side.record_event()
+            self._hdl.barrier(channel=0)
+            ready = torch.cuda.Event(enable_timing=self.stalls is not None)
+            ready.record(self._side)
+            if self.stalls is not None:
+                self.exchange_times.append((x0, ready))
+        self.h2d_bytes = 28 * (hi - lo)
+        return (slot, None, ready)
 
     def post_frame(self, position=None, orientation=None):
         """Start the exchange of the next frame (rank 0 supplies it; others pass nothing).
