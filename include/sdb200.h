@@ -239,6 +239,17 @@ uint64_t sdb_launch_count(void);
 double sdb_test_rot_increment(float w, float z, float pw, float pz, int32_t* bad);
 void sdb_test_wrap2d(float lx, float ly, float xy, float vx, float vy, float* ox, float* oy);
 
+/* ---- intermediate scattering function -----------------------------------------------------------
+ * Dynamics.compute_isf (dynamics.py:233-235; wave vectors :105-112): for every origin the SUM over
+ * molecules of the mean over `angular_resolution` wave vectors of length `wave_number` of
+ * cos(k . dr); divide by n for the reference's value.  d_out double[n_origins] (cleared by the call).
+ * sdb_isf takes one (x, y) array pair whose components are elem_stride floats apart per molecule
+ * ((N,3) row-major displacement array: d_dx = base, d_dy = base + 1, elem_stride = 3). */
+int sdb_isf_origins(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride,
+                    double wave_number, int32_t angular_resolution, double* d_out, void* stream);
+int sdb_isf(const float* d_dx, const float* d_dy, int32_t elem_stride, int32_t n, double wave_number,
+            int32_t angular_resolution, double* d_out, void* stream);
+
 /* ---- one call per frame -------------------------------------------------------------------------
  * The body of the reference hot loop (read/_read.py:134-153) for every active origin, enqueued from
  * native code: upload of the descriptor block (h_desc, pinned: n_origins SdbOrigin records, then at

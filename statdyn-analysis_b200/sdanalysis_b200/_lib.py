@@ -38,6 +38,8 @@ EXPORTS = (
     "sdb_overlap_stats",
     "sdb_multicast_copy",
     "sdb_frame_step",
+    "sdb_isf_origins",
+    "sdb_isf",
     "sdb_profile_enable",
     "sdb_profile_collect",
     "sdb_first_passage",
@@ -143,6 +145,8 @@ def load():
             [POINTER(SdbDynParams), P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int32, P, P, P, P, c_int32,
              c_int32, POINTER(c_float), c_int32, ctypes.c_double, c_int32, P],
         ),
+        "sdb_isf_origins": (c_int32, [P, c_int32, c_int32, c_int32, c_double, c_int32, P, P]),
+        "sdb_isf": (c_int32, [P, P, c_int32, c_int32, c_double, c_int32, P, P]),
         "sdb_profile_enable": (None, [c_int32]),
         "sdb_profile_collect": (c_int32, [POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
         "sdb_first_passage": (c_int32, [P, c_int32, c_int32, c_double, c_int64, P, P]),

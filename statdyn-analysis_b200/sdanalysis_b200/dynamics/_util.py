@@ -187,6 +187,26 @@ class TrackedMotion:
         host = norms.cpu().numpy()
         return host[0], host[1]
 
+    def isf(self, wave_number, angular_resolution=360):
+        """Mean over ``angular_resolution`` wave vectors and over the molecules of ``cos(k . dr)``
+        (``Dynamics.compute_isf``, reference ``dynamics.py:233-235``), evaluated on the device."""
+        torch, lib = _lib.torch(), _lib.load()
+        if self._engine is not None:
+            eng = self._engine
+            delta = eng.origins[0].delta
+            device, n = eng.device, eng.n
+            args = (delta.data_ptr(), delta.data_ptr() + 4 * eng.stride, 1)
+        else:
+            gen = self._general
+            device, n = gen.device, gen.n
+            args = (gen.dtrans.data_ptr(), gen.dtrans.data_ptr() + 4, 3)
+        with torch.cuda.device(device):
+            out = torch.zeros(1, dtype=torch.float64, device=device)
+            _lib.check(
+                lib.sdb_isf(*args, n, float(wave_number), int(angular_resolution), out.data_ptr(), _lib.stream_ptr(device))
+            )
+            return float(out.item()) / n
+
     def current_row(self, timediff=0):
         """The ``compute_all`` quantities of the current state without adding a sample."""
         if self._engine is not None:

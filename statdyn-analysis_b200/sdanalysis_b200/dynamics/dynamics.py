@@ -52,6 +52,7 @@ class Dynamics:
         self.timestep = timestep
         self.num_particles = position.shape[0]
         self.wave_number = wave_number
+        self.angular_resolution = int(angular_resolution)
         options = dict(wave_number=wave_number, mol_sites=self.mol_vector, struct_mode=struct_mode)
         self.motion = TrackedMotion(
             create_freud_box(np.asarray(box, dtype=np.float64), is_2D=is2d),
@@ -132,10 +133,8 @@ class Dynamics:
         return self._current()["msr"]
 
     def compute_isf(self) -> float:
-        raise NotImplementedError(
-            "the intermediate scattering function is not on the accelerated path (SURVEY 8f-3); "
-            "it is off by default in the reference (dynamics.py:364-366)"
-        )
+        """Intermediate scattering function (reference ``dynamics.py:233-235``), ``csrc/isf.cu``."""
+        return self.motion.isf(self.wave_number, self.angular_resolution)
 
     def compute_rotational_relax1(self) -> float:
         return self._current()["rot1"]
@@ -174,7 +173,7 @@ class Dynamics:
         if self.mol_vector is None or self.motion.previous_orientation is None:
             row["struct"] = np.nan
         if scattering_function and self.wave_number is not None:
-            logger.warning("scattering_function requested: not on the accelerated path, left as NaN")
+            row["scattering_function"] = self.compute_isf()
         self._row = row
         return dict(row)
 

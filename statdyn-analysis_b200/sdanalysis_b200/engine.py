@@ -278,12 +278,13 @@ class _Ring:
 class StepResult:
     """Handle to the sums of one engine step; ``rows()`` waits for the device and finalises."""
 
-    def __init__(self, engine, keys, timediffs, sums_host, event):
+    def __init__(self, engine, keys, timediffs, sums_host, event, isf_host=None):
         self.engine = engine
         self.keys = keys
         self.timediffs = timediffs
         self._sums = sums_host
         self._event = event
+        self._isf = isf_host  # per-origin sums of the angular mean of cos(k . dr), or None
 
     def sums(self):
         if self._event is not None:
@@ -294,12 +295,18 @@ class StepResult:
     def rows(self, check=True, strict=True):
         """One dict of the 15 ``compute_all`` quantities per active origin, in ``keys`` order.
         ``strict``: raise ZeroDivisionError for N < 10 like ``mobile_overlap`` does in compute_all."""
-        return self.engine.finalize_rows(self.sums(), self.timediffs, check=check, strict=strict)
+        rows = self.engine.finalize_rows(self.sums(), self.timediffs, check=check, strict=strict)
+        if self._isf is not None:
+            for row, value in zip(rows, self._isf):
+                row["scattering_function"] = float(value) / self.engine.n
+        return rows
 
     def table(self, check=True, strict=True):
         """The same quantities as columns: ``{quantity: (A,) array}`` plus ``keyframe`` (vectorised over
         the active origins; this is what the ``dynamics`` table of ``process_file`` is assembled from)."""
         table = self.engine.finalize_table(self.sums(), self.timediffs, check=check, strict=strict)
+        if self._isf is not None:
+            table["scattering_function"] = np.asarray(self._isf, dtype=np.float64) / self.engine.n
         table["keyframe"] = list(self.keys)
         return table
 
@@ -320,6 +327,8 @@ class DynamicsEngine:
         device=None,
         ring_depth=3,
         overlap_fraction=0.1,
+        compute_isf=False,
+        angular_resolution=360,
     ):
         self.torch = torch = _lib.torch()
         self.device = _lib.require_cuda(device)
@@ -343,6 +352,10 @@ class DynamicsEngine:
         self.compute_struct = (
             bool(compute_struct) and self.compute_sums and self.distance is not None and self.mol_sites is not None
         )
+        # intermediate scattering function (Dynamics.compute_isf, off by default like the reference's
+        # --scattering-function): one extra kernel per frame, csrc/isf.cu
+        self.compute_isf = bool(compute_isf) and self.compute_sums and wave_number is not None
+        self.angular_resolution = int(angular_resolution)
         if struct_mode not in ("reference", "physical"):
             raise ValueError("struct_mode must be 'reference' or 'physical'")
         self.struct_mode = 0 if struct_mode == "reference" else 1
@@ -395,6 +408,9 @@ class DynamicsEngine:
             nbytes = int(self.lib.sdb_overlap_ws_bytes(cap, self.n))
             self._ov_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             self._ov_ws_ptr = self._ov_ws.data_ptr()
+        if self.compute_isf:
+            self._isf_dev = [torch.zeros(cap, dtype=torch.float64, device=dev) for _ in range(self._ring_depth)]
+            self._isf_host = [torch.zeros(cap, dtype=torch.float64).pin_memory() for _ in range(self._ring_depth)]
         # raw pointers / numpy views used every frame (tensor.data_ptr() and .numpy() are slow)
         self._desc_host = [t.numpy() for t in self._desc_ring.bufs]
         self._desc_host_ptr = [t.data_ptr() for t in self._desc_ring.bufs]
@@ -699,6 +715,17 @@ class DynamicsEngine:
                 )
             )
             self._desc_ring.release(ri)
+            isf_host = None
+            if do_sums and self.compute_isf:
+                _lib.check(
+                    lib.sdb_isf_origins(
+                        self._desc_dev_ptr[ri], n_active, self.n, self.stride, float(self.wave_number),
+                        self.angular_resolution, self._isf_dev[si].data_ptr(), _lib.stream_ptr(self.device),
+                    )
+                )
+                if want_host:
+                    self._isf_host[si][:n_active].copy_(self._isf_dev[si][:n_active], non_blocking=True)
+                    isf_host = self._isf_host[si].numpy()[:n_active]
             if self._staged_slot is not None:
                 consumed = torch.cuda.Event()
                 consumed.record()
@@ -761,7 +788,7 @@ class DynamicsEngine:
             # device-resident result (multi-GPU gather path): valid until ring_depth further steps
             return keys, timediffs, (sums_dev[:n_active] if do_sums else None)
         sums_host = sums_pinned.numpy()[:n_active] if do_sums else None
-        return StepResult(self, keys, timediffs, sums_host, event)
+        return StepResult(self, keys, timediffs, sums_host, event, isf_host)
 
     # ------------------------------------------------------------------------------------------
     def finalize_rows(self, sums, timediffs, check=True, strict=True):

@@ -108,8 +108,6 @@ def process_frames(
     """Run the hot loop of ``process_file`` (reference ``_read.py:128-168``) over any iterator of
     ``(indexes, frame)`` pairs.  Rows are passed to ``sink(row)``; returns the engine (per-origin
     passage times stay on the device until ``engine.summary(key)`` is called)."""
-    if scattering_function:
-        logger.warning("scattering_function is not on the accelerated path; the column stays NaN")
     engine = None
     pending = deque()
 
@@ -142,6 +140,7 @@ def process_frames(
                 device=device,
                 struct_mode=struct_mode,
                 ring_depth=pipeline_depth + 1,
+                compute_isf=scattering_function,
             )
         try:
             pending.append(engine.step(frame.timestep, frame.position, frame.orientation, list(indexes)))

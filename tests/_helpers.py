@@ -11,7 +11,7 @@ RATIO_KEYS = ("alpha", "alpha_rot", "gamma")  # value = ratio - 1: compared on t
 RTOL = 1e-5  # BASELINE.json north_star: floating-point dynamics quantities within rtol 1e-5
 
 
-def oracle_process(frames, wave_number=WAVE_NUMBER, ulps=2):
+def oracle_process(frames, wave_number=WAVE_NUMBER, ulps=2, scattering_function=False):
     """frames: iterable of (indexes, frame).  Returns (rows, summaries, near) where ``near[key]`` is
     a dict tracker-name -> bool mask of molecules that ever came within ``ulps`` ulp of a cutoff of
     that tracker (those are excluded from the bit-exact comparison, as north_star allows)."""
@@ -27,7 +27,7 @@ def oracle_process(frames, wave_number=WAVE_NUMBER, ulps=2):
                 )
                 near[index] = {name: np.zeros(len(frame.position), dtype=bool) for name in keyframes[index][1].mol_relax}
             dyn, relax = keyframes[index]
-            row = dyn.compute_all(frame.timestep, frame.position, frame.orientation)
+            row = dyn.compute_all(frame.timestep, frame.position, frame.orientation, scattering_function=scattering_function)
             relax.add(frame.timestep, frame.position, frame.orientation)
             row["keyframe"] = index
             row["_tie"] = _overlap_tie(dyn)
@@ -78,4 +78,4 @@ def compare_rows(gpu_rows, ref_rows, n, n_sites=3, struct_slack=2):
             assert got["overlap"] == want["overlap"], f"overlap {where}"
         else:
             assert 0.0 <= got["overlap"] <= 1.0
-        assert np.isnan(got["scattering_function"])
+        assert np.isnan(got["scattering_function"]) == np.isnan(want["scattering_function"])
