@@ -633,22 +633,30 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 4) dyn_step_kernel(const __
         dyn_step_tile<SUMS, OV, TRACK, true>(a, sh, quiet_tab, part);
 }
 
-// Sum the per-warp-tile partials of one origin: block = 256 threads = 16 sums x 16 strided readers.
-__global__ void __launch_bounds__(256) dyn_finalize_kernel(const double* __restrict__ partials, int n_parts,
-                                                            double* __restrict__ sums, int with_ov)
+// Sum the per-warp-tile partials of one origin: block = 1024 threads = 16 sums x 64 strided readers,
+// four independent rows in flight per reader (the walk is latency bound: ~4k rows of 128 bytes).
+__global__ void __launch_bounds__(1024) dyn_finalize_kernel(const double* __restrict__ partials, int n_parts,
+                                                             double* __restrict__ sums, int with_ov)
 {
-    __shared__ double sh[16][17];
+    __shared__ double sh[64][17];
     const int o = blockIdx.x;
     const int v = threadIdx.x & 15, r = threadIdx.x >> 4;
-    const double* base = partials + (long)o * n_parts * SDB_NSUM;
-    double s = 0.0;
-    for (int p = r; p < n_parts; p += 16) s += base[(long)p * SDB_NSUM + v];
-    sh[r][v] = s;
+    const double* base = partials + (long)o * n_parts * SDB_NSUM + v;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = r;
+    for (; p + 192 < n_parts; p += 256) {
+        s0 += base[(long)p * SDB_NSUM];
+        s1 += base[(long)(p + 64) * SDB_NSUM];
+        s2 += base[(long)(p + 128) * SDB_NSUM];
+        s3 += base[(long)(p + 192) * SDB_NSUM];
+    }
+    for (; p < n_parts; p += 64) s0 += base[(long)p * SDB_NSUM];
+    sh[r][v] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (threadIdx.x < 16) {
         double t = 0.0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) t += sh[i][threadIdx.x];
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) t += sh[i][threadIdx.x];
         const int vv = threadIdx.x;
         // the struct / overlap slots are owned by their own kernels; spare slots are zeroed
         if (vv != SDB_S_STRUCT && vv != SDB_S_OVERLAP) {
@@ -766,7 +774,7 @@ extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, co
     if (lrc) return lrc;
     SDB_CHECK_LAUNCH("dyn_step_kernel");
     if (p.do_sums) {
-        dyn_finalize_kernel<<<n_origins, 256, 0, s>>>(d_partials, a.n_parts, d_sums, a.ov_on);
+        dyn_finalize_kernel<<<n_origins, 1024, 0, s>>>(d_partials, a.n_parts, d_sums, a.ov_on);
         SDB_CHECK_LAUNCH("dyn_finalize_kernel");
     }
     return SDB_OK;

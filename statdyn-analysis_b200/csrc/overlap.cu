@@ -128,15 +128,20 @@ __device__ void block_pick(const uint32_t* hist, int nbins, uint32_t remaining, 
     const int first = threadIdx.x * per;
     uint32_t mine = 0;
     for (int b = first; b < first + per && b < nbins; ++b) mine += hist[b];
-    scratch[threadIdx.x] = mine;
-    __syncthreads();
-    for (int off = 1; off < (int)blockDim.x; off <<= 1) {  // inclusive suffix sum over threads
-        const uint32_t add = threadIdx.x + off < blockDim.x ? scratch[threadIdx.x + off] : 0;
-        __syncthreads();
-        scratch[threadIdx.x] += add;
-        __syncthreads();
+    // inclusive suffix sum over the threads: shuffles inside a warp, one shared-memory hop across warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    uint32_t suffix = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t up = __shfl_down_sync(0xffffffffu, suffix, off);
+        if (lane + off < 32) suffix += up;
     }
-    uint32_t higher = scratch[threadIdx.x] - mine;
+    if (lane == 0) scratch[warp] = suffix;  // total of this warp
+    __syncthreads();
+    uint32_t later = 0;  // total of the warps after this one
+    for (int w = warp + 1; w < n_warps; ++w) later += scratch[w];
+    const uint32_t higher0 = suffix - mine + later;
+    uint32_t higher = higher0;
     if (higher < remaining && higher + mine >= remaining) {
         for (int b = min(first + per, nbins) - 1; b >= first; --b) {
             const uint32_t h = hist[b];

@@ -281,8 +281,16 @@ extern "C" int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t
                                               (size_t)n_origins, s),
                             "sdb_struct: clear");
     if (rc) return rc;
+    // grid.x blocks per origin, each striding over the 1024-molecule tiles; sized so that the grid is a
+    // whole number of waves (148 SMs x 5 resident blocks of 256 threads at 48 registers)
     const int tiles = (n + 1023) / 1024;
-    dim3 grid(tiles < 48 ? tiles : 48, n_origins);
+    const int base = tiles < 48 ? tiles : 48;
+    const long wave = 148L * 5;
+    const long waves = ((long)base * n_origins + wave - 1) / wave;
+    long gx = waves * wave / n_origins;
+    if (gx < 1) gx = 1;
+    if (gx > tiles) gx = tiles;
+    dim3 grid((unsigned)gx, n_origins);
     if (n_sites == 3 && mode == 0)
         struct3_kernel<<<grid, 256, 0, s>>>(a);
     else if (n_sites == 3)
