@@ -30,6 +30,21 @@ def create_wave_vector(wave_number: float, angular_resolution: int):
     return np.concatenate([np.cos(angles), np.sin(angles)], axis=1) * wave_number
 
 
+def molecule2particles(position: np.ndarray, orientation: np.ndarray, mol_vector: np.ndarray) -> np.ndarray:
+    """Reference ``dynamics/_util.py:42-54`` verbatim in behaviour, including the pairing of SURVEY trap
+    T2 (rotated sites are site-major, translations molecule-major).  Host-side helper: the hot path
+    evaluates the same rows inside ``csrc/struct.cu`` without materialising them."""
+    from ..util import rotate_vectors
+
+    if isinstance(orientation, tuple):
+        raise ValueError("Expecting numpy array found tuple", orientation)
+    if np.allclose(orientation, 0.0):
+        orientation[:, 0] = 1.0
+    rotated = np.concatenate([rotate_vectors(orientation, pos) for pos in mol_vector.astype(np.float32)])
+    translated = np.repeat(position, mol_vector.shape[0], axis=0)
+    return rotated + translated
+
+
 class _GeneralState:
     """(N,3) accumulators on the device, advanced by ``sdb_motion_general``."""
 

@@ -140,6 +140,18 @@ class _FusedTracker:
         raise RuntimeError("this tracker is advanced by its Relaxations object (fused on the device)")
 
 
+class StructRelaxations(MolecularRelaxation):
+    """First passage of every *site* of every molecule, reported as the per-molecule mean
+    (reference ``relaxations.py:297-305``; unused by the reference's driver)."""
+
+    def __init__(self, num_elements: int, threshold: float, molecule) -> None:
+        self.molecule = molecule
+        super().__init__(num_elements * self.molecule.num_particles, threshold)
+
+    def get_status(self):
+        return self._status.reshape((-1, self.molecule.num_particles)).mean(axis=1)
+
+
 def create_mol_relaxations(
     num_elements: int,
     threshold: float,

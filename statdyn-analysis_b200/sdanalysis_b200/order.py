@@ -85,6 +85,39 @@ def neighbour_analysis(
     return host
 
 
+class NeighbourQuery:
+    """What ``setup_neighbours`` returns (stands in for ``freud.locality.NearestNeighbors`` after
+    ``compute``): ``getNeighborList()`` (N,k) uint32, ``getRsqList()`` (N,k) f32 with -1 for a missing
+    neighbour, ``nlist.neighbor_counts`` (N,) uint32 -- all from one device cell-list build."""
+
+    def __init__(self, result):
+        self._result = result
+        self.nlist = self
+
+    def getNeighborList(self):
+        return self._result["nlist"]
+
+    def getRsqList(self):
+        return self._result["rsq"]
+
+    @property
+    def r_sq_list(self):
+        return self._result["rsq"]
+
+    @property
+    def neighbor_counts(self):
+        return self._result["counts"]
+
+
+def setup_neighbours(box, position, max_radius: float = 3.5, max_neighbours: int = 8, is_2D: bool = True):
+    """Reference ``order.py:174-183``: k nearest neighbours within ``max_radius`` (strict cut)."""
+    if not is_2D:
+        raise NotImplementedError("the cell-list kernel covers the reference's 2D boxes only")
+    return NeighbourQuery(
+        neighbour_analysis(box, position, None, max_radius, max_neighbours, want=("nlist", "rsq", "counts"))
+    )
+
+
 def compute_neighbours(box, position, max_radius: float = 3.5, max_neighbours: int = 8) -> np.ndarray:
     """Indices of the nearest neighbours of each molecule, (N, max_neighbours) uint32, sorted by
     distance, ``2**32 - 1`` marking a missing neighbour (reference ``order.py:186-207``)."""

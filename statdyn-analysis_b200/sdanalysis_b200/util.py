@@ -66,6 +66,68 @@ def z2quaternion(theta) -> np.ndarray:
     return q.astype(np.float32)
 
 
+def _qmul(a, b):
+    """Hamilton product of quaternion arrays (w, x, y, z), broadcasting."""
+    aw, ax, ay, az = np.moveaxis(np.asarray(a), -1, 0)
+    bw, bx, by, bz = np.moveaxis(np.asarray(b), -1, 0)
+    return np.stack(
+        [
+            aw * bw - ax * bx - ay * by - az * bz,
+            aw * bx + ax * bw + ay * bz - az * by,
+            aw * by - ax * bz + ay * bw + az * bx,
+            aw * bz + ax * by - ay * bx + az * bw,
+        ],
+        axis=-1,
+    )
+
+
+def _qconj(q):
+    q = np.array(q, copy=True)
+    q[..., 1:] *= -1
+    return q
+
+
+def rotate_vectors(quaternion, vector):
+    """``rowan.rotate``: q (0, v) q* (reference ``util.py:142-143``).  Host-side helper for a handful of
+    vectors; the per-site rotations of ``struct`` run in ``csrc/struct.cu``."""
+    quaternion = np.asarray(quaternion)
+    vector = np.asarray(vector)
+    v4 = np.concatenate([np.zeros(vector.shape[:-1] + (1,), dtype=vector.dtype), vector], axis=-1)
+    return _qmul(quaternion, _qmul(v4, _qconj(quaternion)))[..., 1:]
+
+
+def quaternion_rotation(initial, final):
+    """``rowan.geometry.intrinsic_distance``: |log(initial* final)| in [0, pi] (``util.py:138-139``)."""
+    p = _qmul(_qconj(np.asarray(initial, dtype=np.float64)), np.asarray(final, dtype=np.float64))
+    norm = np.linalg.norm(p, axis=-1)
+    vec = np.linalg.norm(p[..., 1:], axis=-1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ang = np.where(vec > 0, np.arccos(np.clip(p[..., 0] / norm, -1.0, 1.0)), 0.0)
+        return np.sqrt(np.log(norm) ** 2 + ang ** 2)
+
+
+def quaternion_angle(quaternion) -> np.ndarray:
+    """``rowan.geometry.angle``: 2 acos(w) (``util.py:146-147``)."""
+    return 2 * np.arccos(np.asarray(quaternion)[..., 0])
+
+
+def quaternion2z(quaternion: np.ndarray) -> np.ndarray:
+    """z-angle of ``rowan.to_euler`` (convention zyx, intrinsic), float32 (``util.py:160-167``)."""
+    q = np.asarray(quaternion, dtype=np.float64)
+    w, x, y, z = np.moveaxis(q, -1, 0)
+    s = 1.0 / np.sqrt(w * w + x * x + y * y + z * z)  # rowan.to_matrix scales by 1 / |q|
+    m10 = 2 * s * (x * y + z * w)
+    m00 = 1 - 2 * s * (y * y + z * z)
+    return np.arctan2(np.clip(m10, -1, 1), np.clip(m00, -1, 1)).astype(np.float32)
+
+
+def orientation2positions(mol, position: np.ndarray, orientation: np.ndarray) -> np.ndarray:
+    """Site positions, site-major (reference ``util.py:170-175``)."""
+    return np.tile(position, (mol.num_particles, 1)) + np.concatenate(
+        [rotate_vectors(orientation, pos) for pos in mol.positions]
+    )
+
+
 class Variables(NamedTuple):
     """Simulation variables encoded in a file name (reference ``util.py:33-88``)."""
 

@@ -165,3 +165,49 @@ def test_schedules_match_survey_counts():
     assert len(pairs) == 1001 and sum(len(i) for _, i in pairs) == 2405
     pairs = list(linear_schedule(1000, 10, 99))
     assert len(pairs[-1][1]) == 100 and sum(len(i) for _, i in pairs) == 50500
+
+
+def test_quaternion_helpers_match_the_rowan_restatement():
+    """util.rotate_vectors / quaternion_rotation / quaternion2z / z2quaternion (reference util.py:138-167)
+    against oracle/rowan_shim.py, and the reference's own golden vectors (test/util_test.py:235-250)."""
+    from oracle import rowan_shim as rowan
+    from sdanalysis_b200 import util
+
+    rng = np.random.default_rng(3)
+    q = rng.normal(size=(64, 4))
+    q /= np.linalg.norm(q, axis=1)[:, None]
+    p = rng.normal(size=(64, 4))
+    p /= np.linalg.norm(p, axis=1)[:, None]
+    v = rng.normal(size=(64, 3))
+    assert np.allclose(util.rotate_vectors(q, v), rowan.rotate(q, v), atol=1e-12)
+    assert np.allclose(util.quaternion_rotation(q, p), rowan.intrinsic_distance(q, p), atol=1e-12)
+    assert np.allclose(util.quaternion2z(q), rowan.to_euler(q)[:, 0], atol=1e-6)
+    theta = rng.uniform(-np.pi, np.pi, 64)
+    assert np.allclose(util.quaternion2z(util.z2quaternion(theta)), theta, atol=2e-7)
+    golden = [  # test/util_test.py:235-250: the four orientations of the p2gg crystal, one per quadrant
+        ([0.982_461_99, 0.0, 0.0, 0.186_462_98], 0.375_121_38),
+        ([0.209_398_27, 0.0, 0.0, 0.977_830_41], 2.719_673_4),
+        ([0.976_600_05, 0.0, 0.0, -0.215_063_53], -0.433_513_61),
+        ([-0.211_795_45, 0.0, 0.0, 0.977_314], -2.714_769_36),
+    ]
+    for quat, angle in golden:
+        assert np.allclose(util.quaternion2z(np.array([quat], dtype=np.float32)), angle)
+
+
+def test_molecule2particles_reproduces_the_reference_pairing():
+    """dynamics/_util.py:42-54: rotated sites are concatenated site-major, translations repeated
+    molecule-major (SURVEY trap T2) -- the helper keeps that behaviour, like csrc/struct.cu."""
+    from sdanalysis_b200.dynamics._util import molecule2particles
+    from sdanalysis_b200.molecules import Trimer
+
+    mol = Trimer()
+    n = 4
+    position = np.arange(3 * n, dtype=np.float32).reshape(n, 3)
+    orientation = np.zeros((n, 4), dtype=np.float32)
+    out = molecule2particles(position, orientation, mol.positions)
+    assert out.shape == (3 * n, 3)
+    sites = mol.positions.astype(np.float32)
+    for row in range(3 * n):
+        assert np.allclose(out[row], sites[row // n] + position[row // 3], atol=1e-6)
+    with pytest.raises(ValueError):
+        molecule2particles(position, (1, 0, 0, 0), mol.positions)

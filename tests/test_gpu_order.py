@@ -86,3 +86,16 @@ def test_isolated_molecules_have_no_neighbours():
     got = order.neighbour_analysis(box, pos, quat, 3.5, 8, want=("nlist", "rsq", "counts", "order"))
     assert np.all(got["nlist"] == MISSING) and np.all(got["rsq"] == -1) and np.all(got["counts"] == 0)
     assert np.all(got["order"] == 1.0)  # missing neighbours are replaced by the molecule itself
+
+
+def test_setup_neighbours_query_object(golden_dir):
+    """order.setup_neighbours (reference order.py:174-183): list, squared distances and counts of one
+    cell-list build agree with the individual functions."""
+    from sdanalysis_b200 import order
+
+    g = np.load(golden_dir / "liquid.npz")
+    query = order.setup_neighbours(g["box"], g["position"], 3.5, 8)
+    assert np.array_equal(query.getNeighborList(), order.compute_neighbours(g["box"], g["position"], 3.5, 8))
+    rsq = query.nlist.r_sq_list
+    assert np.allclose(np.sqrt(np.where(rsq < 0, 0, rsq)), order.relative_distances(g["box"], g["position"], 3.5, 8))
+    assert np.array_equal(np.minimum(query.nlist.neighbor_counts, 8), (query.getNeighborList() != 2 ** 32 - 1).sum(axis=1))

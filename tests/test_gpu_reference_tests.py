@@ -270,3 +270,23 @@ def test_crystal_known_answers(sd, crystal):
     assert np.all(sd.order.create_orient_ordering(0.60)(type("F", (), dict(box=box, position=pos, orientation=quat))))
     assert np.all(np.isfinite(sd.order.relative_distances(box, pos)))
     assert np.all(np.isfinite(sd.order.relative_orientations(box, pos, quat)))
+
+
+def test_struct_relaxations_and_factory(sd):
+    """relaxations.py:297-335: StructRelaxations reports the per-molecule mean over sites;
+    create_mol_relaxations validates its arguments and picks the tracker class."""
+    from sdanalysis_b200.dynamics import relaxations
+    from sdanalysis_b200.molecules import Trimer
+
+    tracker = relaxations.StructRelaxations(4, 0.5, Trimer())
+    tracker.add(3, np.array([1.0] * 3 + [0.0] * 9, dtype=np.float32))
+    status = tracker.get_status()
+    assert status.shape == (4,) and status[0] == 3 and np.all(status[1:] == 2 ** 32 - 1)
+    assert isinstance(relaxations.create_mol_relaxations(5, 0.4), relaxations.MolecularRelaxation)
+    last = relaxations.create_mol_relaxations(5, 0.4, last_passage=True)
+    assert isinstance(last, relaxations.LastMolecularRelaxation)
+    with pytest.raises(ValueError):
+        relaxations.create_mol_relaxations(5, -0.1)
+    with pytest.raises(ValueError):
+        relaxations.create_mol_relaxations(5, 0.4, last_passage=True, last_passage_cutoff=-1.0)
+    assert relaxations.RelaxationType["rotation"] is relaxations.RelaxationType.rotation
