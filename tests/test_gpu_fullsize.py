@@ -191,3 +191,46 @@ def test_predicted_overlap_brackets_match_sampled_ones(monkeypatch):
         walk.advance(1)
     assert cands[1][0] == cands[1][1] > 0  # no history yet: both engines sample
     assert all(p < s / 3 for p, s in cands[25:])  # old origin: predicted brackets are much tighter
+
+
+def test_four_million_molecules_config5_shape():
+    """BASELINE.json configs[4] molecule count (4 M, sigma_r = 0.03, LastMolecularRelaxation among the
+    six default trackers): sums against torch on the device state, passage-time ordering, and the
+    multi-tile / multi-segment indexing at the largest N of the configurations."""
+    import torch
+
+    from sdanalysis_b200.engine import DynamicsEngine
+    from sdanalysis_b200.molecules import Trimer
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    dev = torch.device("cuda", 0)
+    n = 4_000_000
+    walk = SyntheticTrimer(n, seed=5, sigma_r=0.03, sigma_theta=0.06, device=dev)
+    eng = DynamicsEngine(n, walk.box, WAVE, mol_sites=Trimer().positions, device=dev)
+    table = None
+    for t in range(10):
+        pos, quat = walk.frame()
+        active = [0] if t < 4 else [0, 1, 2]
+        table = eng.step(walk.timestep, pos, quat, active).table()
+        walk.advance(40)
+    d = eng.origins[0].delta[:, :n].double()
+    d2 = d[0] ** 2 + d[1] ** 2
+    th = d[2].abs()
+    np.testing.assert_allclose(table["msd"][0], d2.mean().item(), rtol=1e-6)
+    np.testing.assert_allclose(table["msr"][0], (th ** 2).mean().item(), rtol=1e-6)
+    np.testing.assert_allclose(table["rot1"][0], th.cos().mean().item(), rtol=1e-5, atol=1e-7)
+    dist = np.float32(np.pi / (2 * WAVE))
+    disp32 = torch.sqrt((eng.origins[0].delta[0, :n] ** 2 + eng.origins[0].delta[1, :n] ** 2))
+    assert abs(table["com_struct"][0] - (disp32 < float(dist)).double().mean().item()) <= 2 / n
+    k = n // 10
+    top_r = torch.topk(d2.float(), k).indices
+    top_t = torch.topk(th.float(), k).indices
+    both = np.intersect1d(top_r.cpu().numpy(), top_t.cpu().numpy()).size
+    assert abs(table["overlap"][0] * k - both) <= 2  # ties at the cut are broken by index
+    s = eng.summary(0)
+    unset = 2 ** 32 - 1
+    fired = s["tau_D"] != unset
+    assert fired.sum() > 0 and np.all(s["tau_F"][fired] <= s["tau_D"][fired])
+    last = s["tau_L"] != unset
+    assert last.sum() > 0 and np.all(s["tau_F"][last] <= s["tau_L"][last])
+    assert table["time"].tolist() == [360, 200, 200]
