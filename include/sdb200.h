@@ -111,8 +111,10 @@ typedef struct {
     int32_t first;        /* index of the first origin of the segment in the origin array */
     int32_t count;        /* number of origins in the segment */
     uint32_t flags;       /* SDB_SEG_* */
-    uint32_t reserved;
+    uint32_t reserved;    /* 0, or 1 + the index of the increment set precomputed by sdb_dyn_increments
+                             for this segment's previous sample */
 } SdbSegment;
+#define SDB_MAX_INC_SETS 4
 #define SDB_SEG_NO_ROTATION 1u /* either sample has no orientation: skip the rotation update
                                   (_util.py:150 "if previous_orientation is not None and ...") */
 #define SDB_SEG_ZERO_STEP 2u   /* no new sample: recompute the sums / trackers of the current state
@@ -130,11 +132,23 @@ typedef struct {
  *   d_sums  double[n_origins][SDB_NSUM] out, filled by the finalize kernel launched by this call
  *   d_ov_ws workspace of the bracketed `overlap` selection prepared by sdb_overlap_prepare for the
  *           same descriptors (NULL: no overlap bookkeeping), sized for ov_ws_origins origins
+ *   d_inc_ws / inc_sets  increments precomputed by sdb_dyn_increments for this frame (NULL / 0: every
+ *           segment computes its own); used by the segments whose `reserved` field names a set
  */
 int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
                  float* d_cur_compact, const SdbOrigin* d_origins, int32_t n_origins,
                  const SdbSegment* d_segments, int32_t n_segments, double* d_partials,
-                 double* d_sums, void* d_ov_ws, int32_t ov_ws_origins, void* stream);
+                 double* d_sums, void* d_ov_ws, int32_t ov_ws_origins, void* d_inc_ws,
+                 int32_t inc_sets, void* stream);
+/* Per-frame increments (minimum-image step and rotation increment of every molecule, the arithmetic of
+ * TrackedMotion.add _util.py:149-153) for up to SDB_MAX_INC_SETS previous samples h_prev[i] (device
+ * pointers to (x, y, qw, qz) planes; h_seg_flags[i] = SDB_SEG_NO_ROTATION or 0), computed once per
+ * frame instead of once per segment.  Also writes d_cur_compact (may be NULL).  d_ws holds
+ * sdb_dyn_increments_bytes(n, stride, n_sets) bytes. */
+size_t sdb_dyn_increments_bytes(int32_t n, int32_t stride, int32_t n_sets);
+int sdb_dyn_increments(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
+                       float* d_cur_compact, const void* const* h_prev, const uint32_t* h_seg_flags,
+                       int32_t n_sets, void* d_ws, void* stream);
 /* |dr| and |dtheta| of every molecule of one origin (compute_displacement / compute_rotation,
  * dynamics.py:179-181,217-219): d_disp, d_rot float[n] (either may be NULL). */
 int sdb_dyn_norms(const float* d_delta, int32_t n, int32_t stride, float* d_disp, float* d_rot,
@@ -257,13 +271,15 @@ int sdb_isf(const float* d_dx, const float* d_dy, int32_t elem_stride, int32_t n
  * sdb_overlap_prepare -> sdb_dyn_step -> sdb_struct -> sdb_overlap_resolve with the same meaning of
  * the arguments as those calls (overlap_k <= 0 or d_ov_ws NULL: no `overlap`; h_sites_xy NULL: no
  * `struct`), then the download of d_sums[n_origins][SDB_NSUM] to h_sums (pinned; NULL: stay on the
- * device).  Asynchronous on `stream`. */
+ * device).  inc_sets > 0: sdb_dyn_increments(h_inc_prev, h_inc_flags, inc_sets, d_inc_ws) runs first and
+ * the segments whose `reserved` field names a set use its increments.  Asynchronous on `stream`. */
 int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
                    float* d_cur_compact, const void* h_desc, void* d_desc, int32_t desc_bytes,
                    int32_t segments_offset, int32_t n_origins, int32_t n_segments,
                    int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
                    void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy,
-                   int32_t n_sites, double struct_dist, int32_t struct_mode, void* stream);
+                   int32_t n_sites, double struct_dist, int32_t struct_mode, const void* const* h_inc_prev,
+                   const uint32_t* h_inc_flags, int32_t inc_sets, void* d_inc_ws, void* stream);
 
 /* Per-kernel-group device times of sdb_frame_step (CUDA events on the launching stream), for
  * bench.py's roofline: groups 0 overlap prepare, 1 dyn_step + finalize, 2 struct, 3 overlap resolve.

@@ -29,7 +29,29 @@ struct StepArgs {
     int full_parts;  // number of complete 256-molecule tiles (a partial last tile may follow)
     int ov_on;  // bracketed overlap selection: count keys above the brackets, collect candidates
     SdbOvWorkspace ov;
+    // per-frame precomputed increments (dyn_increments_kernel), one set per distinct previous sample:
+    // wx, wy float[sets][stride], alpha double[sets][stride], bad uint32[sets][n_parts]; null: none
+    const float* inc_wx;
+    const float* inc_wy;
+    const double* inc_al;
+    const uint32_t* inc_bad;
 };
+
+// Layout of the increments workspace.
+struct IncLayout {
+    size_t off_wy, off_al, off_bad, bytes;
+};
+inline IncLayout sdb_inc_layout(int n, int stride, int n_sets)
+{
+    auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t n_parts = (size_t)((n + SDB_WARP_MOLS - 1) / SDB_WARP_MOLS);
+    IncLayout l;
+    l.off_wy = align(sizeof(float) * (size_t)stride * n_sets);
+    l.off_al = l.off_wy + align(sizeof(float) * (size_t)stride * n_sets);
+    l.off_bad = l.off_al + align(sizeof(double) * (size_t)stride * n_sets);
+    l.bytes = l.off_bad + align(sizeof(uint32_t) * n_parts * n_sets);
+    return l;
+}
 
 
 // cos(x) for x >= 0 with ~1e-7 absolute error: two-constant Cody-Waite reduction to [-pi, pi], then
@@ -170,8 +192,98 @@ __device__ __forceinline__ float4 sdb_quiet_interval(const SdbTracker* tr, int n
     return q;
 }
 
+// Phase 1 of a warp tile: the increments of this lane's 8 molecules for one previous sample.
+//   w = box.wrap(prev - cur)  (f32, freud operation order)     _util.py:149
+//   alpha = to_euler(q / q_prev)[0]  (f64)                     _util.py:150-153
+// Returns the lane's count of quaternion pairs rowan would reject (or that are not planar).
+template <bool TAIL>
+__device__ __forceinline__ int sdb_tile_increments(const StepArgs& a, const float* prev, uint32_t seg_flags, bool zero_step,
+                                                   bool write_compact, int part, int lane, int (&j0)[SDB_GROUPS],
+                                                   float (&wx)[SDB_GROUPS][4], float (&wy)[SDB_GROUPS][4],
+                                                   double (&al)[SDB_GROUPS][4])
+{
+    int bad = 0;
+    const int n = a.p.n;
+    const long stride = a.p.stride;
+    const bool rotate = (seg_flags & SDB_SEG_NO_ROTATION) == 0 && !zero_step;
+#pragma unroll
+    for (int g = 0; g < SDB_GROUPS; ++g) {
+        const int jg = part * SDB_WARP_MOLS + g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
+        j0[g] = jg;
+        float cx[4], cy[4], cw[4], cz[4];
+        if (zero_step || jg >= n) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                cx[e] = 0.f; cy[e] = 0.f; cw[e] = 1.f; cz[e] = 0.f;
+            }
+        } else if (!TAIL || jg + SDB_LANE_MOLS <= n) {
+            const float4 p0 = sdb_ldg4(a.pos + 3L * jg);
+            const float4 p1 = sdb_ldg4(a.pos + 3L * jg + 4);
+            const float4 p2 = sdb_ldg4(a.pos + 3L * jg + 8);
+            cx[0] = p0.x; cy[0] = p0.y;
+            cx[1] = p0.w; cy[1] = p1.x;
+            cx[2] = p1.z; cy[2] = p1.w;
+            cx[3] = p2.y; cy[3] = p2.z;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+                if (a.quat) q = sdb_ldg4(a.quat + 4L * (jg + e));
+                cw[e] = q.x; cz[e] = q.w;
+                bad += (q.y != 0.f) | (q.z != 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = jg + e;
+                const bool ok = j < n;
+                cx[e] = ok ? __ldg(a.pos + 3L * j) : 0.f;
+                cy[e] = ok ? __ldg(a.pos + 3L * j + 1) : 0.f;
+                float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+                if (ok && a.quat) q = sdb_ldg4(a.quat + 4L * j);
+                cw[e] = q.x; cz[e] = q.w;
+                bad += (q.y != 0.f) | (q.z != 0.f);
+            }
+        }
+        if (a.cur_compact && write_compact && !zero_step && jg < n) {
+            // planes are padded to a multiple of 4: whole-vector stores are safe
+            float* c = a.cur_compact + jg;
+            *reinterpret_cast<float4*>(c) = make_float4(cx[0], cx[1], cx[2], cx[3]);
+            *reinterpret_cast<float4*>(c + stride) = make_float4(cy[0], cy[1], cy[2], cy[3]);
+            *reinterpret_cast<float4*>(c + 2 * stride) = make_float4(cw[0], cw[1], cw[2], cw[3]);
+            *reinterpret_cast<float4*>(c + 3 * stride) = make_float4(cz[0], cz[1], cz[2], cz[3]);
+        }
+        float px[4], py[4], pw[4], pz[4];
+        if (prev != nullptr && jg < n && !zero_step) {
+            const float4 vx = sdb_ldg4(prev + jg);
+            const float4 vy = sdb_ldg4(prev + stride + jg);
+            const float4 vw = sdb_ldg4(prev + 2 * stride + jg);
+            const float4 vz = sdb_ldg4(prev + 3 * stride + jg);
+            px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
+            py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
+            pw[0] = vw.x; pw[1] = vw.y; pw[2] = vw.z; pw[3] = vw.w;
+            pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
+        } else {  // origin created at this frame: previous sample == current sample
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                px[e] = cx[e]; py[e] = cy[e]; pw[e] = cw[e]; pz[e] = cz[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            sdb_wrap2d(a.p.lx, a.p.ly, a.p.xy, SDB_FSUB(px[e], cx[e]), SDB_FSUB(py[e], cy[e]), wx[g][e], wy[g][e]);
+            al[g][e] = 0.0;
+            if (rotate) {
+                int b;
+                al[g][e] = sdb_rot_increment(cw[e], cz[e], pw[e], pz[e], a.atan_tab, b);
+                bad += (b != 0) & (jg + e < n);
+            }
+        }
+    }
+    return bad;
+}
+
 // One warp tile (256 molecules) of one segment.  TAIL: the tile is the partial last one (bounds checks).
-template <bool SUMS, bool OV, bool TRACK, bool TAIL>
+template <bool SUMS, bool OV, bool TRACK, bool PRE, bool TAIL>
 __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared& sh, const float4* quiet_tab,
                                               const int part)
 {
@@ -251,87 +363,34 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
         if (s < seg.count) issue(s, s);
 
     // ---- phase 1: per-segment increments of this lane's 8 molecules, kept in registers ----------
-    //   w = box.wrap(prev - cur)  (f32, freud operation order)     _util.py:149
-    //   alpha = to_euler(q / q_prev)[0]  (f64)                     _util.py:150-153
     int j0[SDB_GROUPS];
     float wx[SDB_GROUPS][4], wy[SDB_GROUPS][4];
     double al[SDB_GROUPS][4];
-    int bad = 0;
-    const bool rotate = (seg.flags & SDB_SEG_NO_ROTATION) == 0 && !zero_step;
+    int bad_warp;
+    if (PRE && seg.reserved != 0u && !zero_step) {
+        // the increments of this previous sample were computed once for the whole frame
+        const long set_off = (long)(seg.reserved - 1u) * stride;
 #pragma unroll
-    for (int g = 0; g < SDB_GROUPS; ++g) {
-        const int jg = part * SDB_WARP_MOLS + g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
-        j0[g] = jg;
-        float cx[4], cy[4], cw[4], cz[4];
-        if (zero_step || jg >= n) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                cx[e] = 0.f; cy[e] = 0.f; cw[e] = 1.f; cz[e] = 0.f;
+        for (int g = 0; g < SDB_GROUPS; ++g) {
+            const int jg = part * SDB_WARP_MOLS + g * (32 * SDB_LANE_MOLS) + lane * SDB_LANE_MOLS;
+            j0[g] = jg;
+            float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vy = vx;
+            double2 a0 = make_double2(0.0, 0.0), a1 = a0;
+            if (jg < n) {
+                vx = sdb_ldg4(a.inc_wx + set_off + jg);
+                vy = sdb_ldg4(a.inc_wy + set_off + jg);
+                a0 = __ldg(reinterpret_cast<const double2*>(a.inc_al + set_off + jg));
+                a1 = __ldg(reinterpret_cast<const double2*>(a.inc_al + set_off + jg + 2));
             }
-        } else if (!TAIL || jg + SDB_LANE_MOLS <= n) {
-            const float4 p0 = sdb_ldg4(a.pos + 3L * jg);
-            const float4 p1 = sdb_ldg4(a.pos + 3L * jg + 4);
-            const float4 p2 = sdb_ldg4(a.pos + 3L * jg + 8);
-            cx[0] = p0.x; cy[0] = p0.y;
-            cx[1] = p0.w; cy[1] = p1.x;
-            cx[2] = p1.z; cy[2] = p1.w;
-            cx[3] = p2.y; cy[3] = p2.z;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
-                if (a.quat) q = sdb_ldg4(a.quat + 4L * (jg + e));
-                cw[e] = q.x; cz[e] = q.w;
-                bad += (q.y != 0.f) | (q.z != 0.f);
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = jg + e;
-                const bool ok = j < n;
-                cx[e] = ok ? __ldg(a.pos + 3L * j) : 0.f;
-                cy[e] = ok ? __ldg(a.pos + 3L * j + 1) : 0.f;
-                float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
-                if (ok && a.quat) q = sdb_ldg4(a.quat + 4L * j);
-                cw[e] = q.x; cz[e] = q.w;
-                bad += (q.y != 0.f) | (q.z != 0.f);
-            }
+            wx[g][0] = vx.x; wx[g][1] = vx.y; wx[g][2] = vx.z; wx[g][3] = vx.w;
+            wy[g][0] = vy.x; wy[g][1] = vy.y; wy[g][2] = vy.z; wy[g][3] = vy.w;
+            al[g][0] = a0.x; al[g][1] = a0.y; al[g][2] = a1.x; al[g][3] = a1.y;
         }
-        if (a.cur_compact && blockIdx.y == 0 && !zero_step && jg < n) {
-            // planes are padded to a multiple of 4: whole-vector stores are safe
-            float* c = a.cur_compact + jg;
-            *reinterpret_cast<float4*>(c) = make_float4(cx[0], cx[1], cx[2], cx[3]);
-            *reinterpret_cast<float4*>(c + stride) = make_float4(cy[0], cy[1], cy[2], cy[3]);
-            *reinterpret_cast<float4*>(c + 2 * stride) = make_float4(cw[0], cw[1], cw[2], cw[3]);
-            *reinterpret_cast<float4*>(c + 3 * stride) = make_float4(cz[0], cz[1], cz[2], cz[3]);
-        }
-        float px[4], py[4], pw[4], pz[4];
-        if (prev != nullptr && jg < n && !zero_step) {
-            const float4 vx = sdb_ldg4(prev + jg);
-            const float4 vy = sdb_ldg4(prev + stride + jg);
-            const float4 vw = sdb_ldg4(prev + 2 * stride + jg);
-            const float4 vz = sdb_ldg4(prev + 3 * stride + jg);
-            px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
-            py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
-            pw[0] = vw.x; pw[1] = vw.y; pw[2] = vw.z; pw[3] = vw.w;
-            pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
-        } else {  // origin created at this frame: previous sample == current sample
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                px[e] = cx[e]; py[e] = cy[e]; pw[e] = cw[e]; pz[e] = cz[e];
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            sdb_wrap2d(a.p.lx, a.p.ly, a.p.xy, SDB_FSUB(px[e], cx[e]), SDB_FSUB(py[e], cy[e]), wx[g][e], wy[g][e]);
-            al[g][e] = 0.0;
-            if (rotate) {
-                int b;
-                al[g][e] = sdb_rot_increment(cw[e], cz[e], pw[e], pz[e], a.atan_tab, b);
-                bad += (b != 0) & (jg + e < n);
-            }
-        }
+        bad_warp = (int)__ldg(a.inc_bad + (long)(seg.reserved - 1u) * a.n_parts + part);
+    } else {
+        const int bad = sdb_tile_increments<TAIL>(a, prev, seg.flags, zero_step, blockIdx.y == 0, part, lane, j0, wx, wy, al);
+        bad_warp = __reduce_add_sync(0xffffffffu, bad);
     }
-    const int bad_warp = __reduce_add_sync(0xffffffffu, bad);
 
     // ---- tracker pre-digestion (uniform across the grid) ------------------------------------------
     // A group of 4 molecules cannot change its flag bytes when (a) all four are below every "greater
@@ -614,7 +673,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
 }
 
 // grid = (warp tiles / 4, segments).  The partial last tile (if any) takes the bounds-checked path.
-template <bool SUMS, bool OV, bool TRACK>
+template <bool SUMS, bool OV, bool TRACK, bool PRE>
 __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 4) dyn_step_kernel(const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -628,9 +687,50 @@ __global__ void __launch_bounds__(SDB_BLOCK_THREADS, 4) dyn_step_kernel(const __
     const int part = blockIdx.x * SDB_BLOCK_WARPS + (threadIdx.x >> 5);  // warp tile index
     if (part >= a.n_parts) return;
     if (part < a.full_parts)
-        dyn_step_tile<SUMS, OV, TRACK, false>(a, sh, quiet_tab, part);
+        dyn_step_tile<SUMS, OV, TRACK, PRE, false>(a, sh, quiet_tab, part);
     else
-        dyn_step_tile<SUMS, OV, TRACK, true>(a, sh, quiet_tab, part);
+        dyn_step_tile<SUMS, OV, TRACK, PRE, true>(a, sh, quiet_tab, part);
+}
+
+// Increments of every molecule for up to SDB_MAX_INC_SETS previous samples, once per frame: with several
+// segments per previous sample (origins are split into segments to fill the GPU) phase 1 -- two f32
+// divisions, an f64 atan2 -- would otherwise be repeated by every segment.  grid = (tiles / 4, sets).
+struct IncArgs {
+    StepArgs a;
+    const float* prev[SDB_MAX_INC_SETS];
+    uint32_t flags[SDB_MAX_INC_SETS];
+    float* wx;
+    float* wy;
+    double* al;
+    uint32_t* bad;
+};
+
+__global__ void __launch_bounds__(SDB_BLOCK_THREADS) dyn_increments_kernel(const __grid_constant__ IncArgs ia)
+{
+    const StepArgs& a = ia.a;
+    const int lane = threadIdx.x & 31;
+    const int part = blockIdx.x * SDB_BLOCK_WARPS + (threadIdx.x >> 5);
+    if (part >= a.n_parts) return;
+    const int set = blockIdx.y;
+    int j0[SDB_GROUPS];
+    float wx[SDB_GROUPS][4], wy[SDB_GROUPS][4];
+    double al[SDB_GROUPS][4];
+    int bad;
+    if (part < a.full_parts)
+        bad = sdb_tile_increments<false>(a, ia.prev[set], ia.flags[set], false, set == 0, part, lane, j0, wx, wy, al);
+    else
+        bad = sdb_tile_increments<true>(a, ia.prev[set], ia.flags[set], false, set == 0, part, lane, j0, wx, wy, al);
+    const long set_off = (long)set * a.p.stride;
+#pragma unroll
+    for (int g = 0; g < SDB_GROUPS; ++g) {
+        if (j0[g] >= a.p.n) continue;
+        *reinterpret_cast<float4*>(ia.wx + set_off + j0[g]) = make_float4(wx[g][0], wx[g][1], wx[g][2], wx[g][3]);
+        *reinterpret_cast<float4*>(ia.wy + set_off + j0[g]) = make_float4(wy[g][0], wy[g][1], wy[g][2], wy[g][3]);
+        *reinterpret_cast<double2*>(ia.al + set_off + j0[g]) = make_double2(al[g][0], al[g][1]);
+        *reinterpret_cast<double2*>(ia.al + set_off + j0[g] + 2) = make_double2(al[g][2], al[g][3]);
+    }
+    const int bad_warp = __reduce_add_sync(0xffffffffu, bad);
+    if (lane == 0) ia.bad[(long)set * a.n_parts + part] = (uint32_t)bad_warp;
 }
 
 // Sum the per-warp-tile partials of one origin: block = 1024 threads = 16 sums x 64 strided readers,
@@ -711,10 +811,59 @@ extern "C" int sdb_dyn_norms(const float* d_delta, int32_t n, int32_t stride, fl
 
 extern "C" int32_t sdb_dyn_num_parts(int32_t n) { return (n + SDB_WARP_MOLS - 1) / SDB_WARP_MOLS; }
 
+extern "C" size_t sdb_dyn_increments_bytes(int32_t n, int32_t stride, int32_t n_sets)
+{
+    if (n <= 0 || stride < n || n_sets <= 0 || n_sets > SDB_MAX_INC_SETS) return 0;
+    return sdb_inc_layout(n, stride, n_sets).bytes;
+}
+
+static void sdb_inc_pointers(void* d_ws, int n, int stride, int n_sets, float** wx, float** wy, double** al, uint32_t** bad)
+{
+    const IncLayout l = sdb_inc_layout(n, stride, n_sets);
+    char* b = static_cast<char*>(d_ws);
+    *wx = reinterpret_cast<float*>(b);
+    *wy = reinterpret_cast<float*>(b + l.off_wy);
+    *al = reinterpret_cast<double*>(b + l.off_al);
+    *bad = reinterpret_cast<uint32_t*>(b + l.off_bad);
+}
+
+extern "C" int sdb_dyn_increments(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
+                                  float* d_cur_compact, const void* const* h_prev, const uint32_t* h_seg_flags,
+                                  int32_t n_sets, void* d_ws, void* stream)
+{
+    if (!h_params || !d_pos || !h_prev || !h_seg_flags || !d_ws || n_sets <= 0 || n_sets > SDB_MAX_INC_SETS) {
+        sdb_set_error("sdb_dyn_increments: bad argument");
+        return SDB_EINVAL;
+    }
+    const SdbDynParams& p = *h_params;
+    if (p.n <= 0 || p.stride < p.n || (p.stride & 3)) {
+        sdb_set_error("sdb_dyn_increments: bad sizes n=%d stride=%d", p.n, p.stride);
+        return SDB_EINVAL;
+    }
+    IncArgs ia{};
+    ia.a.p = p;
+    ia.a.pos = d_pos;
+    ia.a.quat = d_quat;
+    ia.a.cur_compact = d_cur_compact;
+    ia.a.atan_tab = sdb_device_atan_table();
+    if (!ia.a.atan_tab) return SDB_ECUDA;
+    ia.a.n_parts = sdb_dyn_num_parts(p.n);
+    ia.a.full_parts = p.n / SDB_WARP_MOLS;
+    for (int i = 0; i < n_sets; ++i) {
+        ia.prev[i] = static_cast<const float*>(h_prev[i]);
+        ia.flags[i] = h_seg_flags[i];
+    }
+    sdb_inc_pointers(d_ws, p.n, p.stride, n_sets, &ia.wx, &ia.wy, &ia.al, &ia.bad);
+    const dim3 grid((ia.a.n_parts + SDB_BLOCK_WARPS - 1) / SDB_BLOCK_WARPS, n_sets);
+    dyn_increments_kernel<<<grid, SDB_BLOCK_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(ia);
+    SDB_CHECK_LAUNCH("dyn_increments_kernel");
+    return SDB_OK;
+}
+
 extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat, float* d_cur_compact,
                             const SdbOrigin* d_origins, int32_t n_origins, const SdbSegment* d_segments,
                             int32_t n_segments, double* d_partials, double* d_sums, void* d_ov_ws,
-                            int32_t ov_ws_origins, void* stream)
+                            int32_t ov_ws_origins, void* d_inc_ws, int32_t inc_sets, void* stream)
 {
     if (!h_params || !d_origins || !d_segments || (d_ov_ws && n_origins > ov_ws_origins)) {
         sdb_set_error("sdb_dyn_step: null argument");
@@ -744,13 +893,26 @@ extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, co
     a.ov_on = d_ov_ws != nullptr && p.do_sums;
     if (a.ov_on) sdb_ov_layout(d_ov_ws, ov_ws_origins, p.n, &a.ov);
     else a.ov = SdbOvWorkspace{};
+    a.inc_wx = a.inc_wy = nullptr;
+    a.inc_al = nullptr;
+    a.inc_bad = nullptr;
+    if (d_inc_ws && inc_sets > 0 && inc_sets <= SDB_MAX_INC_SETS) {
+        float *wx, *wy;
+        double* al;
+        uint32_t* bad;
+        sdb_inc_pointers(d_inc_ws, p.n, p.stride, inc_sets, &wx, &wy, &al, &bad);
+        a.inc_wx = wx;
+        a.inc_wy = wy;
+        a.inc_al = al;
+        a.inc_bad = bad;
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     a.full_parts = p.n / SDB_WARP_MOLS;
-    const int variant = (p.do_sums ? 4 : 0) | (a.ov_on ? 2 : 0) | (p.n_trackers > 0 ? 1 : 0);
+    const int variant = (a.inc_wx ? 8 : 0) | (p.do_sums ? 4 : 0) | (a.ov_on ? 2 : 0) | (p.n_trackers > 0 ? 1 : 0);
     const dim3 grid((a.n_parts + SDB_BLOCK_WARPS - 1) / SDB_BLOCK_WARPS, n_segments);
     constexpr size_t smem = sizeof(StepWarpShared) * SDB_BLOCK_WARPS + 256 * sizeof(float4);
     auto launch = [&](void (*kernel)(const StepArgs)) -> int {
-        static std::atomic<bool> configured[8][64];  // [variant][device]: opt in to > 48 KB of shared memory once
+        static std::atomic<bool> configured[16][64];  // [variant][device]: opt in to > 48 KB of shared memory once
         int dev = 0;
         cudaGetDevice(&dev);
         if (dev >= 64 || !configured[variant][dev].load(std::memory_order_acquire)) {
@@ -764,12 +926,18 @@ extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, co
     };
     int lrc;
     switch (variant) {
-        case 0: lrc = launch(dyn_step_kernel<false, false, false>); break;
-        case 1: lrc = launch(dyn_step_kernel<false, false, true>); break;
-        case 4: lrc = launch(dyn_step_kernel<true, false, false>); break;
-        case 5: lrc = launch(dyn_step_kernel<true, false, true>); break;
-        case 6: lrc = launch(dyn_step_kernel<true, true, false>); break;
-        default: lrc = launch(dyn_step_kernel<true, true, true>); break;
+        case 0: lrc = launch(dyn_step_kernel<false, false, false, false>); break;
+        case 1: lrc = launch(dyn_step_kernel<false, false, true, false>); break;
+        case 4: lrc = launch(dyn_step_kernel<true, false, false, false>); break;
+        case 5: lrc = launch(dyn_step_kernel<true, false, true, false>); break;
+        case 6: lrc = launch(dyn_step_kernel<true, true, false, false>); break;
+        case 7: lrc = launch(dyn_step_kernel<true, true, true, false>); break;
+        case 8: lrc = launch(dyn_step_kernel<false, false, false, true>); break;
+        case 9: lrc = launch(dyn_step_kernel<false, false, true, true>); break;
+        case 12: lrc = launch(dyn_step_kernel<true, false, false, true>); break;
+        case 13: lrc = launch(dyn_step_kernel<true, false, true, true>); break;
+        case 14: lrc = launch(dyn_step_kernel<true, true, false, true>); break;
+        default: lrc = launch(dyn_step_kernel<true, true, true, true>); break;
     }
     if (lrc) return lrc;
     SDB_CHECK_LAUNCH("dyn_step_kernel");

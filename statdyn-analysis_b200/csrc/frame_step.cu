@@ -72,7 +72,8 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
                               int32_t segments_offset, int32_t n_origins, int32_t n_segments,
                               int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
                               void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy,
-                              int32_t n_sites, double struct_dist, int32_t struct_mode, void* stream)
+                              int32_t n_sites, double struct_dist, int32_t struct_mode, const void* const* h_inc_prev,
+                              const uint32_t* h_inc_flags, int32_t inc_sets, void* d_inc_ws, void* stream)
 {
     if (!h_params || !h_desc || !d_desc || desc_bytes <= 0 || segments_offset <= 0 || segments_offset >= desc_bytes) {
         sdb_set_error("sdb_frame_step: bad descriptor arguments");
@@ -99,8 +100,14 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
         if (rc) return rc;
     }
     if (prof) cudaEventRecord(prof_copy.ev[1], s);
-    rc = sdb_dyn_step(h_params, d_pos, d_quat, d_cur_compact, d_origins, n_origins, d_segments, n_segments, d_partials,
-                      d_sums, use_ov ? d_ov_ws : nullptr, ov_ws_origins, stream);
+    const bool use_inc = inc_sets > 0 && d_inc_ws != nullptr && h_inc_prev != nullptr && h_inc_flags != nullptr && d_pos;
+    if (use_inc) {  // phase 1 once per frame and previous sample (it also writes the new previous planes)
+        rc = sdb_dyn_increments(h_params, d_pos, d_quat, d_cur_compact, h_inc_prev, h_inc_flags, inc_sets, d_inc_ws, stream);
+        if (rc) return rc;
+    }
+    rc = sdb_dyn_step(h_params, d_pos, d_quat, use_inc ? nullptr : d_cur_compact, d_origins, n_origins, d_segments,
+                      n_segments, d_partials, d_sums, use_ov ? d_ov_ws : nullptr, ov_ws_origins,
+                      use_inc ? d_inc_ws : nullptr, use_inc ? inc_sets : 0, stream);
     if (rc) return rc;
     if (prof) cudaEventRecord(prof_copy.ev[2], s);
     if (sums && h_sites_xy && n_sites > 0) {

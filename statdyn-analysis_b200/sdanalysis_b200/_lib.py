@@ -21,11 +21,14 @@ S_STRUCT, S_OVERLAP, S_BADQUAT = 10, 11, 12
 
 ORIGIN_NEW, ORIGIN_LITERAL, ORIGIN_HISTORY = 1, 2, 4
 HISTORY_WORDS = 16
+SDB_MAX_INC_SETS = 4
 SEG_NO_ROTATION, SEG_ZERO_STEP = 1, 2
 
 # Every symbol include/sdb200.h declares; tests check that the library exports all of them.
 EXPORTS = (
     "sdb_dyn_step",
+    "sdb_dyn_increments",
+    "sdb_dyn_increments_bytes",
     "sdb_dyn_num_parts",
     "sdb_dyn_norms",
     "sdb_pack_frame",
@@ -128,7 +131,9 @@ def load():
     lib = ctypes.CDLL(str(LIB_PATH))
     P = c_void_p
     sig = {
-        "sdb_dyn_step": (c_int32, [POINTER(SdbDynParams), P, P, P, P, c_int32, P, c_int32, P, P, P, c_int32, P]),
+        "sdb_dyn_step": (c_int32, [POINTER(SdbDynParams), P, P, P, P, c_int32, P, c_int32, P, P, P, c_int32, P, c_int32, P]),
+        "sdb_dyn_increments_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+        "sdb_dyn_increments": (c_int32, [POINTER(SdbDynParams), P, P, P, POINTER(c_void_p), POINTER(c_uint32), c_int32, P, P]),
         "sdb_dyn_num_parts": (c_int32, [c_int32]),
         "sdb_dyn_norms": (c_int32, [P, c_int32, c_int32, P, P, P]),
         "sdb_pack_frame": (c_int32, [P, P, c_int32, c_int32, P, P, P]),
@@ -143,7 +148,8 @@ def load():
         "sdb_frame_step": (
             c_int32,
             [POINTER(SdbDynParams), P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int32, P, P, P, P, c_int32,
-             c_int32, POINTER(c_float), c_int32, ctypes.c_double, c_int32, P],
+             c_int32, POINTER(c_float), c_int32, ctypes.c_double, c_int32, POINTER(c_void_p), POINTER(c_uint32),
+             c_int32, P, P],
         ),
         "sdb_isf_origins": (c_int32, [P, c_int32, c_int32, c_int32, c_double, c_int32, P, P]),
         "sdb_isf": (c_int32, [P, P, c_int32, c_int32, c_double, c_int32, P, P]),

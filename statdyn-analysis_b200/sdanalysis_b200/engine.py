@@ -383,6 +383,13 @@ class DynamicsEngine:
         import os
 
         self._origin_flags = ORIGIN_HISTORY if os.environ.get("SDB_OV_PREDICT", "1") != "0" else 0
+        # SDB_INCREMENTS=0: every segment recomputes the frame increments itself (no per-frame pass)
+        self._inc_ok = os.environ.get("SDB_INCREMENTS", "1") != "0"
+        # the per-frame pass costs about one phase 1 plus 76 B per molecule of traffic: it pays when
+        # several segments share a previous sample and each has few origins to amortise its own phase 1
+        # over (measured: 25 origins in 3 segments -11 % on dyn_step, 200 origins in 3 segments +3 %)
+        self._inc_max_per_segment = int(os.environ.get("SDB_INCREMENTS_MAX_PER_SEGMENT", "12"))
+        self._inc_ws = None
         self._sites_c = None if self.mol_sites is None else _lib.float_array(self.mol_sites.reshape(-1))
         self.frames_seen = 0
         self.updates = 0  # molecule x origin updates performed
@@ -418,6 +425,21 @@ class DynamicsEngine:
         self._sums_host_ptr = [t.data_ptr() for t in self._sums_ring.bufs]
         self._sums_dev_ptr = [t.data_ptr() for t in self._sums_dev]
         self._partials_ptr = self._partials.data_ptr()
+
+    def _inc_args(self, inc_sets):
+        """ctypes arguments (h_prev, h_flags, n_sets, d_ws) of the per-frame increments pass."""
+        import ctypes
+
+        if not inc_sets:
+            return None, None, 0, 0
+        if self._inc_ws is None:
+            nbytes = int(self.lib.sdb_dyn_increments_bytes(self.n, self.stride, _lib.SDB_MAX_INC_SETS))
+            self._inc_ws = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
+        k = len(inc_sets)
+        prev = (ctypes.c_void_p * _lib.SDB_MAX_INC_SETS)(*[p for p, _ in inc_sets])
+        flags = (ctypes.c_uint32 * _lib.SDB_MAX_INC_SETS)(*[f for _, f in inc_sets])
+        # the workspace is laid out for exactly k sets by both calls
+        return prev, flags, k, self._inc_ws.data_ptr()
 
     def _stage_frame(self, position, orientation):
         """Return device tensors (pos (N,3) f32, quat (N,4) f32 or None).
@@ -610,6 +632,13 @@ class DynamicsEngine:
                 seg_count_max = plan["seg_count_max"]
                 n_segments = len(sdesc)
                 fast = True
+                # every segment shares the previous frame: its increments are computed once per frame
+                inc_sets = []
+                if n_segments > 1 and self._inc_ok and n_active <= self._inc_max_per_segment * n_segments:
+                    inc_sets = [(plan["prev"].ptr, int(sdesc["flags"][0]))]
+                    sdesc["reserved"] = 1
+                else:
+                    sdesc["reserved"] = 0
             else:
                 fast = False
                 self._flush_plan()
@@ -663,7 +692,19 @@ class DynamicsEngine:
                     for org, t in zip(ordered, td.tolist())
                 ]
                 timediffs = td.tolist()
-                sdesc = np.array([(p, f, c, fl, 0) for (p, fl, f, c) in seg_rows], dtype=SEGMENT_DTYPE)
+                # previous samples shared by several segments: their increments are computed once per frame
+                inc_sets, set_of = [], {}
+                if self._inc_ok and not zero_step:
+                    counts = {}
+                    for (p, fl, f, c) in seg_rows:
+                        if p:
+                            counts[(p, fl)] = counts.get((p, fl), 0) + 1
+                    for key, cnt in counts.items():
+                        members = sum(c for (p, fl, f, c) in seg_rows if (p, fl) == key)
+                        if cnt > 1 and members <= self._inc_max_per_segment * cnt and len(inc_sets) < _lib.SDB_MAX_INC_SETS:
+                            set_of[key] = len(inc_sets) + 1
+                            inc_sets.append(key)
+                sdesc = np.array([(p, f, c, fl, set_of.get((p, fl), 0)) for (p, fl, f, c) in seg_rows], dtype=SEGMENT_DTYPE)
                 seg_count_max = max(row[3] for row in seg_rows)
                 n_segments = len(seg_rows)
 
@@ -711,6 +752,7 @@ class DynamicsEngine:
                     len(self.mol_sites) if (do_sums and self.compute_struct) else 0,
                     float(self.distance) if self.distance is not None else 0.0,
                     self.struct_mode,
+                    *self._inc_args(inc_sets),
                     _lib.stream_ptr(self.device),
                 )
             )
