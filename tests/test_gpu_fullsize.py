@@ -234,3 +234,37 @@ def test_four_million_molecules_config5_shape():
     last = s["tau_L"] != unset
     assert last.sum() > 0 and np.all(s["tau_F"][last] <= s["tau_L"][last])
     assert table["time"].tolist() == [360, 200, 200]
+
+
+def test_per_frame_increments_pass_is_bit_identical(monkeypatch):
+    """sdb_dyn_increments (phase 1 once per frame and previous sample, used when several small segments
+    share it) leaves every accumulator, flag and sum bit-identical to the in-kernel phase 1; also with
+    a partial last tile and origins created along the way."""
+    import torch
+
+    from sdanalysis_b200.engine import DynamicsEngine
+    from sdanalysis_b200.molecules import Trimer
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    dev = torch.device("cuda", 0)
+    n = 70_001  # partial last tile, n not a multiple of 4
+    walk = SyntheticTrimer(n, seed=8, sigma_r=0.05, sigma_theta=0.1, device=dev)
+    monkeypatch.setenv("SDB_INCREMENTS", "1")
+    monkeypatch.setenv("SDB_INCREMENTS_MAX_PER_SEGMENT", "64")
+    with_pass = DynamicsEngine(n, walk.box, WAVE, mol_sites=Trimer().positions, device=dev)
+    monkeypatch.setenv("SDB_INCREMENTS", "0")
+    without = DynamicsEngine(n, walk.box, WAVE, mol_sites=Trimer().positions, device=dev)
+    used = 0
+    for t in range(8):
+        pos, quat = walk.frame()
+        active = list(range(20 if t < 4 else 24))  # 3 segments of 8; four more origins join at t = 4
+        a = with_pass.step(walk.timestep, pos, quat, active)
+        b = without.step(walk.timestep, pos, quat, active)
+        used += with_pass._inc_ws is not None
+        assert np.array_equal(a.sums(), b.sums()), t
+        walk.advance(3)
+    assert used > 0  # the pass really ran
+    for key in (0, 7, 19, 23):
+        assert torch.equal(with_pass.origins[key].delta, without.origins[key].delta)
+        assert torch.equal(with_pass.origins[key].flags, without.origins[key].flags)
+        assert torch.equal(with_pass.origins[key].status[:, :n], without.origins[key].status[:, :n])
