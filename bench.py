@@ -326,15 +326,31 @@ def run_gpu(args):
         sampler = ClockSampler(local_rank) if rank == 0 else None
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        cuprof = os.environ.get("SDB_BENCH_CUPROFILE") == "1" and not host_frames
+        if cuprof:  # `ncu --profile-from-start off`: the launch list then holds exactly the timed region
+            torch.cuda.cudart().cudaProfilerStart()
         t_start.record()
         host_t0 = time.perf_counter()
+        pyprof = None
+        if os.environ.get("SDB_BENCH_PYPROFILE") == "1" and rank == 0:
+            import cProfile
+
+            pyprof = cProfile.Profile()
+            pyprof.enable()
         for i in range(steps):
             one_step(warmup + i, timestep)
             timestep += 1
+        if pyprof is not None:
+            import pstats
+
+            pyprof.disable()
+            pstats.Stats(pyprof, stream=sys.stderr).sort_stats("tottime").print_stats(35)
         host_ms = 1e3 * (time.perf_counter() - host_t0) / steps
         last_rows = drain()
         t_end.record()
         torch.cuda.synchronize()
+        if cuprof:
+            torch.cuda.cudart().cudaProfilerStop()
         if world > 1:
             dist.barrier()
         clocks = sampler.stop() if sampler else None

@@ -860,10 +860,30 @@ extern "C" int sdb_dyn_increments(const SdbDynParams* h_params, const float* d_p
     return SDB_OK;
 }
 
+// Sum of the per-tile partial rows of every origin (second half of sdb_dyn_step; sdb_frame_step runs it
+// on its side stream next to the struct kernel).
+int sdb_dyn_finalize(const double* d_partials, int32_t n, double* d_sums, int32_t n_origins, int32_t with_ov, void* stream)
+{
+    if (n_origins <= 0) return SDB_OK;
+    dyn_finalize_kernel<<<n_origins, 1024, 0, static_cast<cudaStream_t>(stream)>>>(d_partials, sdb_dyn_num_parts(n), d_sums,
+                                                                                   with_ov);
+    SDB_CHECK_LAUNCH("dyn_finalize_kernel");
+    return SDB_OK;
+}
+
 extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat, float* d_cur_compact,
                             const SdbOrigin* d_origins, int32_t n_origins, const SdbSegment* d_segments,
                             int32_t n_segments, double* d_partials, double* d_sums, void* d_ov_ws,
                             int32_t ov_ws_origins, void* d_inc_ws, int32_t inc_sets, void* stream)
+{
+    return sdb_dyn_step_launch(h_params, d_pos, d_quat, d_cur_compact, d_origins, n_origins, d_segments, n_segments,
+                               d_partials, d_sums, d_ov_ws, ov_ws_origins, d_inc_ws, inc_sets, 1, stream);
+}
+
+int sdb_dyn_step_launch(const SdbDynParams* h_params, const float* d_pos, const float* d_quat, float* d_cur_compact,
+                        const SdbOrigin* d_origins, int32_t n_origins, const SdbSegment* d_segments, int32_t n_segments,
+                        double* d_partials, double* d_sums, void* d_ov_ws, int32_t ov_ws_origins, void* d_inc_ws,
+                        int32_t inc_sets, int32_t finalize, void* stream)
 {
     if (!h_params || !d_origins || !d_segments || (d_ov_ws && n_origins > ov_ws_origins)) {
         sdb_set_error("sdb_dyn_step: null argument");
@@ -941,10 +961,7 @@ extern "C" int sdb_dyn_step(const SdbDynParams* h_params, const float* d_pos, co
     }
     if (lrc) return lrc;
     SDB_CHECK_LAUNCH("dyn_step_kernel");
-    if (p.do_sums) {
-        dyn_finalize_kernel<<<n_origins, 1024, 0, s>>>(d_partials, a.n_parts, d_sums, a.ov_on);
-        SDB_CHECK_LAUNCH("dyn_finalize_kernel");
-    }
+    if (p.do_sums && finalize) return sdb_dyn_finalize(d_partials, p.n, d_sums, n_origins, a.ov_on, stream);
     return SDB_OK;
 }
 

@@ -1,6 +1,7 @@
 // frame_step.cu -- one call per frame: the whole device-side sequence of the hot loop body
 // (reference read/_read.py:134-153 for every active origin) enqueued from native code, so the host
 // spends one FFI call per frame instead of one per kernel group plus tensor copies.
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -17,6 +18,40 @@ std::mutex g_prof_mutex;
 bool g_prof_on = false;
 std::vector<StepEvents> g_prof_steps;
 std::vector<StepEvents> g_prof_free;
+
+// ---- side stream (one per device): the overlap bookkeeping and the row sums are chains of small,
+// latency-bound kernels that depend only on the descriptors / on dyn_step_kernel's partial rows; they run
+// next to the increments pass and next to the struct kernel instead of in front of / behind them.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, prepared = nullptr, stepped = nullptr, joined = nullptr;
+    int state = 0;  // 0 untried, 1 ready, -1 unavailable
+};
+SideStream g_side[64];
+std::mutex g_side_mutex;
+
+SideStream* side_stream()
+{
+    static const bool enabled = [] {
+        const char* e = getenv("SDB_SIDE_STREAM");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    SideStream& ss = g_side[dev];
+    if (ss.state == 0) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+        bool ok = cudaStreamCreateWithPriority(&ss.stream, cudaStreamNonBlocking, hi) == cudaSuccess;
+        for (cudaEvent_t* e : {&ss.fork, &ss.prepared, &ss.stepped, &ss.joined})
+            ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+        ss.state = ok ? 1 : -1;
+        if (!ok) cudaGetLastError();
+    }
+    return ss.state == 1 ? &ss : nullptr;
+}
 
 StepEvents* prof_begin(int n_origins)
 {
@@ -94,10 +129,19 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
         prof_copy = *prof;  // the vector may grow under another thread; the handles stay valid
         cudaEventRecord(prof_copy.ev[0], s);
     }
+    SideStream* side = sums ? side_stream() : nullptr;
     if (use_ov) {
+        // overlap prepare needs only the descriptors (and, for sampled brackets, the state before the update)
+        void* ps = stream;
+        if (side) {
+            cudaEventRecord(side->fork, s);
+            cudaStreamWaitEvent(side->stream, side->fork, 0);
+            ps = side->stream;
+        }
         rc = sdb_overlap_prepare(h_params, d_pos, d_quat, d_origins, n_origins, d_segments, n_segments,
-                                 max_segment_count, overlap_k, d_ov_ws, ov_ws_origins, stream);
+                                 max_segment_count, overlap_k, d_ov_ws, ov_ws_origins, ps);
         if (rc) return rc;
+        if (side) cudaEventRecord(side->prepared, side->stream);
     }
     if (prof) cudaEventRecord(prof_copy.ev[1], s);
     const bool use_inc = inc_sets > 0 && d_inc_ws != nullptr && h_inc_prev != nullptr && h_inc_flags != nullptr && d_pos;
@@ -105,20 +149,41 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
         rc = sdb_dyn_increments(h_params, d_pos, d_quat, d_cur_compact, h_inc_prev, h_inc_flags, inc_sets, d_inc_ws, stream);
         if (rc) return rc;
     }
-    rc = sdb_dyn_step(h_params, d_pos, d_quat, use_inc ? nullptr : d_cur_compact, d_origins, n_origins, d_segments,
-                      n_segments, d_partials, d_sums, use_ov ? d_ov_ws : nullptr, ov_ws_origins,
-                      use_inc ? d_inc_ws : nullptr, use_inc ? inc_sets : 0, stream);
+    if (use_ov && side) cudaStreamWaitEvent(s, side->prepared, 0);
+    rc = sdb_dyn_step_launch(h_params, d_pos, d_quat, use_inc ? nullptr : d_cur_compact, d_origins, n_origins, d_segments,
+                             n_segments, d_partials, d_sums, use_ov ? d_ov_ws : nullptr, ov_ws_origins,
+                             use_inc ? d_inc_ws : nullptr, use_inc ? inc_sets : 0, side ? 0 : 1, stream);
     if (rc) return rc;
     if (prof) cudaEventRecord(prof_copy.ev[2], s);
+    // row sums + overlap resolve (side stream)  ||  struct (this stream)
+    void* rs = stream;
+    if (side) {
+        cudaEventRecord(side->stepped, s);
+        cudaStreamWaitEvent(side->stream, side->stepped, 0);
+        rs = side->stream;
+        rc = sdb_dyn_finalize(d_partials, h_params->n, d_sums, n_origins, use_ov ? 1 : 0, rs);
+        if (rc) return rc;
+    }
+    auto resolve = [&]() -> int {
+        if (!use_ov) return SDB_OK;
+        return sdb_overlap_resolve(d_origins, n_origins, h_params->n, h_params->stride, overlap_k, d_ov_ws, ov_ws_origins,
+                                   d_sums, rs);
+    };
+    if (side) {
+        rc = resolve();
+        if (rc) return rc;
+        cudaEventRecord(side->joined, side->stream);
+    }
     if (sums && h_sites_xy && n_sites > 0) {
         rc = sdb_struct(d_origins, n_origins, h_params->n, h_params->stride, h_sites_xy, n_sites, struct_dist, struct_mode,
                         d_sums, stream);
         if (rc) return rc;
     }
     if (prof) cudaEventRecord(prof_copy.ev[3], s);
-    if (use_ov) {
-        rc = sdb_overlap_resolve(d_origins, n_origins, h_params->n, h_params->stride, overlap_k, d_ov_ws, ov_ws_origins,
-                                 d_sums, stream);
+    if (side) {
+        cudaStreamWaitEvent(s, side->joined, 0);
+    } else {
+        rc = resolve();
         if (rc) return rc;
     }
     if (prof) cudaEventRecord(prof_copy.ev[4], s);

@@ -26,6 +26,13 @@ void sdb_count_launch(int n = 1);
 const double (*sdb_device_atan_table())[2];  // device pointer to the 1024-entry cos/sin table
 const double (*sdb_host_atan_table())[2];
 
+// sdb_dyn_step in two halves (the second can run on another stream): csrc/dyn_step.cu
+int sdb_dyn_step_launch(const SdbDynParams* h_params, const float* d_pos, const float* d_quat, float* d_cur_compact,
+                        const SdbOrigin* d_origins, int32_t n_origins, const SdbSegment* d_segments, int32_t n_segments,
+                        double* d_partials, double* d_sums, void* d_ov_ws, int32_t ov_ws_origins, void* d_inc_ws,
+                        int32_t inc_sets, int32_t finalize, void* stream);
+int sdb_dyn_finalize(const double* d_partials, int32_t n, double* d_sums, int32_t n_origins, int32_t with_ov, void* stream);
+
 #define SDB_CHECK_LAUNCH(what)                                       \
     do {                                                             \
         sdb_count_launch();                                          \
