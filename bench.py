@@ -230,7 +230,13 @@ def run_gpu(args):
         # origin creation: origin k starts at frame k (linear schedule, keyframe_interval = 1)
         timestep = 0
         # frames: a random walk generated on rank 0's GPU
-        walk = SyntheticTrimer(n, seed=4, sigma_r=SIGMA_R, sigma_theta=SIGMA_T, device=device) if rank == 0 else None
+        # (several GPUs: every rank runs the same seeded walk on its own device, so that the frames of the
+        # device-resident phase can be held sharded by rows -- rank r keeps rows slice_bounds(r) of each frame)
+        walk = SyntheticTrimer(n, seed=4, sigma_r=SIGMA_R, sigma_theta=SIGMA_T, device=device)
+        sharded_resident = (
+            world > 1 and not host_frames and sharded.exchange == "multicast" and bool(getattr(sharded, "_mc_ptr", 0))
+            and n % (4 * world) == 0 and os.environ.get("SDB_BENCH_RESIDENT", "sharded") == "sharded"
+        )
         for k in range(n_origins):
             active = all_keys[: k + 1]
             if world > 1:
@@ -239,8 +245,7 @@ def run_gpu(args):
             else:
                 pos, quat = walk.frame()
                 engine.step(timestep, pos, quat, active, want_sums=False)
-            if rank == 0:
-                walk.advance(1)
+            walk.advance(1)
             timestep += 1
         torch.cuda.synchronize()
         # the frames of the measured steps
@@ -267,6 +272,12 @@ def run_gpu(args):
             rc = torch.cuda.cudart().cudaHostRegister(shared.data_ptr(), shared.numel() * 4, 0)
             assert int(rc) == 0, f"cudaHostRegister failed: {rc}"
             frames = [(shared[i, : 3 * n].view(n, 3), shared[i, 3 * n :].view(n, 4)) for i in range(n_frames)]
+        elif sharded_resident:
+            lo, hi = sharded.slice_bounds()
+            for _ in range(n_frames):
+                pos, quat = walk.frame()
+                walk.advance(1)
+                frames.append((pos[lo:hi].clone(), quat[lo:hi].clone()))
         elif rank == 0:
             for _ in range(n_frames):
                 pos, quat = walk.frame()
@@ -287,7 +298,7 @@ def run_gpu(args):
             if world > 1:
                 # software pipeline: the exchange of frame i + 1 is enqueued (side stream) before the
                 # kernels of frame i, so it overlaps them
-                post = sharded.post_frame_sliced if shared_host else sharded.post_frame
+                post = sharded.post_frame_sliced if (shared_host or sharded_resident) else sharded.post_frame
                 if i not in posted:
                     posted[i] = post(*frames[i])
                 if i + 1 < n_frames:
@@ -337,18 +348,34 @@ def run_gpu(args):
 
             pyprof = cProfile.Profile()
             pyprof.enable()
+        shard_prof = os.environ.get("SDB_SHARD_PROFILE") == "1"
+        step_events, host_marks = [], []
         for i in range(steps):
             one_step(warmup + i, timestep)
             timestep += 1
+            if shard_prof:  # diagnostics: device time and host time of every step
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                step_events.append(ev)
+                host_marks.append(time.perf_counter())
         if pyprof is not None:
             import pstats
 
             pyprof.disable()
             pstats.Stats(pyprof, stream=sys.stderr).sort_stats("tottime").print_stats(35)
         host_ms = 1e3 * (time.perf_counter() - host_t0) / steps
+        drain_t0 = time.perf_counter()
         last_rows = drain()
         t_end.record()
         torch.cuda.synchronize()
+        if shard_prof and len(step_events) > 2:
+            dev_ms = sorted(a.elapsed_time(b) for a, b in zip(step_events[:-1], step_events[1:]))
+            host_ms_l = sorted(1e3 * (b - a) for a, b in zip(host_marks[:-1], host_marks[1:]))
+            print(f"[rank {rank}] host_frames={host_frames} per-step device interval ms: median {dev_ms[len(dev_ms)//2]:.3f} "
+                  f"p90 {dev_ms[int(0.9*len(dev_ms))]:.3f} max {dev_ms[-1]:.3f}; host interval: median {host_ms_l[len(host_ms_l)//2]:.3f} "
+                  f"p90 {host_ms_l[int(0.9*len(host_ms_l))]:.3f} max {host_ms_l[-1]:.3f}; first-step-to-start {t_start.elapsed_time(step_events[0]):.3f} "
+                  f"drain (host) {1e3*(time.perf_counter()-drain_t0):.3f} ms, last step to end {step_events[-1].elapsed_time(t_end):.3f} ms",
+                  file=sys.stderr, flush=True)
         if cuprof:
             torch.cuda.cudart().cudaProfilerStop()
         if world > 1:
@@ -392,7 +419,8 @@ def run_gpu(args):
         torch.cuda.empty_cache()
         if os.environ.get("SDB_SHARD_PROFILE") == "1":
             print(f"[rank {rank}] host enqueue time per step {host_ms:.3f} ms", file=sys.stderr, flush=True)
-        return {"ms": ms, "clocks": clocks, "launches": launches, "kern": kern, "h2d": h2d, "d2h": d2h, "rows": last_rows}
+        return {"ms": ms, "clocks": clocks, "launches": launches, "kern": kern, "h2d": h2d, "d2h": d2h, "rows": last_rows,
+                "sharded_resident": sharded_resident}
 
     dev = phase(host_frames=False)
     e2e = phase(host_frames=True)
@@ -443,7 +471,10 @@ def run_gpu(args):
         "config": {
             "workload": WORKLOAD, "molecules": n, "origins": n_origins, "origins_per_gpu": len(local_keys),
             "parallelism": (
-                f"origin-sharded x{world}, frame pushed to every rank by multicast stores over NVSwitch, rows gathered once per batch (NCCL)"
+                f"origin-sharded x{world}, frame pushed to every rank by multicast stores over NVSwitch "
+                + ("(device-resident phase: every rank holds 1/R of the rows of each frame in HBM and multicasts them), "
+                   if dev["sharded_resident"] else "(from the reader rank), ")
+                + "rows gathered once per batch (NCCL)"
                 if world > 1 else "single GPU"
             ),
             "l2": "inputs larger than L2 (>= 25 MB of state per origin and step)",

@@ -272,17 +272,26 @@ int sdb_isf(const float* d_dx, const float* d_dy, int32_t elem_stride, int32_t n
  * the arguments as those calls (overlap_k <= 0 or d_ov_ws NULL: no `overlap`; h_sites_xy NULL: no
  * `struct`), then the download of d_sums[n_origins][SDB_NSUM] to h_sums (pinned; NULL: stay on the
  * device).  inc_sets > 0: sdb_dyn_increments(h_inc_prev, h_inc_flags, inc_sets, d_inc_ws) runs first and
- * the segments whose `reserved` field names a set use its increments.  Asynchronous on `stream`. */
+ * the segments whose `reserved` field names a set use its increments.  Asynchronous on `stream`.
+ * The overlap bookkeeping and the row sums (small, latency-bound kernels) run on an internal
+ * high-priority side stream next to the increments pass and the struct kernel and are joined before
+ * the download (SDB_SIDE_STREAM=0: everything on `stream`).
+ * step_flags: SDB_STEP_PREDICTED -- every origin has taken part in the two previous frames (increasing
+ * time, sums requested), so its overlap bracket is predicted from its threshold history and the sample
+ * kernels are skipped; an origin for which that does not hold takes the exact selection kernel. */
+#define SDB_STEP_PREDICTED 1
 int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
                    float* d_cur_compact, const void* h_desc, void* d_desc, int32_t desc_bytes,
                    int32_t segments_offset, int32_t n_origins, int32_t n_segments,
                    int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
                    void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy,
                    int32_t n_sites, double struct_dist, int32_t struct_mode, const void* const* h_inc_prev,
-                   const uint32_t* h_inc_flags, int32_t inc_sets, void* d_inc_ws, void* stream);
+                   const uint32_t* h_inc_flags, int32_t inc_sets, void* d_inc_ws, int32_t step_flags,
+                   void* stream);
 
 /* Per-kernel-group device times of sdb_frame_step (CUDA events on the launching stream), for
- * bench.py's roofline: groups 0 overlap prepare, 1 dyn_step + finalize, 2 struct, 3 overlap resolve.
+ * bench.py's roofline: groups 0 overlap prepare (main-stream part), 1 increments pass + dyn_step, 2 struct,
+ * 3 what is left of the side stream's row sums + overlap resolve after struct.
  * sdb_profile_collect waits for the recorded events, returns the summed times in ms (h_ms[4]), the
  * number of steps and of origin-steps, and clears the collection. */
 void sdb_profile_enable(int32_t on);

@@ -108,7 +108,7 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
                               int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
                               void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy,
                               int32_t n_sites, double struct_dist, int32_t struct_mode, const void* const* h_inc_prev,
-                              const uint32_t* h_inc_flags, int32_t inc_sets, void* d_inc_ws, void* stream)
+                              const uint32_t* h_inc_flags, int32_t inc_sets, void* d_inc_ws, int32_t step_flags, void* stream)
 {
     if (!h_params || !h_desc || !d_desc || desc_bytes <= 0 || segments_offset <= 0 || segments_offset >= desc_bytes) {
         sdb_set_error("sdb_frame_step: bad descriptor arguments");
@@ -138,8 +138,9 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
             cudaStreamWaitEvent(side->stream, side->fork, 0);
             ps = side->stream;
         }
-        rc = sdb_overlap_prepare(h_params, d_pos, d_quat, d_origins, n_origins, d_segments, n_segments,
-                                 max_segment_count, overlap_k, d_ov_ws, ov_ws_origins, ps);
+        rc = sdb_overlap_prepare_ex(h_params, d_pos, d_quat, d_origins, n_origins, d_segments, n_segments,
+                                    max_segment_count, overlap_k, d_ov_ws, ov_ws_origins,
+                                    (step_flags & SDB_STEP_PREDICTED) != 0, ps);
         if (rc) return rc;
         if (side) cudaEventRecord(side->prepared, side->stream);
     }
@@ -152,7 +153,7 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
     if (use_ov && side) cudaStreamWaitEvent(s, side->prepared, 0);
     rc = sdb_dyn_step_launch(h_params, d_pos, d_quat, use_inc ? nullptr : d_cur_compact, d_origins, n_origins, d_segments,
                              n_segments, d_partials, d_sums, use_ov ? d_ov_ws : nullptr, ov_ws_origins,
-                             use_inc ? d_inc_ws : nullptr, use_inc ? inc_sets : 0, side ? 0 : 1, stream);
+                             use_inc ? d_inc_ws : nullptr, use_inc ? inc_sets : 0, (side || use_ov) ? 0 : 1, stream);
     if (rc) return rc;
     if (prof) cudaEventRecord(prof_copy.ev[2], s);
     // row sums + overlap resolve (side stream)  ||  struct (this stream)
@@ -161,13 +162,15 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
         cudaEventRecord(side->stepped, s);
         cudaStreamWaitEvent(side->stream, side->stepped, 0);
         rs = side->stream;
-        rc = sdb_dyn_finalize(d_partials, h_params->n, d_sums, n_origins, use_ov ? 1 : 0, rs);
-        if (rc) return rc;
+        if (!use_ov) {
+            rc = sdb_dyn_finalize(d_partials, h_params->n, d_sums, n_origins, 0, rs);
+            if (rc) return rc;
+        }
     }
-    auto resolve = [&]() -> int {
+    auto resolve = [&]() -> int {  // row sums + selections + intersection in one launch
         if (!use_ov) return SDB_OK;
-        return sdb_overlap_resolve(d_origins, n_origins, h_params->n, h_params->stride, overlap_k, d_ov_ws, ov_ws_origins,
-                                   d_sums, rs);
+        return sdb_overlap_resolve_fused(d_origins, n_origins, h_params->n, h_params->stride, overlap_k, d_ov_ws,
+                                         ov_ws_origins, d_partials, d_sums, rs);
     };
     if (side) {
         rc = resolve();

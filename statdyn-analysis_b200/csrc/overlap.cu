@@ -22,6 +22,8 @@
 // equal to it, those with the largest molecule indices (numpy's introsort leaves the choice among
 // equal keys unspecified -- parity trap T4; for all-equal arrays this rule gives identical sets for
 // both arrays, i.e. overlap = 1, like the reference).
+#include <cstdlib>
+
 #include "sdb_internal.cuh"
 
 namespace {
@@ -169,6 +171,8 @@ struct BracketArgs {
     long stride;
     SdbOvWorkspace w;
     uint32_t rank_hi, rank_lo;  // ranks counted from the largest sample value (1 = maximum)
+    int no_sample;              // the sample kernels were skipped: an origin without a predicted bracket gets an
+                                // open one (every molecule a candidate -> overflow -> exact kernel)
 };
 
 __global__ void __launch_bounds__(512) ov_bracket_kernel(const BracketArgs a)
@@ -177,6 +181,12 @@ __global__ void __launch_bounds__(512) ov_bracket_kernel(const BracketArgs a)
     __shared__ uint32_t scratch[512];
     const int arr = blockIdx.x, o = blockIdx.y;
     const SdbOrigin org = a.origins[o];
+    // clear this frame's candidate counter, select record and the fail list (consumed by the resolve step)
+    if (arr == 0 && threadIdx.x < 8) {
+        a.w.select[8L * o + threadIdx.x] = 0u;
+        if (threadIdx.x < 2) a.w.cand_cnt[2 * o + threadIdx.x] = 0u;
+        if (o == 0 && threadIdx.x == 2) a.w.fail[0] = 0u;
+    }
     if (org.flags & SDB_ORIGIN_NEW) return;
     if (a.w.sample_stride > 1) {
         // both arrays are predicted or neither (the sample kernel tests array 0 only)
@@ -194,6 +204,13 @@ __global__ void __launch_bounds__(512) ov_bracket_kernel(const BracketArgs a)
             }
             return;
         }
+    }
+    if (a.no_sample) {
+        if (threadIdx.x == 0) {
+            a.w.brackets[o * 4 + 2 * arr + 0] = 0.0f;
+            a.w.brackets[o * 4 + 2 * arr + 1] = __uint_as_float(0x7f7fffffu);
+        }
+        return;
     }
     const uint32_t* keys = reinterpret_cast<const uint32_t*>(a.w.samples + ((long)o * 2 + arr) * a.w.n_samples);
     const int ns = a.w.n_samples;
@@ -422,6 +439,255 @@ __global__ void __launch_bounds__(256) ov_intersect_kernel(const ResolveArgs a)
 }
 
 // =================================================================================================
+// 4b. fused resolve (sdb_frame_step): row sums + both selections + intersection of one origin in ONE
+//     block of 1024 threads.  The chain finalize -> select -> intersect of the kernels above is bound by
+//     launch gaps and dependent global-memory round trips (~130 us whatever the number of origins);
+//     here the candidates of the origin are copied to shared memory once, the two selections run side
+//     by side on the two halves of the block (named barriers), and the intersection follows in place.
+// =================================================================================================
+constexpr int RES_THREADS = 1024;
+constexpr int RES_HALF = 512;
+constexpr int RES_SMEM_CAND = 15872;  // candidates held in shared memory: 3 x 4 B x 15872 = 186 KB
+
+struct FusedArgs {
+    const SdbOrigin* origins;
+    SdbOvWorkspace w;
+    const double* partials;  // [origins][n_parts][SDB_NSUM]
+    double* sums;
+    int n_parts;
+    uint32_t k;
+    long stride;
+    int smem_cand;  // candidates that fit the dynamic shared memory of this launch (0: none)
+};
+
+__device__ __forceinline__ void half_sync(int h)
+{
+    if (h) asm volatile("bar.sync 2, 512;" ::: "memory");
+    else asm volatile("bar.sync 1, 512;" ::: "memory");
+}
+
+// block_pick for one half of the block (512 threads, named barrier 1 + h); `t` = thread index in the half.
+__device__ __forceinline__ void half_pick(const uint32_t* hist, int nbins, uint32_t remaining, uint32_t* scratch,
+                                          uint32_t* res, int h, int t, uint32_t& bin, uint32_t& above, uint32_t& at_bin)
+{
+    const int per = (nbins + RES_HALF - 1) / RES_HALF;
+    const int first = t * per;
+    uint32_t mine = 0;
+    for (int b = first; b < first + per && b < nbins; ++b) mine += hist[b];
+    const int lane = t & 31, warp = t >> 5;
+    uint32_t suffix = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t up = __shfl_down_sync(0xffffffffu, suffix, off);
+        if (lane + off < 32) suffix += up;
+    }
+    if (lane == 0) scratch[warp] = suffix;
+    half_sync(h);
+    uint32_t later = 0;
+    for (int w = warp + 1; w < RES_HALF / 32; ++w) later += scratch[w];
+    uint32_t higher = suffix - mine + later;
+    if (higher < remaining && higher + mine >= remaining) {
+        for (int b = min(first + per, nbins) - 1; b >= first; --b) {
+            const uint32_t hv = hist[b];
+            if (higher + hv >= remaining) {
+                res[0] = (uint32_t)b;
+                res[1] = higher;
+                res[2] = hv;
+                break;
+            }
+            higher += hv;
+        }
+    }
+    half_sync(h);
+    bin = res[0];
+    above = res[1];
+    at_bin = res[2];
+    half_sync(h);
+}
+
+// Strided walk of one half of the block, 8 independent loads in flight per thread.
+template <class F>
+__device__ __forceinline__ void half_walk8(const uint32_t* v, uint32_t n, uint32_t t, F f)
+{
+    uint32_t i = t;
+    for (; i + 7 * RES_HALF < n; i += 8 * RES_HALF) {
+        uint32_t x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = v[i + u * RES_HALF];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f(x[u], i + u * RES_HALF);
+    }
+    for (; i < n; i += RES_HALF) f(v[i], i);
+}
+
+// (launch bounds: 32 registers per thread, so that the struct kernel's CTAs fit next to this block)
+__global__ void __launch_bounds__(RES_THREADS, 2) ov_resolve_fused_kernel(const FusedArgs a)
+{
+    extern __shared__ __align__(16) uint32_t cand_sm[];  // [3][RES_SMEM_CAND]: index, bits of d2, bits of |dtheta|
+    __shared__ uint32_t hist[2][OV_BINS];
+    __shared__ double fin[64][17];
+    __shared__ double osum[SDB_NSUM];
+    __shared__ uint32_t scratch[2][RES_HALF / 32], res[2][3], tot[2], out_thr[2], out_cut[2], out_fail[2], both_total;
+    const int o = blockIdx.x, tid = threadIdx.x;
+
+    // ---- row sums of this origin (dyn_finalize_kernel) -------------------------------------------
+    {
+        const int v = tid & 15, r = tid >> 4;
+        const double* base = a.partials + (long)o * a.n_parts * SDB_NSUM + v;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int p = r;
+        for (; p + 192 < a.n_parts; p += 256) {
+            s0 += base[(long)p * SDB_NSUM];
+            s1 += base[(long)(p + 64) * SDB_NSUM];
+            s2 += base[(long)(p + 128) * SDB_NSUM];
+            s3 += base[(long)(p + 192) * SDB_NSUM];
+        }
+        for (; p < a.n_parts; p += 64) s0 += base[(long)p * SDB_NSUM];
+        fin[r][v] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (tid < 16) {
+            double t = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < 64; ++i) t += fin[i][tid];
+            osum[tid] = t;
+            if (tid != SDB_S_STRUCT && tid != SDB_S_OVERLAP) {
+                const bool produced = tid < SDB_NFSUM || tid == SDB_S_COMSTRUCT || tid == SDB_S_BADQUAT || tid >= SDB_S_OV_RABOVE;
+                a.sums[(long)o * SDB_NSUM + tid] = produced ? t : 0.0;
+            }
+        }
+        if (tid < 2) {
+            tot[tid] = 0;
+            out_fail[tid] = 0;
+            out_thr[tid] = 0;
+            out_cut[tid] = 0;
+        }
+        if (tid == 0) both_total = 0;
+    }
+    const SdbOrigin org = a.origins[o];
+    double* sums = a.sums + (long)o * SDB_NSUM;
+    uint32_t* sel = a.w.select + 8L * o;
+    if (org.flags & SDB_ORIGIN_NEW) {
+        // all keys are zero: ties are broken by index for both arrays -> identical sets
+        if (tid == 0) {
+            sums[SDB_S_OVERLAP] = (double)a.k;
+            ov_record_history(org, a.stride, 0u, 0u, 0u);
+        }
+        return;
+    }
+    const uint32_t n_cand = a.w.cand_cnt[2 * o];
+    const bool overflow = a.w.cand_cnt[2 * o + 1] != 0 || n_cand > (uint32_t)a.w.cand_cap;
+    const bool in_sm = !overflow && n_cand <= (uint32_t)a.smem_cand;
+    const long row = (long)o * a.w.cand_cap;
+    if (in_sm) {
+        for (uint32_t i = tid; i < n_cand; i += RES_THREADS) {
+            cand_sm[i] = __ldg(a.w.cand_idx + row + i);
+            cand_sm[RES_SMEM_CAND + i] = __ldg(a.w.cand_r + row + i);
+            cand_sm[2 * RES_SMEM_CAND + i] = __ldg(a.w.cand_t + row + i);
+        }
+    }
+    __syncthreads();
+    const uint32_t* idx = in_sm ? cand_sm : a.w.cand_idx + row;
+    const uint32_t* keys_r = in_sm ? cand_sm + RES_SMEM_CAND : a.w.cand_r + row;
+    const uint32_t* keys_t = in_sm ? cand_sm + 2 * RES_SMEM_CAND : a.w.cand_t + row;
+
+    // ---- the two selections, one per half of the block ---------------------------------------------
+    {
+        const int h = tid >> 9, t = tid & (RES_HALF - 1);
+        const uint32_t* keys = h ? keys_t : keys_r;
+        uint32_t* hh = hist[h];
+        const uint32_t plo = __float_as_uint(a.w.brackets[o * 4 + 2 * h]), phi = __float_as_uint(a.w.brackets[o * 4 + 2 * h + 1]);
+        const long need = (long)a.k - (long)osum[h ? SDB_S_OV_TABOVE : SDB_S_OV_RABOVE];
+        uint32_t inside = 0;
+        if (!overflow) half_walk8(keys, n_cand, t, [&](uint32_t kv, uint32_t) { inside += kv >= plo && kv <= phi; });
+        inside = __reduce_add_sync(0xffffffffu, inside);
+        if ((t & 31) == 0 && inside) atomicAdd(&tot[h], inside);
+        half_sync(h);
+        const uint32_t total = tot[h];
+        if (overflow || need < 1 || need > (long)total) {
+            if (t == 0) out_fail[h] = overflow ? 1u : 2u;
+        } else {
+            const int bits = phi > plo ? 32 - __clz(phi - plo) : 0;
+            uint32_t value = 0, rem = (uint32_t)need, eq = total;
+            for (int done = 0; done < bits;) {
+                const int nb = min(11, bits - done), shift = bits - done - nb;
+                for (int b = t; b < OV_BINS; b += RES_HALF) hh[b] = 0;
+                half_sync(h);
+                half_walk8(keys, n_cand, t, [&](uint32_t key, uint32_t) {
+                    if (key < plo || key > phi) return;
+                    const uint32_t kv = key - plo;
+                    if (done > 0 && (kv >> (shift + nb)) != (value >> (shift + nb))) return;
+                    atomicAdd(&hh[(kv >> shift) & ((1u << nb) - 1u)], 1u);
+                });
+                half_sync(h);
+                uint32_t bin, above, at_bin;
+                half_pick(hh, 1 << nb, rem, scratch[h], res[h], h, t, bin, above, at_bin);
+                value |= bin << shift;
+                rem -= above;
+                eq = at_bin;
+                done += nb;
+            }
+            const uint32_t thr = value + plo;
+            uint32_t cut = 0;
+            if (eq > rem) {  // keep the rem largest molecule indices among the keys equal to the threshold
+                const int idx_bits = 32 - __clz(max(a.w.n_parts * SDB_WARP_MOLS - 1, 1));
+                uint32_t r = rem;
+                for (int done = 0; done < idx_bits;) {
+                    const int nb = min(11, idx_bits - done), shift = idx_bits - done - nb;
+                    for (int b = t; b < OV_BINS; b += RES_HALF) hh[b] = 0;
+                    half_sync(h);
+                    half_walk8(keys, n_cand, t, [&](uint32_t key, uint32_t i) {
+                        if (key != thr) return;
+                        const uint32_t id = idx[i];
+                        if (done > 0 && (id >> (shift + nb)) != (cut >> (shift + nb))) return;
+                        atomicAdd(&hh[(id >> shift) & ((1u << nb) - 1u)], 1u);
+                    });
+                    half_sync(h);
+                    uint32_t bin, above, at_bin;
+                    half_pick(hh, 1 << nb, r, scratch[h], res[h], h, t, bin, above, at_bin);
+                    cut |= bin << shift;
+                    r -= above;
+                    done += nb;
+                }
+            }
+            if (t == 0) {
+                out_thr[h] = thr;
+                out_cut[h] = cut;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 2) {
+        sel[2 * tid + RS_THR] = out_thr[tid];
+        sel[2 * tid + RS_CUT] = out_cut[tid];
+        sel[RS_FAIL + tid] = out_fail[tid];
+    }
+    if (out_fail[0] | out_fail[1]) {
+        if (tid == 0) {
+            const uint32_t slot = atomicAdd(a.w.fail, 1u);
+            a.w.fail[1 + slot] = (uint32_t)o;  // the exact kernel records the thresholds
+        }
+        return;
+    }
+
+    // ---- intersection ---------------------------------------------------------------------------
+    const uint32_t thr_r = out_thr[0], cut_r = out_cut[0], thr_t = out_thr[1], cut_t = out_cut[1];
+    uint32_t both = 0;
+    for (uint32_t i = tid; i < n_cand; i += RES_THREADS) {
+        const uint32_t id = idx[i], r = keys_r[i], t = keys_t[i];
+        const bool in_r = r > thr_r || (r == thr_r && id >= cut_r);
+        const bool in_t = t > thr_t || (t == thr_t && id >= cut_t);
+        both += in_r && in_t;
+    }
+    both = __reduce_add_sync(0xffffffffu, both);
+    if ((tid & 31) == 0 && both) atomicAdd(&both_total, both);
+    __syncthreads();
+    if (tid == 0) {
+        sums[SDB_S_OVERLAP] = (double)both_total + osum[SDB_S_OV_BOTH];
+        ov_record_history(org, a.stride, 0u, thr_r, thr_t);
+    }
+}
+
+// =================================================================================================
 // 5. exact selection over the whole array: one block per origin of the list
 // =================================================================================================
 struct ExactArgs {
@@ -579,6 +845,16 @@ extern "C" int sdb_overlap_prepare(const SdbDynParams* h_params, const float* d_
                                    int32_t n_segments, int32_t max_segment_count, int32_t k, void* d_ws,
                                    int32_t ws_origins, void* stream)
 {
+    return sdb_overlap_prepare_ex(h_params, d_pos, d_quat, d_origins, n_origins, d_segments, n_segments, max_segment_count, k,
+                                  d_ws, ws_origins, 0, stream);
+}
+
+// skip_sample != 0: the caller knows that every origin has a threshold history (two or more consecutive
+// frames with increasing time), so the brackets are predicted and the sample kernels are not launched.
+int sdb_overlap_prepare_ex(const SdbDynParams* h_params, const float* d_pos, const float* d_quat, const SdbOrigin* d_origins,
+                           int32_t n_origins, const SdbSegment* d_segments, int32_t n_segments, int32_t max_segment_count,
+                           int32_t k, void* d_ws, int32_t ws_origins, int32_t skip_sample, void* stream)
+{
     if (!h_params || !d_origins || !d_segments || !d_ws || n_origins > ws_origins || k <= 0 || k > h_params->n ||
         max_segment_count <= 0 || max_segment_count > 65535 || n_segments > 65535) {
         sdb_set_error("sdb_overlap_prepare: bad argument");
@@ -599,19 +875,14 @@ extern "C" int sdb_overlap_prepare(const SdbDynParams* h_params, const float* d_
         sdb_set_error("sdb_overlap_prepare: more segments than workspace rows");
         return SDB_EINVAL;
     }
-    // candidate counters, select records and the fail list are contiguous: one clear
-    int rc = sdb_check_cuda(cudaMemsetAsync(sa.w.cand_cnt, 0, sizeof(uint32_t) * 2 * (size_t)ws_origins, s),
-                            "sdb_overlap_prepare: clear counters");
-    if (rc) return rc;
-    rc = sdb_check_cuda(cudaMemsetAsync(sa.w.select, 0, sizeof(uint32_t) * 8 * (size_t)ws_origins, s),
-                        "sdb_overlap_prepare: clear select");
-    if (rc) return rc;
-    rc = sdb_check_cuda(cudaMemsetAsync(sa.w.fail, 0, sizeof(uint32_t), s), "sdb_overlap_prepare: clear fail list");
-    if (rc) return rc;
-    ov_increment_kernel<<<dim3((sa.w.n_samples + 127) / 128, n_segments), 128, 0, s>>>(sa);
-    SDB_CHECK_LAUNCH("ov_increment_kernel");
-    ov_sample_kernel<<<dim3((sa.w.n_samples / 4 + 127) / 128, max_segment_count, n_segments), 128, 0, s>>>(sa);
-    SDB_CHECK_LAUNCH("ov_sample_kernel");
+    // (the candidate counters, select records and the fail list are cleared by ov_bracket_kernel)
+    skip_sample = skip_sample && sa.w.sample_stride > 1;  // tiny systems: the sample is the whole array
+    if (!skip_sample) {
+        ov_increment_kernel<<<dim3((sa.w.n_samples + 127) / 128, n_segments), 128, 0, s>>>(sa);
+        SDB_CHECK_LAUNCH("ov_increment_kernel");
+        ov_sample_kernel<<<dim3((sa.w.n_samples / 4 + 127) / 128, max_segment_count, n_segments), 128, 0, s>>>(sa);
+        SDB_CHECK_LAUNCH("ov_sample_kernel");
+    }
 
     // ranks (from the top) of the two sample order statistics that bracket the k-th largest key
     BracketArgs ba;
@@ -629,6 +900,7 @@ extern "C" int sdb_overlap_prepare(const SdbDynParams* h_params, const float* d_
         ba.rank_hi = hi < 1.0 ? 0u : (uint32_t)hi;                // 0: open above
         ba.rank_lo = lo > ns ? (uint32_t)ns + 1u : (uint32_t)lo;  // > ns: open below
     }
+    ba.no_sample = skip_sample && sa.w.sample_stride > 1;
     ov_bracket_kernel<<<dim3(2, n_origins), 512, 0, s>>>(ba);
     SDB_CHECK_LAUNCH("ov_bracket_kernel");
     return SDB_OK;
@@ -659,6 +931,46 @@ extern "C" int sdb_overlap_resolve(const SdbOrigin* d_origins, int32_t n_origins
     SDB_CHECK_LAUNCH("ov_intersect_kernel");
     // origins whose bracket failed: exact selection over the whole array (no-op when the list is empty)
     return launch_exact(d_origins, ra.w.fail, ra.w.select, d_sums, n, stride, k, 0, n_origins, s);
+}
+
+// sdb_dyn_finalize + sdb_overlap_resolve in one launch per frame (plus the exact kernel for failed brackets):
+// the resolve step of sdb_frame_step.  Expects dyn_step_kernel's partial rows (not yet summed).
+int sdb_overlap_resolve_fused(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride, int32_t k, void* d_ws,
+                              int32_t ws_origins, const double* d_partials, double* d_sums, void* stream)
+{
+    if (!d_origins || !d_ws || !d_sums || !d_partials || n <= 0 || k <= 0 || k > n || n_origins > ws_origins) {
+        sdb_set_error("sdb_overlap_resolve_fused: bad argument");
+        return SDB_EINVAL;
+    }
+    if (n_origins <= 0) return SDB_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    FusedArgs fa;
+    fa.origins = d_origins;
+    fa.partials = d_partials;
+    fa.sums = d_sums;
+    fa.k = (uint32_t)k;
+    fa.stride = stride;
+    sdb_ov_layout(d_ws, ws_origins, n, &fa.w);
+    fa.n_parts = fa.w.n_parts;
+    constexpr size_t smem = sizeof(uint32_t) * 3 * RES_SMEM_CAND;
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+        int rc = sdb_check_cuda(cudaFuncSetAttribute(ov_resolve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                "ov_resolve_fused_kernel: shared memory size");
+        if (rc) return rc;
+        if (dev < 64) configured[dev].store(true, std::memory_order_release);
+    }
+    // With many origins the struct kernel next to this one hides the chain anyway, and blocks that hold 186 KB
+    // of shared memory each slow that kernel down a lot (200 origins: struct 0.52 -> 0.67 ms): candidates stay
+    // in global memory (L2) then.
+    static const int smem_max_origins = [] { const char* e = getenv("SDB_RESOLVE_SMEM_MAX_ORIGINS"); return e ? atoi(e) : 64; }();
+    const bool use_smem = n_origins <= smem_max_origins;
+    fa.smem_cand = use_smem ? RES_SMEM_CAND : 0;
+    ov_resolve_fused_kernel<<<n_origins, RES_THREADS, use_smem ? smem : 0, s>>>(fa);
+    SDB_CHECK_LAUNCH("ov_resolve_fused_kernel");
+    return launch_exact(d_origins, fa.w.fail, fa.w.select, d_sums, n, stride, k, 0, n_origins, s);
 }
 
 // Diagnostics of the last sdb_overlap_resolve on this workspace (synchronises the stream):

@@ -33,6 +33,14 @@ int sdb_dyn_step_launch(const SdbDynParams* h_params, const float* d_pos, const 
                         int32_t inc_sets, int32_t finalize, void* stream);
 int sdb_dyn_finalize(const double* d_partials, int32_t n, double* d_sums, int32_t n_origins, int32_t with_ov, void* stream);
 
+// row sums + overlap selection + intersection in one launch: csrc/overlap.cu
+int sdb_overlap_resolve_fused(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride, int32_t k, void* d_ws,
+                              int32_t ws_origins, const double* d_partials, double* d_sums, void* stream);
+
+int sdb_overlap_prepare_ex(const SdbDynParams* h_params, const float* d_pos, const float* d_quat, const SdbOrigin* d_origins,
+                           int32_t n_origins, const SdbSegment* d_segments, int32_t n_segments, int32_t max_segment_count,
+                           int32_t k, void* d_ws, int32_t ws_origins, int32_t skip_sample, void* stream);
+
 #define SDB_CHECK_LAUNCH(what)                                       \
     do {                                                             \
         sdb_count_launch();                                          \
@@ -98,12 +106,16 @@ __device__ __forceinline__ uint32_t* sdb_history(const SdbOrigin& org, long stri
     return (org.flags & SDB_ORIGIN_HISTORY) ? reinterpret_cast<uint32_t*>(org.d_delta + 3 * stride) : nullptr;
 }
 
-// Bracket predicted by linear extrapolation (in time) of the last two exact thresholds of one key
-// array: [lo, hi] = extrapolation +- 2^widen max(|step| / 2, 8 thr / sqrt(n)).  Any bracket is safe --
-// the selection verifies that the k-th largest key lies inside and falls back to the exact kernel
-// otherwise; the width covers the observed prediction error (<= 0.24 |step| for young origins, threshold
-// jitter <= 4 / sqrt(n) relative for old ones) twice, and `widen` grows whenever a bracket misses.
-// About 0.4 % of the molecules become candidates instead of ~5 % with the sampled bracket.
+// Bracket predicted by extrapolating (in time) the last two exact thresholds of one key array.  Two
+// models are evaluated and the bracket is their envelope widened by 2^widen max(|step| / 10, 8 thr / sqrt(n)):
+//   linear in the key            -- |dr|^2 of diffusing molecules, |dtheta| of freely rotating ones;
+//   linear in the "other power"  -- key^2 for |dtheta| (rotational diffusion: |dtheta| ~ sqrt(t)),
+//                                   sqrt(key) for |dr|^2 (ballistic motion: |dr|^2 ~ t^2).
+// Young origins, whose thresholds move by a large fraction of their value per frame, get a bracket of
+// ~0.3 |step| instead of the |step| a single linear model needs to be safe; old origins reach the noise
+// floor (threshold jitter <= 4 / sqrt(n) relative).  Any bracket is safe -- the selection verifies that
+// the k-th largest key lies inside and falls back to the exact kernel otherwise, and `widen` grows
+// whenever a bracket misses.
 __device__ __forceinline__ bool sdb_predict_bracket(const uint32_t* hist, uint32_t td, int arr, float inv_sqrt_n,
                                                     float& lo, float& hi)
 {
@@ -112,11 +124,19 @@ __device__ __forceinline__ bool sdb_predict_bracket(const uint32_t* hist, uint32
     if (!(td > td1 && td1 > td0)) return false;
     const float t1 = __uint_as_float(hist[arr ? SDB_H_T1 : SDB_H_R1]), t0 = __uint_as_float(hist[arr ? SDB_H_T0 : SDB_H_R0]);
     if (!(t1 > 0.0f) || !(t0 > 0.0f) || !(t1 < INFINITY)) return false;
-    const float step = (t1 - t0) * ((float)(td - td1) / (float)(td1 - td0));
-    const float centre = t1 + step;
-    const float w = fmaxf(0.5f * fabsf(step), 8.0f * inv_sqrt_n * t1) * (float)(1u << min(hist[SDB_H_WIDEN], 6u));
-    lo = fmaxf(centre - w, 0.0f);
-    hi = centre + w;
+    const float ratio = (float)(td - td1) / (float)(td1 - td0);
+    const float step = (t1 - t0) * ratio;
+    const float lin = t1 + step;
+    float alt;
+    if (arr) {
+        alt = sqrtf(fmaxf(t1 * t1 + (t1 * t1 - t0 * t0) * ratio, 0.0f));
+    } else {
+        const float s1 = sqrtf(t1), s = s1 + (s1 - sqrtf(t0)) * ratio;
+        alt = s > 0.0f ? s * s : 0.0f;
+    }
+    const float w = fmaxf(0.1f * fabsf(step), 8.0f * inv_sqrt_n * t1) * (float)(1u << min(hist[SDB_H_WIDEN], 6u));
+    lo = fmaxf(fminf(lin, alt) - w, 0.0f);
+    hi = fmaxf(lin, alt) + w;
     return hi > lo && hi < INFINITY;
 }
 

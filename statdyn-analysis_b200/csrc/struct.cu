@@ -10,6 +10,8 @@
 //
 // One thread per (origin, molecule j); every row is decided by an f32 filter unless it lies within a
 // safety margin of the cutoff, in which case the exact f64 sequence of rowan.rotate is evaluated.
+#include <cstdlib>
+
 #include "sdb_internal.cuh"
 
 namespace {
@@ -291,6 +293,18 @@ extern "C" int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
     dim3 grid((unsigned)gx, n_origins);
+    {
+        // SDB_STRUCT_CARVEOUT=1 (experiment, off): the L1 / shared-memory split of dyn_step_kernel and the resolve
+        // kernel.  Measured: no gain, struct itself 5-10 % slower
+        static std::atomic<bool> configured[64];
+        static const bool want = [] { const char* e = getenv("SDB_STRUCT_CARVEOUT"); return e && e[0] == '1'; }();
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (want && dev < 64 && !configured[dev].load(std::memory_order_acquire)) {
+            cudaFuncSetAttribute(struct3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            configured[dev].store(true, std::memory_order_release);
+        }
+    }
     if (n_sites == 3 && mode == 0)
         struct3_kernel<<<grid, 256, 0, s>>>(a);
     else if (n_sites == 3)

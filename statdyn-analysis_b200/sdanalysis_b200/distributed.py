@@ -118,6 +118,8 @@ class ShardedDynamics:
         # batched gather (gather="batch")
         self.batch = int(batch)
         self._batch_buf = None
+        self._batch_recv = self._batch_host = None
+        self._rows_r0 = None
         self._batch_meta = []
 
     # -- symmetric-memory ring ------------------------------------------------------------------------
@@ -183,7 +185,9 @@ class ShardedDynamics:
         """Exchange of a frame that EVERY rank can read in host memory (e.g. the same memory-mapped GSD
         file, or a shared pinned buffer): rank r uploads only rows ``slice_bounds(r)`` over its own PCIe
         link and multicasts that slice into the frame slot of every rank, so no single host link carries
-        the whole frame.  Called by all ranks with the same frame; returns a handle for :meth:`step`."""
+        the whole frame.  A rank may instead pass just its rows as device tensors (a trajectory resident
+        in HBM, sharded by rows): they are multicast in place.  Called by all ranks with the same frame;
+        returns a handle for :meth:`step`."""
         torch = self.torch
         if self.exchange != "multicast" or not self._mc_ptr:
             return self.post_frame(position if self.rank == 0 else None, orientation if self.rank == 0 else None)
@@ -191,7 +195,17 @@ class ShardedDynamics:
         slot = self._slot
         lo, hi = self.slice_bounds()
         pos_t, quat_t = torch.as_tensor(position), torch.as_tensor(orientation)
-        if self._slice_stage is None:
+        # a rank that already holds ITS rows of the frame on the device (shape (hi - lo, ...)) multicasts
+        # them straight from there
+        direct = (
+            pos_t.is_cuda and quat_t.is_cuda and pos_t.shape[0] == hi - lo and quat_t.shape[0] == hi - lo
+            and pos_t.dtype == torch.float32 and quat_t.dtype == torch.float32
+            and pos_t.is_contiguous() and quat_t.is_contiguous()
+            and (hi - lo) % 4 == 0 and pos_t.data_ptr() % 16 == 0 and quat_t.data_ptr() % 16 == 0
+        )
+        if not direct and pos_t.shape[0] != self.n:
+            raise ValueError("post_frame_sliced needs the whole frame in host memory or this rank's rows on the device")
+        if not direct and self._slice_stage is None:
             self._slice_stage = [
                 (torch.empty((hi - lo, 3), dtype=torch.float32, device=self.device),
                  torch.empty((hi - lo, 4), dtype=torch.float32, device=self.device))
@@ -199,6 +213,7 @@ class ShardedDynamics:
             ]
             self._slice_free = [None, None]
             self._slice_i = 0
+        main = _lib.current_stream(self.device) if direct else None
         with torch.cuda.stream(self._side):
             nxt = self._consumed[(slot + 1) % self.depth]
             if nxt is not None:
@@ -206,24 +221,29 @@ class ShardedDynamics:
             if self.stalls is not None:
                 x0 = torch.cuda.Event(enable_timing=True)
                 x0.record(self._side)
-            self._slice_i ^= 1
-            spos, squat = self._slice_stage[self._slice_i]
-            free = self._slice_free[self._slice_i]
-            if free is not None:
-                self._side.wait_event(free)
-            spos.copy_(pos_t[lo:hi], non_blocking=True)
-            squat.copy_(quat_t[lo:hi], non_blocking=True)
             lib = _lib.load()
             base = self._mc_ptr + 4 * slot * self.slot_floats
+            if direct:
+                self._side.wait_event(main.record_event())  # the caller's tensors are complete
+                spos, squat = pos_t, quat_t
+            else:
+                self._slice_i ^= 1
+                spos, squat = self._slice_stage[self._slice_i]
+                free = self._slice_free[self._slice_i]
+                if free is not None:
+                    self._side.wait_event(free)
+                spos.copy_(pos_t[lo:hi], non_blocking=True)
+                squat.copy_(quat_t[lo:hi], non_blocking=True)
             _lib.check(lib.sdb_multicast_copy(spos.data_ptr(), base + 12 * lo, 12 * (hi - lo), self._mc_blocks, self._side.cuda_stream))
             _lib.check(lib.sdb_multicast_copy(squat.data_ptr(), base + 4 * self.qoff + 16 * lo, 16 * (hi - lo), self._mc_blocks, self._side.cuda_stream))
-            self._slice_free[self._slice_i] = self._side.record_event()
+            if not direct:
+                self._slice_free[self._slice_i] = self._side.record_event()
             self._hdl.barrier(channel=0)
             ready = torch.cuda.Event(enable_timing=self.stalls is not None)
             ready.record(self._side)
             if self.stalls is not None:
                 self.exchange_times.append((x0, ready))
-        self.h2d_bytes = 28 * (hi - lo)
+        self.h2d_bytes = 0 if direct else 28 * (hi - lo)
         return (slot, None, ready)
 
     def post_frame(self, position=None, orientation=None):
@@ -260,7 +280,7 @@ class ShardedDynamics:
         # symmetric-memory ring: see the class docstring.  Slot reuse: before arriving at the barrier of
         # frame u every rank waits for its own kernels on the slot of frame u + 1; the reader writes that
         # slot only after the barrier, so nobody is still reading it.
-        main = torch.cuda.current_stream(self.device)
+        main = _lib.current_stream(self.device) if self._cuda else None
         with torch.cuda.stream(self._side):
             nxt = self._consumed[(slot + 1) % self.depth]
             if nxt is not None:
@@ -322,8 +342,9 @@ class ShardedDynamics:
         slot, work, ready = handle
         if work is not None:
             work.wait()
+        main = None
         if ready is not None:
-            main = torch.cuda.current_stream(self.device)
+            main = _lib.current_stream(self.device)
             if self.stalls is not None:  # diagnostics: time the compute stream spends waiting for the frame
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(main)
@@ -350,16 +371,19 @@ class ShardedDynamics:
             keys, timediffs = [keys[i] for i in order], [timediffs[i] for i in order]
         if self._use_side:
             done = torch.cuda.Event()
-            done.record()
+            done.record(main if main is not None else _lib.current_stream(self.device))
             self._consumed[slot] = done
         if gather == "batch" and self.world > 1:
             if self._batch_buf is None:
-                self._batch_buf = torch.zeros(
-                    (self.batch, self.max_local, SDB_NSUM), dtype=torch.float64, device=self.device
-                )
+                self._setup_batch_rows()
             i = len(self._batch_meta)
             if keys and sums is not None:
-                self._batch_buf[i, : len(keys)].copy_(sums, non_blocking=True)
+                if self._rows_r0 is not None:
+                    # straight into rank 0's row buffer over NVLink (symmetric memory): flush() then needs no
+                    # collective, only a barrier and one device-to-host copy on rank 0
+                    self._rows_r0[self._rows_parity][self.rank, i, : len(keys)].copy_(sums, non_blocking=True)
+                else:
+                    self._batch_buf[i, : len(keys)].copy_(sums, non_blocking=True)
             self._batch_meta.append((int(timestep), list(active)))
             if len(self._batch_meta) == self.batch:
                 self._flushed = self.flush()
@@ -397,6 +421,37 @@ class ShardedDynamics:
 
         return collect
 
+    def _setup_batch_rows(self):
+        """Buffers of the batched row gather.  With symmetric memory (CUDA, multicast exchange): two
+        alternating row buffers ``[world][batch][max_local][SDB_NSUM]`` on rank 0 that every rank writes its
+        rows into directly; otherwise a local buffer that :meth:`flush` gathers with a collective."""
+        torch = self.torch
+        shape = (self.batch, self.max_local, SDB_NSUM)
+        self._batch_buf = torch.zeros(shape, dtype=torch.float64, device=self.device)
+        self._rows_r0 = None
+        import os
+
+        if self.exchange == "multicast" and self._hdl is not None and os.environ.get("SDB_SHARD_ROWS", "symmetric") == "symmetric":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                group = self.group if self.group is not None else self.dist.group.WORLD
+                per = self.world * self.batch * self.max_local * SDB_NSUM
+                self._rows_sym = symm_mem.empty(2 * per, dtype=torch.float64, device=self.device)
+                self._rows_hdl = symm_mem.rendezvous(self._rows_sym, group.group_name)
+                self._rows_sym.zero_()
+                full = (2, self.world) + shape
+                on_r0 = self._rows_sym.view(full) if self.rank == 0 else self._rows_hdl.get_buffer(0, full, torch.float64)
+                self._rows_r0 = [on_r0[0], on_r0[1]]
+                self._rows_parity = 0
+                torch.cuda.synchronize(self.device)
+                self.dist.barrier(group=self.group)
+            except Exception as exc:
+                import warnings
+
+                warnings.warn(f"symmetric-memory row buffer unavailable ({exc}); gathering rows with a collective")
+                self._rows_r0 = None
+
     def flush(self):
         """Gather the rows of the frames stepped with ``gather="batch"`` since the last flush.
 
@@ -407,23 +462,53 @@ class ShardedDynamics:
         if not meta or self._batch_buf is None:
             return []
         count = len(meta)
-        send = self._batch_buf[:count].contiguous()
-        recv = [torch.empty_like(send) for _ in range(self.world)] if self.rank == 0 else None
+        if self._rows_r0 is not None:
+            # every rank has written its rows into rank 0's buffer: a device-side barrier orders those writes
+            # before rank 0's copy to the host.  The buffers alternate, and a rank reaches the next flush's
+            # barrier only after rank 0 has finished reading this one, so nothing is overwritten early.
+            parity = self._rows_parity
+            self._rows_parity ^= 1
+            self._rows_hdl.barrier(channel=0)
+            if self.rank != 0:
+                return []
+            if self._batch_host is None:
+                self._batch_host = torch.empty((self.world,) + tuple(self._batch_buf.shape), dtype=torch.float64, pin_memory=True)
+            self._batch_host[:, :count].copy_(self._rows_r0[parity][:, :count])
+            return self._assemble(meta, self._batch_host.numpy())
+        send = self._batch_buf[:count]  # leading rows of a contiguous buffer: contiguous
+        if self.rank == 0:
+            if self._batch_recv is None:
+                self._batch_recv = torch.empty((self.world,) + tuple(self._batch_buf.shape), dtype=torch.float64, device=self.device)
+                self._batch_host = torch.empty(tuple(self._batch_recv.shape), dtype=torch.float64, pin_memory=self._cuda)
+            recv = [self._batch_recv[r, :count] for r in range(self.world)]
+        else:
+            recv = None
         dist.gather(send, recv, dst=0, group=self.group)
         if self.rank != 0:
             return []
-        host = [block.cpu().numpy() for block in recv]
+        # one device-to-host copy for all ranks and frames
+        self._batch_host[:, :count].copy_(self._batch_recv[:, :count])
+        return self._assemble(meta, self._batch_host.numpy())
+
+    def _assemble(self, meta, host):
+        """Rows of every frame in the order of its ``active`` list from ``host[rank][frame][local row]``."""
+        count = len(meta)
         out = []
-        cached_active, places, t0 = None, None, None
-        for i, (timestep, active) in enumerate(meta):
-            if active != cached_active:  # the scatter pattern only depends on the active list
-                cached_active = active
-                index = {k: j for j, k in enumerate(active)}
-                places = [np.array([index[k] for k in partition(active, r, self.world)], dtype=np.int64) for r in range(self.world)]
-                t0 = np.array([self._start[k] for k in active], dtype=np.int64)
-            sums = np.zeros((len(active), SDB_NSUM))
+        i = 0
+        while i < count:
+            # a run of frames with the same active list shares its scatter pattern: one assignment per rank
+            active = meta[i][1]
+            j = i + 1
+            while j < count and meta[j][1] == active:
+                j += 1
+            index = {k: c for c, k in enumerate(active)}
+            t0 = np.array([self._start[k] for k in active], dtype=np.int64)
+            sums = np.zeros((j - i, len(active), SDB_NSUM))
             for r in range(self.world):
-                if len(places[r]):
-                    sums[places[r]] = host[r][i, : len(places[r])]
-            out.append((list(active), (timestep - t0).tolist(), sums))
+                place = np.array([index[k] for k in partition(active, r, self.world)], dtype=np.int64)
+                if len(place):
+                    sums[:, place] = host[r, i:j, : len(place)]
+            for f in range(i, j):
+                out.append((list(active), (meta[f][0] - t0).tolist(), sums[f - i]))
+            i = j
         return out

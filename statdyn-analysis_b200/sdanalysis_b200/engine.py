@@ -267,11 +267,14 @@ class _Ring:
             ev.synchronize()
         return self.i, self.bufs[self.i]
 
-    def release(self, i):
+    def release(self, i, stream=None):
         ev = self.events[i]
         if ev is None:
             ev = self.events[i] = self.torch.cuda.Event()
-        ev.record()
+        if stream is None:
+            ev.record()
+        else:
+            ev.record(stream)  # with an explicit stream torch skips its (slow) current-stream lookup
         return ev
 
 
@@ -426,6 +429,9 @@ class DynamicsEngine:
         self._sums_dev_ptr = [t.data_ptr() for t in self._sums_dev]
         self._partials_ptr = self._partials.data_ptr()
 
+    def _stream_ptr(self):
+        return _lib.stream_ptr(self.device)
+
     def _inc_args(self, inc_sets):
         """ctypes arguments (h_prev, h_flags, n_sets, d_ws) of the per-frame increments pass."""
         import ctypes
@@ -498,7 +504,7 @@ class DynamicsEngine:
         dev = self._dev_frames[self._frame_i]
         pos = dev[: 3 * n].view(n, 3)
         quat = dev[qoff : qoff + 4 * n].view(n, 4) if src_quat is not None else None
-        main = torch.cuda.current_stream(self.device)
+        main = self._main
         with torch.cuda.stream(self._copy_stream):
             consumed = self._dev_consumed[self._frame_i]
             if consumed is not None:
@@ -601,8 +607,9 @@ class DynamicsEngine:
         self._ensure_capacity(n_active)
         do_sums = self.compute_sums if want_sums is None else bool(want_sums)
 
-        with torch.cuda.device(self.device):
+        with _lib.device_context(self.device):
             self._staged_slot = None
+            main = self._main = _lib.current_stream(self.device)
             if zero_step:
                 pos = quat = None
             else:
@@ -667,6 +674,7 @@ class DynamicsEngine:
                     elif quat is None or prev is None or not prev.has_orientation:
                         flags |= SEG_NO_ROTATION
                     size = chunk or max(8, math.ceil(len(members) * blocks_per_segment / target_blocks))
+                    size = math.ceil(len(members) / math.ceil(len(members) / size))  # equal shares
                     for first in range(0, len(members), size):
                         part = members[first : first + size]
                         seg_rows.append((0 if prev is None else prev.ptr, flags, len(ordered), len(part)))
@@ -727,6 +735,13 @@ class DynamicsEngine:
             params.do_sums = int(do_sums)
             use_ov = do_sums and self.compute_overlap and self.overlap_k > 0
             want_host = do_sums and to_host
+            # steady state with three or more preceding overlap selections at increasing times: every
+            # origin's bracket is predicted from its threshold history, the sample kernels are skipped
+            step_flags = 0
+            if fast:
+                if use_ov and self._origin_flags and plan["ov_steps"] >= 3 and int(timestep) > plan["timestep"]:
+                    step_flags |= _lib.SDB_STEP_PREDICTED
+                plan["ov_steps"] = plan["ov_steps"] + 1 if (use_ov and int(timestep) > plan["timestep"]) else 0
             # one native call enqueues the whole frame: descriptor upload, overlap sampling/brackets, the
             # fused dynamics kernel, struct, overlap resolve, download of the sums (csrc/frame_step.cu)
             _lib.check(
@@ -753,10 +768,11 @@ class DynamicsEngine:
                     float(self.distance) if self.distance is not None else 0.0,
                     self.struct_mode,
                     *self._inc_args(inc_sets),
-                    _lib.stream_ptr(self.device),
+                    step_flags,
+                    main.cuda_stream,
                 )
             )
-            self._desc_ring.release(ri)
+            self._desc_ring.release(ri, main)
             isf_host = None
             if do_sums and self.compute_isf:
                 _lib.check(
@@ -770,11 +786,11 @@ class DynamicsEngine:
                     isf_host = self._isf_host[si].numpy()[:n_active]
             if self._staged_slot is not None:
                 consumed = torch.cuda.Event()
-                consumed.record()
+                consumed.record(main)
                 self._dev_consumed[self._staged_slot] = consumed
             event = None
             if want_host:
-                event = self._sums_ring.release(si)
+                event = self._sums_ring.release(si, main)
                 self.d2h_bytes = n_active * SDB_NSUM * 8
 
             # ---- bookkeeping -------------------------------------------------------------------
@@ -801,6 +817,7 @@ class DynamicsEngine:
                         target_blocks = 148 * 16
                         blocks_per_segment = (self._n_parts + 3) // 4
                         size = max(8, math.ceil(n_active * blocks_per_segment / target_blocks))
+                        size = math.ceil(n_active / math.ceil(n_active / size))  # equal shares
                         flags = 0 if quat is not None else SEG_NO_ROTATION
                         for first in range(0, n_active, size):
                             plan_sdesc_rows.append((0, first, min(size, n_active - first), flags, 0))
@@ -821,6 +838,7 @@ class DynamicsEngine:
                             "has_quat": quat is not None,
                             "timestep": int(timestep),
                             "steps": 0,
+                            "ov_steps": 0,
                         }
                 self.frames_seen += 1
                 self.updates += n_active * self.n
