@@ -52,6 +52,16 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic(kernel, updates):
+    """DRAM bytes per launch of ``kernel`` from the committed ncu capture, scaled to ``updates`` per launch."""
+    path = REPO / "profiles" / "ncu_traffic.json"
+    try:
+        rec = json.loads(path.read_text())[kernel]
+        return (rec["dram_bytes_read"] + rec["dram_bytes_write"]) * updates / rec["updates_in_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -216,7 +226,10 @@ def run_gpu(args):
     def make_engine():
         return DynamicsEngine(n, box_for(n), WAVE_NUMBER, mol_sites=Trimer().positions, device=device, ring_depth=PIPELINE + 2)
 
-    n_frames = warmup + steps
+    # after the timed region a few more steps run with per-kernel-group CUDA events (sdb_profile_*) for the
+    # roofline: with the events in place the library serialises the kernels it otherwise overlaps
+    prof_steps = max(2, min(steps, 8))
+    n_frames = warmup + steps + prof_steps
 
     def phase(host_frames):
         """Create the origins (untimed), then W warm-up + K timed steps.  Returns timing info."""
@@ -226,7 +239,7 @@ def run_gpu(args):
             def step_fn(ts, pos, quat, keys):
                 return engine.step(ts, pos, quat, keys, to_host=False)
 
-            sharded = ShardedDynamics(n, step_fn, max_local=len(local_keys) + 1, device=device, batch=steps + warmup + 1)
+            sharded = ShardedDynamics(n, step_fn, max_local=len(local_keys) + 1, device=device, batch=n_frames + 1)
         # origin creation: origin k starts at frame k (linear schedule, keyframe_interval = 1)
         timestep = 0
         # frames: a random walk generated on rank 0's GPU
@@ -331,8 +344,6 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
         lib = _lib.load()
-        lib.sdb_profile_collect(None, None, None)  # drop anything collected so far
-        lib.sdb_profile_enable(1)  # per-kernel-group CUDA-event times of every sdb_frame_step call
         launches0 = _lib.launch_count()
         sampler = ClockSampler(local_rank) if rank == 0 else None
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -389,10 +400,20 @@ def run_gpu(args):
         launches = _lib.launch_count() - launches0
         import ctypes
 
+        # ---- kernel timing pass (untimed for `value`): per-kernel-group CUDA events, kernels serialised
+        lib.sdb_profile_collect(None, None, None)  # drop anything collected so far
+        lib.sdb_profile_enable(1)
+        for i in range(prof_steps):
+            one_step(warmup + steps + i, timestep)
+            timestep += 1
+        drain()
+        torch.cuda.synchronize()
         group_ms = (ctypes.c_double * 4)()
         n_steps, n_origin_steps = ctypes.c_int64(0), ctypes.c_int64(0)
         lib.sdb_profile_enable(0)
         _lib.check(lib.sdb_profile_collect(group_ms, ctypes.byref(n_steps), ctypes.byref(n_origin_steps)))
+        if world > 1:
+            dist.barrier()
         count = max(int(n_steps.value), 1)
         kern = {
             "dyn": group_ms[1], "struct": group_ms[2], "overlap": group_ms[0] + group_ms[3], "count": count,
@@ -437,9 +458,13 @@ def run_gpu(args):
     algo_bytes = bytes_per_update * a_local * n
     achieved = algo_bytes / (dyn_ms * 1e-3) / 1e9 if dyn_ms > 0 else 0.0
     roofline = {
-        "kernel": "dyn_step_kernel (+ dyn_finalize_kernel)",
+        "kernel": "dyn_step_kernel (+ dyn_increments_kernel when the per-frame pass is used)",
+        "timing": f"CUDA events around the kernel group in {prof_steps} extra steps right after the timed region (same data, "
+                  "kernels serialised; in the timed region dyn_step, struct and the overlap resolve of different origin groups overlap)",
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None,
+        "traffic": _ncu_traffic("dyn_step_kernel", a_local * n),
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/ncu_traffic.json), "
+                          "scaled by the updates of this launch",
         "algorithmic_bytes_per_update": bytes_per_update,
         "updates_per_launch": a_local * n,
         "launch_ms": dyn_ms,
