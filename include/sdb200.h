@@ -244,6 +244,16 @@ int sdb_orientational_order(const uint32_t* d_nlist, int32_t n, int32_t k, const
                             double* d_order, double* d_angles, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------------------*/
+/* ---- radial distribution function (wave-number estimate) -------------------------------------------
+ * Pair-distance histogram of freud.density.RDF(rmax, dr).compute(box, positions), the heavy part of
+ * calculate_wave_number (dynamics/_util.py:66-86), which Relaxations runs when it is given no wave number
+ * (relaxations.py:61-62): every ordered pair i != j with rsq = |box.wrap(r_j - r_i)|^2 < rmax^2 (f32, freud
+ * operation order) adds one count to bin floorf(sqrtf(rsq) / dr), bins >= nbins are dropped.
+ * h_box: Lx, Ly, Lz, xy, xz, yz; d_pos: float[n][3]; d_counts: uint64[nbins] (overwritten); nbins <= 1024.
+ * All pairs are visited (the reference asks for rmax = min(L)/2.2): O(n^2). */
+int sdb_rdf_histogram(const float* h_box, int32_t is2d, int32_t n, const float* d_pos, float rmax, float dr,
+                      int32_t nbins, uint64_t* d_counts, void* stream);
+
 const char* sdb_last_error(void);
 const char* sdb_version(void);
 /* Number of kernels launched by this library since load (used by bench.py's gpu_launches). */

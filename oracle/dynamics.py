@@ -333,16 +333,42 @@ def create_mol_relaxations(
     return MolecularRelaxation(num_elements, threshold, relaxation_type)
 
 
+def _static_structure_factor(rdf, wave_number, num_particles):
+    """dynamics/_util.py:57-63.  ``wave_number`` is a numpy float64 scalar (an element of ``np.linspace``): under
+    the pinned numpy (< 1.19, value-based casting) its product with the f32 array ``rdf.R`` is f32."""
+    F32 = np.float32
+    dr = rdf.R[1] - rdf.R[0]
+    integral = dr * np.sum((rdf.RDF - F32(1)) * rdf.R * np.sin(F32(wave_number) * rdf.R))
+    density = num_particles / rdf.box.volume
+    return 1 + 4 * np.pi * density / float(wave_number) * float(integral)
+
+
+def calculate_wave_number(box, positions):
+    """dynamics/_util.py:66-86: position of the maximum of the static structure factor on
+    ``linspace(0.5, 20, 200)``, from ``freud.density.RDF(rmax=min(L)/2.2, dr=rmax/200)``."""
+    from .freud_shim import RDF
+
+    rmax = min(box.Lx / 2.2, box.Ly / 2.2)
+    if not box.is2D:
+        rmax = min(rmax, box.Lz / 2.2)
+    dr = rmax / 200
+    rdf = RDF(dr=dr, rmax=rmax)
+    rdf.compute(box, positions)
+    x = np.linspace(0.5, 20, 200)
+    ssf = [_static_structure_factor(rdf, value, len(positions)) for value in x]
+    return x[np.argmax(ssf)]
+
+
 class Relaxations:
-    """dynamics/relaxations.py:40-184 (wave_number must be given: RDF estimation is off-path)."""
+    """dynamics/relaxations.py:40-184."""
 
     def __init__(self, timestep, box, position, orientation, molecule=None, is2D=None, wave_number=None):
         self.init_time = timestep
         is2D = molecule is not None  # relaxations.py:52-55: None -> 3D box (trap T7)
         self.motion = TrackedMotion(create_freud_box(box, is_2D=is2D), position, orientation)
         self._num_elements = position.shape[0]
-        if wave_number is None:
-            raise NotImplementedError("oracle requires an explicit wave number")
+        if wave_number is None:  # relaxations.py:61-62
+            wave_number = calculate_wave_number(self.motion.box, position)
         self.wave_number = wave_number
         d = self.distance
         self.set_mol_relax(

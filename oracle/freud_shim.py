@@ -163,3 +163,60 @@ class NearestNeighbors:
     @property
     def r_sq_list(self):
         return self._rsq
+
+
+class RDF:
+    """freud 1.x ``freud.density.RDF(rmax, dr)`` on one point set (reference call site
+    ``dynamics/_util.py:78-79``; consumers ``_util.py:57-63``: ``.R``, ``.RDF``, ``.box``) [recalled].
+
+    ``nbins = int(floorf(rmax / dr))``; bin ``i`` spans ``[i dr, (i+1) dr)``; ``R[i]`` is the centre of
+    mass of that shell, ``2/3 (r1^3 - r0^3) / (r1^2 - r0^2)``; shell volume ``pi (r1^2 - r0^2)`` in 2D,
+    ``4/3 pi (r1^3 - r0^3)`` in 3D.  Every ordered pair ``i != j`` with ``rsq < rmax^2``
+    (``rsq`` = f32 dot product of ``box.wrap(r_j - r_i)``) adds one count to bin
+    ``floorf(sqrtf(rsq) / dr)``.  ``RDF[i] = counts[i] / N / volume[i] / (N / box.volume)``, all f32.
+    """
+
+    def __init__(self, rmax, dr):
+        self.rmax, self.dr = F32(rmax), F32(dr)
+        self.nbins = int(np.floor(self.rmax / self.dr))
+        i = np.arange(self.nbins, dtype=F32)
+        r0 = i * self.dr
+        r1 = (i + F32(1.0)) * self.dr
+        self.R = (F32(2.0) / F32(3.0) * (r1 * r1 * r1 - r0 * r0 * r0) / (r1 * r1 - r0 * r0)).astype(F32)
+        self._r0, self._r1 = r0.astype(F32), r1.astype(F32)
+
+    def pair_counts(self, box, points, chunk=256):
+        pts = np.ascontiguousarray(points, dtype=F32).reshape(-1, 3)
+        n = len(pts)
+        counts = np.zeros(self.nbins, dtype=np.uint64)
+        rmaxsq = F32(self.rmax * self.rmax)
+        dr_inv = F32(1.0) / self.dr
+        for i0 in range(0, n, chunk):
+            i1 = min(n, i0 + chunk)
+            d = (pts[np.newaxis, :, :] - pts[i0:i1, np.newaxis, :]).reshape(-1, 3)
+            w = box.wrap(d)
+            rsq = (w[:, 0] * w[:, 0] + w[:, 1] * w[:, 1]) + w[:, 2] * w[:, 2]
+            keep = rsq < rmaxsq
+            keep.reshape(i1 - i0, n)[np.arange(i1 - i0), np.arange(i0, i1)] = False  # i != j
+            bins = np.floor(np.sqrt(rsq[keep]) * dr_inv).astype(np.int64)
+            bins = bins[bins < self.nbins]
+            counts += np.bincount(bins, minlength=self.nbins).astype(np.uint64)
+        return counts
+
+    def compute(self, box, points):
+        pts = np.ascontiguousarray(points, dtype=F32).reshape(-1, 3)
+        self.box = box
+        self.counts = self.pair_counts(box, pts)
+        self.RDF = normalise_rdf(self.counts, len(pts), box, self._r0, self._r1)
+        return self
+
+
+def normalise_rdf(counts, n, box, r0, r1):
+    """``RDF::reduceRDF`` [recalled]: f32 throughout."""
+    if box.is2D:
+        vol = F32(np.pi) * (r1 * r1 - r0 * r0)
+    else:
+        vol = F32(4.0) / F32(3.0) * F32(np.pi) * (r1 * r1 * r1 - r0 * r0 * r0)
+    ndens = F32(n) / F32(box.volume)
+    avg = counts.astype(F32) / F32(n)
+    return (avg / vol.astype(F32) / ndens).astype(F32)

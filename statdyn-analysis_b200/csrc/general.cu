@@ -11,27 +11,8 @@
 
 namespace {
 
-struct Box3 {
-    float lx, ly, lz, xy, xz, yz;
-    int is2d;
-};
-
-// freud Box::wrap (oracle/freud_shim.py), general triclinic form
-__device__ __forceinline__ void wrap3(const Box3& b, float vx, float vy, float vz, float& ox, float& oy, float& oz)
-{
-    const float lox = -__fmul_rn(b.lx, 0.5f), loy = -__fmul_rn(b.ly, 0.5f), loz = -__fmul_rn(b.lz, 0.5f);
-    float dx = __fsub_rn(vx, lox), dy = __fsub_rn(vy, loy), dz = __fsub_rn(vz, loz);
-    dx = __fsub_rn(dx, __fadd_rn(__fmul_rn(__fsub_rn(b.xz, __fmul_rn(b.yz, b.xy)), vz), __fmul_rn(b.xy, vy)));
-    dy = __fsub_rn(dy, __fmul_rn(b.yz, vz));
-    const float fx = sdb_frac_wrap(dx, b.lx), fy = sdb_frac_wrap(dy, b.ly);
-    const float fz = b.is2d ? 0.0f : sdb_frac_wrap(dz, b.lz);
-    oz = __fadd_rn(loz, __fmul_rn(fz, b.lz));
-    oy = __fadd_rn(loy, __fmul_rn(fy, b.ly));
-    ox = __fadd_rn(lox, __fmul_rn(fx, b.lx));
-    ox = __fadd_rn(ox, __fadd_rn(__fmul_rn(b.xy, oy), __fmul_rn(b.xz, oz)));
-    oy = __fadd_rn(oy, __fmul_rn(b.yz, oz));
-    if (b.is2d) oz = 0.0f;
-}
+using Box3 = SdbBox3;
+#define wrap3 sdb_wrap3
 
 __device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }

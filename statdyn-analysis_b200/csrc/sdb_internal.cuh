@@ -62,6 +62,29 @@ __device__ __forceinline__ void sdb_st_stream4(float* p, float4 v)
     __stcs(reinterpret_cast<float4*>(p), v);
 }
 
+// ---- freud Box (any dimension, triclinic) -----------------------------------------------------------
+struct SdbBox3 {
+    float lx, ly, lz, xy, xz, yz;
+    int is2d;
+};
+
+// freud Box::wrap (oracle/freud_shim.py), general triclinic form
+__device__ __forceinline__ void sdb_wrap3(const SdbBox3& b, float vx, float vy, float vz, float& ox, float& oy, float& oz)
+{
+    const float lox = -__fmul_rn(b.lx, 0.5f), loy = -__fmul_rn(b.ly, 0.5f), loz = -__fmul_rn(b.lz, 0.5f);
+    float dx = __fsub_rn(vx, lox), dy = __fsub_rn(vy, loy), dz = __fsub_rn(vz, loz);
+    dx = __fsub_rn(dx, __fadd_rn(__fmul_rn(__fsub_rn(b.xz, __fmul_rn(b.yz, b.xy)), vz), __fmul_rn(b.xy, vy)));
+    dy = __fsub_rn(dy, __fmul_rn(b.yz, vz));
+    const float fx = sdb_frac_wrap(dx, b.lx), fy = sdb_frac_wrap(dy, b.ly);
+    const float fz = b.is2d ? 0.0f : sdb_frac_wrap(dz, b.lz);
+    oz = __fadd_rn(loz, __fmul_rn(fz, b.lz));
+    oy = __fadd_rn(loy, __fmul_rn(fy, b.ly));
+    ox = __fadd_rn(lox, __fmul_rn(fx, b.lx));
+    ox = __fadd_rn(ox, __fadd_rn(__fmul_rn(b.xy, oy), __fmul_rn(b.xz, oz)));
+    oy = __fadd_rn(oy, __fmul_rn(b.yz, oz));
+    if (b.is2d) oz = 0.0f;
+}
+
 // ---- TrackedMotion.add for one molecule and one origin (dynamics/_util.py:149-153) ---------------
 // Shared by the fused kernel and the overlap sample kernel so both see bit-identical keys.
 __device__ __forceinline__ void sdb_apply_increment(float& dx, float& dy, float& dt, float wx, float wy, double alpha,

@@ -30,6 +30,78 @@ def create_wave_vector(wave_number: float, angular_resolution: int):
     return np.concatenate([np.cos(angles), np.sin(angles)], axis=1) * wave_number
 
 
+class _Rdf:
+    """What ``_static_structure_factor`` reads from a ``freud.density.RDF``: ``R``, ``RDF``, ``box``."""
+
+    def __init__(self, R, RDF, box, counts):
+        self.R, self.RDF, self.box, self.counts = R, RDF, box, counts
+
+
+def radial_distribution(box: Box, positions, rmax: float, dr: float, device=None) -> _Rdf:
+    """``freud.density.RDF(rmax=rmax, dr=dr).compute(box, positions)`` (reference call
+    ``dynamics/_util.py:78-79``): the pair-distance histogram comes from ``sdb_rdf_histogram``
+    (``csrc/rdf.cu``, all ordered pairs, f32 minimum image exactly as ``Box.wrap``); shell volumes and
+    density normalisation are 200 bins of f32 arithmetic on the host."""
+    torch = _lib.torch()
+    device = _lib.require_cuda(device)
+    lib = _lib.load()
+    rmax32, dr32 = F32(rmax), F32(dr)
+    nbins = int(np.floor(rmax32 / dr32))
+    if nbins <= 0 or nbins > 1024:
+        raise ValueError(f"rmax / dr gives {nbins} bins; between 1 and 1024 are supported")
+    if isinstance(positions, torch.Tensor):
+        pos = positions.to(device=device, dtype=torch.float32).contiguous()
+    else:
+        pos = torch.as_tensor(np.ascontiguousarray(positions, dtype=F32), device=device)
+    n = pos.shape[0]
+    counts = torch.empty(nbins, dtype=torch.int64, device=device)
+    with _lib.device_context(device):
+        _lib.check(
+            lib.sdb_rdf_histogram(
+                _lib.float_array(box.to_array()), int(box.is2D), n, pos.data_ptr(), float(rmax32), float(dr32), nbins,
+                counts.data_ptr(), _lib.stream_ptr(device),
+            )
+        )
+    counts = counts.cpu().numpy().astype(np.uint64)
+    i = np.arange(nbins, dtype=F32)
+    r0, r1 = i * dr32, (i + F32(1.0)) * dr32
+    R = (F32(2.0) / F32(3.0) * (r1 * r1 * r1 - r0 * r0 * r0) / (r1 * r1 - r0 * r0)).astype(F32)
+    if box.is2D:
+        vol = F32(np.pi) * (r1 * r1 - r0 * r0)
+    else:
+        vol = F32(4.0) / F32(3.0) * F32(np.pi) * (r1 * r1 * r1 - r0 * r0 * r0)
+    lx, ly, lz = (float(F32(v)) for v in (box.Lx, box.Ly, box.Lz))
+    ndens = F32(n) / F32(lx * ly if box.is2D else lx * ly * lz)
+    rdf = (counts.astype(F32) / F32(n) / vol.astype(F32) / ndens).astype(F32)
+    return _Rdf(R, rdf, box, counts)
+
+
+def _static_structure_factor(rdf, wave_number: float, num_particles: int):
+    """Reference ``dynamics/_util.py:57-63``.  ``wave_number`` arrives as a numpy float64 scalar; with the
+    reference's pinned numpy (< 1.19) its product with the f32 array ``rdf.R`` is f32, which is kept here."""
+    dr = rdf.R[1] - rdf.R[0]
+    integral = dr * np.sum((rdf.RDF - F32(1)) * rdf.R * np.sin(F32(wave_number) * rdf.R))
+    lx, ly, lz = (float(F32(v)) for v in (rdf.box.Lx, rdf.box.Ly, rdf.box.Lz))
+    density = num_particles / (lx * ly if rdf.box.is2D else lx * ly * lz)
+    return 1 + 4 * np.pi * density / float(wave_number) * float(integral)
+
+
+def calculate_wave_number(box: Box, positions: np.ndarray, device=None):
+    """Wave number of the maximum of the static structure factor (reference ``dynamics/_util.py:66-86``;
+    used by ``Relaxations`` when no wave number is given, ``relaxations.py:61-62``).  Like the reference
+    says: not recommended -- pass the wave number explicitly."""
+    box = as_box(box)
+    lx, ly, lz = (float(F32(v)) for v in (box.Lx, box.Ly, box.Lz))
+    rmax = min(lx / 2.2, ly / 2.2)
+    if not box.is2D:
+        rmax = min(rmax, lz / 2.2)
+    dr = rmax / 200
+    rdf = radial_distribution(box, positions, rmax=rmax, dr=dr, device=device)
+    x = np.linspace(0.5, 20, 200)
+    ssf = [_static_structure_factor(rdf, value, len(positions)) for value in x]
+    return x[np.argmax(ssf)]
+
+
 def molecule2particles(position: np.ndarray, orientation: np.ndarray, mol_vector: np.ndarray) -> np.ndarray:
     """Reference ``dynamics/_util.py:42-54`` verbatim in behaviour, including the pairing of SURVEY trap
     T2 (rotated sites are site-major, translations molecule-major).  Host-side helper: the hot path

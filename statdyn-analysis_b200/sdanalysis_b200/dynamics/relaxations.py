@@ -17,7 +17,7 @@ import pandas
 from .. import _lib
 from ..engine import MAX_STATUS, TrackerSpec, default_tracker_definitions
 from ..util import create_freud_box
-from ._util import TrackedMotion
+from ._util import TrackedMotion, calculate_wave_number
 
 logger = logging.getLogger(__name__)
 
@@ -190,11 +190,8 @@ class Relaxations:
         is2D = False if molecule is None else molecule.dimensions == 2  # relaxations.py:52-55 (trap T7)
         position = np.asarray(position)
         self._num_elements = position.shape[0]
-        if wave_number is None:
-            raise NotImplementedError(
-                "estimating the wave number from the radial distribution function is not on the accelerated "
-                "path (SURVEY 8f-4); pass wave_number explicitly, as sdanalysis comp-dynamics does"
-            )
+        if wave_number is None:  # relaxations.py:61-62
+            wave_number = calculate_wave_number(create_freud_box(np.asarray(box, dtype=np.float64), is_2D=is2D), position)
         self.wave_number = wave_number
         self._definition = default_tracker_definitions(self.distance)
         self.motion = TrackedMotion(
