@@ -167,15 +167,18 @@ __device__ __forceinline__ float sin2_half_fast(float theta)
 // i / 3).  Row i = s n + j is site s of rotation molecule j: away from the two places where s
 // changes the 12 rotation angles are 12 consecutive floats (three 16-byte loads when n is a
 // multiple of 4).  Per row:  |e|^2 = |t|^2 + sin^2(theta/2) (4 vy^2 - 4 vy ty).
-__global__ void __launch_bounds__(256) struct3_kernel(const StructArgs a)
+//
+// Work mapping: a group is 4 translation molecules (12 rows).  Row i = s n + j reads the angle of rotation
+// molecule j, so every angle is needed three times, by groups a third of the array apart.  A thread
+// therefore handles, back to back, the three groups g_s + u (s = 0, 1, 2; g_s = the group holding row
+// s n): their angles are the same 12 floats shifted by at most 11 elements, so the second and third
+// read hit L1 and the dtheta plane crosses DRAM once instead of three times (12 B per update
+// instead of 16-20).
+__device__ __forceinline__ int struct3_group(const StructArgs& a, const float* __restrict__ d, const float* __restrict__ dth,
+                                             const unsigned n, const float cut, const unsigned m0)
 {
-    const int o = blockIdx.y;
-    const float* __restrict__ d = a.origins[o].d_delta;
-    const float* __restrict__ dth = d + 2 * a.stride;
-    const unsigned n = (unsigned)a.n;
-    const float cut = (float)a.cut2;
     int count = 0;
-    for (unsigned m0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; m0 < n; m0 += gridDim.x * blockDim.x * 4u) {
+    {
         const float4 tx4 = sdb_ldg4(d + m0), ty4 = sdb_ldg4(d + a.stride + m0);
         const float tx[4] = {tx4.x, tx4.y, tx4.z, tx4.w};
         const float ty[4] = {ty4.x, ty4.y, ty4.z, ty4.w};
@@ -239,6 +242,25 @@ __global__ void __launch_bounds__(256) struct3_kernel(const StructArgs a)
             }
         }
     }
+    return count;
+}
+
+__global__ void __launch_bounds__(256) struct3_kernel(const StructArgs a)
+{
+    const int o = blockIdx.y;
+    const float* __restrict__ d = a.origins[o].d_delta;
+    const float* __restrict__ dth = d + 2 * a.stride;
+    const unsigned n = (unsigned)a.n;
+    const float cut = (float)a.cut2;
+    // first group of every site (host guarantees 3 n < 2^32) and the number of groups
+    const unsigned g1 = n / 12u, g2 = (unsigned)((2ull * n) / 12ull), g3 = (n + 3u) / 4u;
+    const unsigned span = max(g1, max(g2 - g1, g3 - g2));
+    int count = 0;
+    for (unsigned u = blockIdx.x * blockDim.x + threadIdx.x; u < span; u += gridDim.x * blockDim.x) {
+        if (u < g1) count += struct3_group(a, d, dth, n, cut, 4u * u);
+        if (g1 + u < g2) count += struct3_group(a, d, dth, n, cut, 4u * (g1 + u));
+        if (g2 + u < g3) count += struct3_group(a, d, dth, n, cut, 4u * (g2 + u));
+    }
     count = __reduce_add_sync(0xffffffffu, count);
     __shared__ int warp_counts[8];
     if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = count;
@@ -285,7 +307,9 @@ extern "C" int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t
     if (rc) return rc;
     // grid.x blocks per origin, each striding over the 1024-molecule tiles; sized so that the grid is a
     // whole number of waves (148 SMs x 5 resident blocks of 256 threads at 48 registers)
-    const int tiles = (n + 1023) / 1024;
+    // (struct3_kernel: one block iteration covers 256 groups of each of the three sites = 3072 molecules)
+    const bool fast3 = n_sites == 3 && mode == 0;
+    const int tiles = fast3 ? (n / 12 + 1 + 255) / 256 : (n + 1023) / 1024;
     const int base = tiles < 48 ? tiles : 48;
     const long wave = 148L * 5;
     const long waves = ((long)base * n_origins + wave - 1) / wave;
