@@ -12,6 +12,8 @@
 //                freud does (f32, one rounding per operation), strict rsq < rmax^2, top-k kept
 //                sorted by (rsq, index) in registers; writes the list, r^2, the capped count and
 //                the order parameter  mean_k cos^2(2 * intrinsic_distance(q_nb, q_i)).
+#include <cstdlib>
+
 #include "sdb_internal.cuh"
 
 namespace {
@@ -23,6 +25,7 @@ struct NbArgs {
     float lx, ly, xy;
     int ncx, ncy;
     float rmaxsq;
+    float inv_lx, inv_ly, filt;  // two-phase search: cheap minimum image and its acceptance bound (rmax + eps)^2
     int k;
     uint32_t* cell_of;     // [n]
     uint32_t* cell_count;  // [ncells + 1] -> after scan: cell_start
@@ -218,6 +221,149 @@ __global__ void __launch_bounds__(128) nb_search_kernel(const NbArgs a)
     }
 }
 
+// ---- two-phase search (orthorhombic boxes with at least 3 x 3 cells) ------------------------------------
+// The exact distance (freud's wrap: two IEEE divisions, ~45 instructions) and the sorted insertion
+// (~50) are needed only for the ~8 of ~22 candidates that lie inside the cutoff, but in the
+// one-phase kernel above a warp pays for them at every candidate (some lane always accepts).  Here
+// phase A walks the three cell rows (the 3 cells of a row are one contiguous range of the sorted array)
+// with a cheap minimum image d - L rint(d / L) and keeps the indices of the candidates within
+// rmax + eps in a per-thread list in shared memory (eps covers the f32 rounding of either distance:
+// nothing the exact test accepts is dropped); phase B evaluates exactly those, so its cost follows
+// the number of real neighbours.  The results are identical to nb_search_kernel.
+constexpr int NB_LIST = 24;
+
+template <int K>
+__device__ __forceinline__ void nb_exact_insert(const NbArgs& a, const float4 me, const uint32_t i, const uint32_t p,
+                                                float (&best_r)[K], uint32_t (&best_i)[K], int& found)
+{
+    const float4 other = __ldg(a.sorted + p);
+    const uint32_t j = __float_as_uint(other.z);
+    if (j == i) return;
+    float wx, wy;
+    sdb_wrap2d(a.lx, a.ly, a.xy, __fsub_rn(other.x, me.x), __fsub_rn(other.y, me.y), wx, wy);
+    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)), 0.0f);
+    if (!(r2 < a.rmaxsq)) return;
+    ++found;
+    float cr = r2;
+    uint32_t ci = j;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        const bool before = cr < best_r[s] || (cr == best_r[s] && ci < best_i[s]);
+        const float tr = best_r[s];
+        const uint32_t ti = best_i[s];
+        best_r[s] = before ? cr : tr;
+        best_i[s] = before ? ci : ti;
+        cr = before ? tr : cr;
+        ci = before ? ti : ci;
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void nb_write_results(const NbArgs& a, const uint32_t i, const float (&best_r)[K],
+                                                 const uint32_t (&best_i)[K], const int found)
+{
+    const int kk = a.k;  // K is the compiled capacity, kk <= K the requested width
+    if (a.nlist) {
+#pragma unroll
+        for (int s = 0; s < K; ++s)
+            if (s < kk) a.nlist[(long)i * kk + s] = best_i[s];
+    }
+    if (a.rsq) {
+#pragma unroll
+        for (int s = 0; s < K; ++s)
+            if (s < kk) a.rsq[(long)i * kk + s] = best_i[s] == 0xFFFFFFFFu ? -1.0f : best_r[s];
+    }
+    if (a.counts) a.counts[i] = (uint32_t)min(found, kk);
+    if (a.order && a.quat) {
+        const float4 q = sdb_ldg4(a.quat + 4L * i);
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            if (s < kk) {
+                const uint32_t nb = best_i[s] == 0xFFFFFFFFu ? i : best_i[s];
+                const float4 p = sdb_ldg4(a.quat + 4L * nb);
+                // multiply(conjugate(p), q) with f32 products (rowan on f32 inputs), then
+                // cos^2(2 acos(w/|r|)) = (2 w^2/|r|^2 - 1)^2 in f64
+                const float cx_ = -p.y, cy_ = -p.z, cz_ = -p.w;
+                const float rw = __fsub_rn(__fmul_rn(p.x, q.x),
+                                           __fadd_rn(__fadd_rn(__fmul_rn(cx_, q.y), __fmul_rn(cy_, q.z)), __fmul_rn(cz_, q.w)));
+                const float rx = __fadd_rn(__fadd_rn(__fmul_rn(p.x, q.y), __fmul_rn(q.x, cx_)),
+                                           __fsub_rn(__fmul_rn(cy_, q.w), __fmul_rn(cz_, q.z)));
+                const float ry = __fadd_rn(__fadd_rn(__fmul_rn(p.x, q.z), __fmul_rn(q.x, cy_)),
+                                           __fsub_rn(__fmul_rn(cz_, q.y), __fmul_rn(cx_, q.w)));
+                const float rz = __fadd_rn(__fadd_rn(__fmul_rn(p.x, q.w), __fmul_rn(q.x, cz_)),
+                                           __fsub_rn(__fmul_rn(cx_, q.z), __fmul_rn(cy_, q.y)));
+                const double w2 = (double)rw * (double)rw;
+                const double n2 = w2 + (double)rx * (double)rx + (double)ry * (double)ry + (double)rz * (double)rz;
+                const double c2 = 2.0 * w2 / n2 - 1.0;
+                acc += c2 * c2;
+            }
+        }
+        a.order[i] = acc / (double)kk;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) nb_search2_kernel(const NbArgs a)
+{
+    __shared__ uint32_t surv[NB_LIST][128];  // [slot][thread]: conflict-free
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    const float4 me = a.sorted[t];
+    const uint32_t i = __float_as_uint(me.z);
+    const int cy = cell_coord(me.y, a.ly, a.ncy);
+    const int cx = cell_coord(me.x, a.lx, a.ncx);  // xy == 0
+
+    float best_r[K];
+    uint32_t best_i[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        best_r[s] = INFINITY;
+        best_i[s] = 0xFFFFFFFFu;
+    }
+    int found = 0, cnt = 0;
+
+    // phase A: candidates of the 3 x 3 cells; a row of cells is one range of the sorted array, or two
+    // when it crosses the periodic boundary in x
+    for (int oy = -1; oy <= 1; ++oy) {
+        int yy = cy + oy;
+        yy = yy < 0 ? yy + a.ncy : (yy >= a.ncy ? yy - a.ncy : yy);
+        const uint32_t* row = a.cell_count + (long)yy * a.ncx;
+        uint32_t b0, e0, b1 = 0, e1 = 0;
+        if (cx >= 1 && cx + 1 < a.ncx) {
+            b0 = row[cx - 1];
+            e0 = row[cx + 2];
+        } else if (cx == 0) {
+            b0 = row[0];
+            e0 = row[2];
+            b1 = row[a.ncx - 1];
+            e1 = row[a.ncx];
+        } else {
+            b0 = row[a.ncx - 2];
+            e0 = row[a.ncx];
+            b1 = row[0];
+            e1 = row[1];
+        }
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            const uint32_t begin = part ? b1 : b0, end = part ? e1 : e0;
+            for (uint32_t p = begin; p < end; ++p) {
+                const float4 other = __ldg(a.sorted + p);
+                const float dx = other.x - me.x, dy = other.y - me.y;
+                const float ax = fmaf(-a.lx, rintf(dx * a.inv_lx), dx);
+                const float ay = fmaf(-a.ly, rintf(dy * a.inv_ly), dy);
+                if (fmaf(ax, ax, ay * ay) < a.filt) {
+                    if (cnt < NB_LIST) surv[cnt++][threadIdx.x] = p;
+                    else nb_exact_insert<K>(a, me, i, p, best_r, best_i, found);  // list full: evaluate in place
+                }
+            }
+        }
+    }
+    // phase B: exact distance and sorted insertion of the survivors
+    for (int s = 0; s < cnt; ++s) nb_exact_insert<K>(a, me, i, surv[s][threadIdx.x], best_r, best_i, found);
+    nb_write_results<K>(a, i, best_r, best_i, found);
+}
+
 __global__ void order_from_list_kernel(const uint32_t* __restrict__ nlist, int n, int k, const float* __restrict__ quat,
                                        double* __restrict__ order, double* __restrict__ angles)
 {
@@ -346,7 +492,20 @@ extern "C" int sdb_neighbours(const float* h_box, int32_t n, const float* d_pos,
     nb_scatter_kernel<<<nblk, 256, 0, s>>>(a);
     SDB_CHECK_LAUNCH("nb_scatter_kernel");
     const int sblk = (n + 127) / 128;
-    if (k <= 8)
+    static const bool two_phase_on = [] { const char* e = getenv("SDB_NB_TWO_PHASE"); return !(e && e[0] == '0'); }();
+    if (two_phase_on && a.xy == 0.0f && L.ncx >= 3 && L.ncy >= 3) {
+        // bound of the cheap distance: rmax plus the f32 rounding of both evaluations (a few ulp of L)
+        const float eps = 8.0f * ((nextafterf(a.lx, INFINITY) - a.lx) + (nextafterf(a.ly, INFINITY) - a.ly));
+        a.inv_lx = 1.0f / a.lx;
+        a.inv_ly = 1.0f / a.ly;
+        a.filt = (rmax + eps) * (rmax + eps);
+        if (k <= 8)
+            nb_search2_kernel<8><<<sblk, 128, 0, s>>>(a);
+        else if (k <= 9)
+            nb_search2_kernel<9><<<sblk, 128, 0, s>>>(a);
+        else
+            nb_search2_kernel<SDB_MAX_K><<<sblk, 128, 0, s>>>(a);
+    } else if (k <= 8)
         nb_search_kernel<8><<<sblk, 128, 0, s>>>(a);
     else if (k <= 9)
         nb_search_kernel<9><<<sblk, 128, 0, s>>>(a);
