@@ -442,12 +442,13 @@ __global__ void __launch_bounds__(256) ov_intersect_kernel(const ResolveArgs a)
 // 4b. fused resolve (sdb_frame_step): row sums + both selections + intersection of one origin in ONE
 //     block of 1024 threads.  The chain finalize -> select -> intersect of the kernels above is bound by
 //     launch gaps and dependent global-memory round trips (~130 us whatever the number of origins);
-//     here the candidates of the origin are copied to shared memory once, the two selections run side
-//     by side on the two halves of the block (named barriers), and the intersection follows in place.
+//     here the two selections run side by side on the two halves of the block (named barriers) and the
+//     intersection follows in place.  The candidates (~10 k per origin with predicted brackets) are walked
+//     in L2: staging them in 186 KB of shared memory per block was measured and dropped -- it did not
+//     shorten the kernel and slowed the struct kernel running beside it by 10-30 %.
 // =================================================================================================
 constexpr int RES_THREADS = 1024;
 constexpr int RES_HALF = 512;
-constexpr int RES_SMEM_CAND = 15872;  // candidates held in shared memory: 3 x 4 B x 15872 = 186 KB
 
 struct FusedArgs {
     const SdbOrigin* origins;
@@ -457,7 +458,6 @@ struct FusedArgs {
     int n_parts;
     uint32_t k;
     long stride;
-    int smem_cand;  // candidates that fit the dynamic shared memory of this launch (0: none)
 };
 
 __device__ __forceinline__ void half_sync(int h)
@@ -523,7 +523,6 @@ __device__ __forceinline__ void half_walk8(const uint32_t* v, uint32_t n, uint32
 // (launch bounds: 32 registers per thread, so that the struct kernel's CTAs fit next to this block)
 __global__ void __launch_bounds__(RES_THREADS, 2) ov_resolve_fused_kernel(const FusedArgs a)
 {
-    extern __shared__ __align__(16) uint32_t cand_sm[];  // [3][RES_SMEM_CAND]: index, bits of d2, bits of |dtheta|
     __shared__ uint32_t hist[2][OV_BINS];
     __shared__ double fin[64][17];
     __shared__ double osum[SDB_NSUM];
@@ -576,19 +575,11 @@ __global__ void __launch_bounds__(RES_THREADS, 2) ov_resolve_fused_kernel(const 
     }
     const uint32_t n_cand = a.w.cand_cnt[2 * o];
     const bool overflow = a.w.cand_cnt[2 * o + 1] != 0 || n_cand > (uint32_t)a.w.cand_cap;
-    const bool in_sm = !overflow && n_cand <= (uint32_t)a.smem_cand;
     const long row = (long)o * a.w.cand_cap;
-    if (in_sm) {
-        for (uint32_t i = tid; i < n_cand; i += RES_THREADS) {
-            cand_sm[i] = __ldg(a.w.cand_idx + row + i);
-            cand_sm[RES_SMEM_CAND + i] = __ldg(a.w.cand_r + row + i);
-            cand_sm[2 * RES_SMEM_CAND + i] = __ldg(a.w.cand_t + row + i);
-        }
-    }
     __syncthreads();
-    const uint32_t* idx = in_sm ? cand_sm : a.w.cand_idx + row;
-    const uint32_t* keys_r = in_sm ? cand_sm + RES_SMEM_CAND : a.w.cand_r + row;
-    const uint32_t* keys_t = in_sm ? cand_sm + 2 * RES_SMEM_CAND : a.w.cand_t + row;
+    const uint32_t* idx = a.w.cand_idx + row;
+    const uint32_t* keys_r = a.w.cand_r + row;
+    const uint32_t* keys_t = a.w.cand_t + row;
 
     // ---- the two selections, one per half of the block ---------------------------------------------
     {
@@ -952,23 +943,7 @@ int sdb_overlap_resolve_fused(const SdbOrigin* d_origins, int32_t n_origins, int
     fa.stride = stride;
     sdb_ov_layout(d_ws, ws_origins, n, &fa.w);
     fa.n_parts = fa.w.n_parts;
-    constexpr size_t smem = sizeof(uint32_t) * 3 * RES_SMEM_CAND;
-    static std::atomic<bool> configured[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        int rc = sdb_check_cuda(cudaFuncSetAttribute(ov_resolve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                                "ov_resolve_fused_kernel: shared memory size");
-        if (rc) return rc;
-        if (dev < 64) configured[dev].store(true, std::memory_order_release);
-    }
-    // With many origins the struct kernel next to this one hides the chain anyway, and blocks that hold 186 KB
-    // of shared memory each slow that kernel down a lot (200 origins: struct 0.52 -> 0.67 ms): candidates stay
-    // in global memory (L2) then.
-    static const int smem_max_origins = [] { const char* e = getenv("SDB_RESOLVE_SMEM_MAX_ORIGINS"); return e ? atoi(e) : 64; }();
-    const bool use_smem = n_origins <= smem_max_origins;
-    fa.smem_cand = use_smem ? RES_SMEM_CAND : 0;
-    ov_resolve_fused_kernel<<<n_origins, RES_THREADS, use_smem ? smem : 0, s>>>(fa);
+    ov_resolve_fused_kernel<<<n_origins, RES_THREADS, 0, s>>>(fa);
     SDB_CHECK_LAUNCH("ov_resolve_fused_kernel");
     return launch_exact(d_origins, fa.w.fail, fa.w.select, d_sums, n, stride, k, 0, n_origins, s);
 }

@@ -203,26 +203,33 @@ __device__ __forceinline__ int struct3_group(const StructArgs& a, const float* _
                 const float4 v = sdb_ldg4(dth + j0 + 4 * q);
                 th[4 * q] = v.x; th[4 * q + 1] = v.y; th[4 * q + 2] = v.z; th[4 * q + 3] = v.w;
             }
-            unsigned near = 0u;  // rows the fast filter cannot decide (within the margin, or |theta| > 16)
+            // rows the fast filter cannot decide (within the margin, or |theta| > 16) are rare (~1e-5): the
+            // group is then redone row by row; the common case pays one flag instead of a bit mask per row
+            float th_max = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 12; ++r) th_max = fmaxf(th_max, fabsf(th[r]));
+            bool undecided = th_max > 16.0f;
+            int fast = 0;
 #pragma unroll
             for (int r = 0; r < 12; ++r) {
                 const int e = r / 3;
                 const float e2 = fmaf(sin2_half_fast(th[r]), fmaf(-b4, ty[e], c4), t2[e]);
-                const bool undecided = !(fabsf(e2 - cut) > mg[e]) || fabsf(th[r]) > 16.0f;
-                near |= (unsigned)undecided << r;
-                count += (e2 < cut) && !undecided;
+                undecided |= !(fabsf(e2 - cut) > mg[e]);
+                fast += e2 < cut;
             }
-            while (near) {  // about one row in 1e5
-                const unsigned r = __ffs(near) - 1u;
-                near &= near - 1u;
-                const unsigned m = m0 + r / 3u;
-                const float theta = __ldg(dth + j0 + r), txm = __ldg(d + m), tym = __ldg(d + a.stride + m);
-                const float t2m = fmaf(txm, txm, tym * tym);
-                const float e2 = fmaf(two_one_minus_cos(theta), vy * (vy - tym), t2m);
-                bool inside = e2 < cut;
-                if (!(fabsf(e2 - cut) > 8e-6f * (t2m + 1.0f + 8.0f * vy * vy)))
-                    inside = struct_row_exact(theta, (double)txm, (double)tym, (double)vx, (double)vy, a.cut2);
-                count += inside;
+            if (!undecided) {
+                count += fast;
+            } else {
+                for (unsigned r = 0; r < 12u; ++r) {
+                    const unsigned m = m0 + r / 3u;
+                    const float theta = __ldg(dth + j0 + r), txm = __ldg(d + m), tym = __ldg(d + a.stride + m);
+                    const float t2m = fmaf(txm, txm, tym * tym);
+                    const float e2 = fmaf(two_one_minus_cos(theta), vy * (vy - tym), t2m);
+                    bool inside = e2 < cut;
+                    if (!(fabsf(e2 - cut) > 8e-6f * (t2m + 1.0f + 8.0f * vy * vy)))
+                        inside = struct_row_exact(theta, (double)txm, (double)tym, (double)vx, (double)vy, a.cut2);
+                    count += inside;
+                }
             }
         } else {  // a site boundary, the last molecules, or n not a multiple of 4: row by row
             for (unsigned r = 0; r < 12u; ++r) {

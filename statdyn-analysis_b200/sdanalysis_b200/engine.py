@@ -391,7 +391,7 @@ class DynamicsEngine:
         # the per-frame pass costs about one phase 1 plus 76 B per molecule of traffic: it pays when
         # several segments share a previous sample and each has few origins to amortise its own phase 1
         # over (measured: 25 origins in 3 segments -11 % on dyn_step, 200 origins in 3 segments +3 %)
-        self._inc_max_per_segment = int(os.environ.get("SDB_INCREMENTS_MAX_PER_SEGMENT", "12"))
+        self._inc_max_per_segment = int(os.environ.get("SDB_INCREMENTS_MAX_PER_SEGMENT", "40"))
         self._inc_ws = None
         self._sites_c = None if self.mol_sites is None else _lib.float_array(self.mol_sites.reshape(-1))
         self.frames_seen = 0
