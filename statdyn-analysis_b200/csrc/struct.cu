@@ -151,21 +151,11 @@ __global__ void __launch_bounds__(256) struct_kernel(const StructArgs a)
     }
 }
 
-// sin^2(theta / 2) through the special-function unit, |theta| <= 16: sin.approx reduces its argument itself
-// (one product with 1 / 2 pi rounded towards zero, then the fractional revolution), so for half angles up
-// to 8 rad the absolute error stays below ~1.5e-6 (argument rounding 1e-6 rad + 2^-21 of the unit),
-// i.e. < 6e-6 on 2 (1 - cos theta) -- inside the filter margin below.
-__device__ __forceinline__ float sin2_half_fast(float theta)
-{
-    const float sn = __sinf(0.5f * theta);
-    return sn * sn;
-}
-
 // Fast kernel for three sites, mode 0.  Each thread owns 4 consecutive TRANSLATION molecules
 // m0..m0+3, i.e. the 12 consecutive rows i = 3 m0 .. 3 m0 + 11 (row i is translated by molecule
 // i / 3).  Row i = s n + j is site s of rotation molecule j: away from the two places where s
 // changes the 12 rotation angles are 12 consecutive floats (three 16-byte loads when n is a
-// multiple of 4).  Per row:  |e|^2 = |t|^2 + sin^2(theta/2) (4 vy^2 - 4 vy ty).
+// multiple of 4).  Per row:  |e|^2 = |t|^2 + (1 - cos theta) 2 vy (vy - ty).
 //
 // Work mapping: a group is 4 translation molecules (12 rows).  Row i = s n + j reads the angle of rotation
 // molecule j, so every angle is needed three times, by groups a third of the array apart.  A thread
@@ -188,13 +178,17 @@ __device__ __forceinline__ int struct3_group(const StructArgs& a, const float* _
         if (m0 + 4u <= n && s0 == s_last && (j0 & 3u) == 0u) {
             const float vx = s0 == 0u ? a.sx[0] : (s0 == 1u ? a.sx[1] : a.sx[2]);
             const float vy = s0 == 0u ? a.sy[0] : (s0 == 1u ? a.sy[1] : a.sy[2]);
-            const float c4 = 4.0f * vy * vy, b4 = 4.0f * vy;
+            // |e|^2 - cut = (|t|^2 + g - cut) - g cos(theta),  g = 2 vy (vy - ty): one cos.approx (absolute error
+            // < 2.5e-6 for |theta| <= 16, argument reduction included) and one fma per row
+            const float c2 = 2.0f * vy * vy, b2 = 2.0f * vy;
             const float vmargin = 8e-6f * (1.0f + 8.0f * vy * vy);
-            float t2[4], mg[4];
+            float g[4], base[4], mg[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                t2[e] = fmaf(tx[e], tx[e], ty[e] * ty[e]);
-                mg[e] = fmaf(8e-6f, t2[e], vmargin);
+                const float t2 = fmaf(tx[e], tx[e], ty[e] * ty[e]);
+                g[e] = fmaf(-b2, ty[e], c2);
+                base[e] = (t2 + g[e]) - cut;
+                mg[e] = fmaf(8e-6f, t2, vmargin);
             }
             float th[12];
 #pragma unroll
@@ -203,18 +197,19 @@ __device__ __forceinline__ int struct3_group(const StructArgs& a, const float* _
                 th[4 * q] = v.x; th[4 * q + 1] = v.y; th[4 * q + 2] = v.z; th[4 * q + 3] = v.w;
             }
             // rows the fast filter cannot decide (within the margin, or |theta| > 16) are rare (~1e-5): the
-            // group is then redone row by row; the common case pays one flag instead of a bit mask per row
+            // group is then redone row by row.  (A NaN row is "not inside" on both paths.)
             float th_max = 0.0f;
 #pragma unroll
             for (int r = 0; r < 12; ++r) th_max = fmaxf(th_max, fabsf(th[r]));
             bool undecided = th_max > 16.0f;
             int fast = 0;
 #pragma unroll
-            for (int r = 0; r < 12; ++r) {
-                const int e = r / 3;
-                const float e2 = fmaf(sin2_half_fast(th[r]), fmaf(-b4, ty[e], c4), t2[e]);
-                undecided |= !(fabsf(e2 - cut) > mg[e]);
-                fast += e2 < cut;
+            for (int e = 0; e < 4; ++e) {
+                const float d0 = fmaf(-__cosf(th[3 * e]), g[e], base[e]);
+                const float d1 = fmaf(-__cosf(th[3 * e + 1]), g[e], base[e]);
+                const float d2 = fmaf(-__cosf(th[3 * e + 2]), g[e], base[e]);
+                fast += (d0 < 0.0f) + (d1 < 0.0f) + (d2 < 0.0f);
+                undecided |= !(fminf(fminf(fabsf(d0), fabsf(d1)), fabsf(d2)) > mg[e]);
             }
             if (!undecided) {
                 count += fast;
