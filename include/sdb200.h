@@ -244,6 +244,16 @@ int sdb_orientational_order(const uint32_t* d_nlist, int32_t n, int32_t k, const
                             double* d_order, double* d_angles, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------------------*/
+/* ---- Voronoi neighbour counts ---------------------------------------------------------------------
+ * freud.voronoi.Voronoi(box, buff).computeNeighbors(position).nlist.neighbor_counts of
+ * order.compute_voronoi_neighs (order.py:312-315) for an orthorhombic 2D box: the cell of every molecule is
+ * clipped by the bisectors of its neighbours in order of distance (d_nlist: (n, k) from sdb_neighbours with
+ * radius rmax, k <= SDB_MAX_K) until no farther molecule can cut it; molecules whose list ends before that
+ * are redone against all molecules.  d_counts: uint32[n] (0xFFFFFFFF: the cell meets the molecule's own
+ * periodic images); d_scratch: uint32[n + 1]. */
+int sdb_voronoi_counts(const float* h_box, int32_t n, const float* d_pos, const uint32_t* d_nlist, int32_t k,
+                       float rmax, uint32_t* d_counts, uint32_t* d_scratch, void* stream);
+
 /* ---- radial distribution function (wave-number estimate) -------------------------------------------
  * Pair-distance histogram of freud.density.RDF(rmax, dr).compute(box, positions), the heavy part of
  * calculate_wave_number (dynamics/_util.py:66-86), which Relaxations runs when it is given no wave number

@@ -220,3 +220,52 @@ def normalise_rdf(counts, n, box, r0, r1):
     ndens = F32(n) / F32(box.volume)
     avg = counts.astype(F32) / F32(n)
     return (avg / vol.astype(F32) / ndens).astype(F32)
+
+
+class Voronoi:
+    """freud 1.x ``freud.voronoi.Voronoi(box, buff).computeNeighbors(positions)`` in 2D (reference call
+    site ``order.py:312-315``; only ``nlist.neighbor_counts`` is consumed) [recalled]: the points are
+    extended by the periodic images that lie within ``buff`` of the box, ``scipy.spatial.Voronoi`` (qhull)
+    is run on the extended set, and every finite ridge that touches a real point makes the two generating
+    points (images mapped back to their originals) neighbours of each other; a pair is counted once."""
+
+    def __init__(self, box, buff=0.1):
+        self.box, self.buff = box, float(buff)
+
+    def computeNeighbors(self, positions):
+        from scipy.spatial import Voronoi as QhullVoronoi
+
+        pts = np.asarray(positions, dtype=np.float64)[:, :2]
+        n = len(pts)
+        L = np.array([self.box.Lx, self.box.Ly], dtype=np.float64)
+        buff = min(self.buff, 0.5 * float(L.min()))
+        expanded, ids = [pts], [np.arange(n)]
+        for sx in (-1, 0, 1):
+            for sy in (-1, 0, 1):
+                if sx == 0 and sy == 0:
+                    continue
+                img = pts + np.array([sx, sy]) * L
+                keep = np.all((img > -L / 2 - buff) & (img < L / 2 + buff), axis=1)
+                expanded.append(img[keep])
+                ids.append(np.nonzero(keep)[0])
+        expanded, ids = np.concatenate(expanded), np.concatenate(ids)
+        vor = QhullVoronoi(expanded)
+        pairs = set()
+        self.ridge_lengths = {}
+        for (p, q), verts in zip(vor.ridge_points, vor.ridge_vertices):
+            if (p >= n and q >= n) or -1 in verts:
+                continue
+            i, j = int(ids[p]), int(ids[q])
+            if i == j:
+                continue
+            key = (min(i, j), max(i, j))
+            pairs.add(key)
+            length = float(np.linalg.norm(vor.vertices[verts[0]] - vor.vertices[verts[1]]))
+            self.ridge_lengths[key] = min(length, self.ridge_lengths.get(key, np.inf))
+        counts = np.zeros(n, dtype=np.uint32)
+        for i, j in pairs:
+            counts[i] += 1
+            counts[j] += 1
+        self.nlist = NeighborListView(counts)
+        self.pairs = pairs
+        return self

@@ -61,3 +61,13 @@ def relative_distances(box, position, max_radius=3.5, max_neighbours=8):
     distances[:] = nn.r_sq_list
     distances[distances < 0] = 0
     return np.sqrt(distances)
+
+
+def compute_voronoi_neighs(box, position, return_query=False, buff=5):
+    """order.py:312-315 (``buff=5`` like the reference; a larger buffer gives the exact periodic diagram
+    when cells are wider than that, which freud's buffer does not cover)."""
+    from .freud_shim import Voronoi
+
+    vor = Voronoi(create_freud_box(box), buff=buff)
+    query = vor.computeNeighbors(position)
+    return query if return_query else query.nlist.neighbor_counts

@@ -155,7 +155,13 @@ __device__ __forceinline__ void sdb_mbar_wait(uint64_t* bar, uint32_t parity)
 
 // Per-warp shared memory: a ring of state tiles filled by bulk copies (one origin per stage), the
 // reduction scratch and the staged overlap candidates.  Warps never synchronise with each other.
-constexpr int SDB_STAGES = 3;
+#ifndef SDB_STAGES_OVERRIDE
+#define SDB_STAGES_OVERRIDE 3
+#endif
+#ifndef SDB_MIN_BLOCKS
+#define SDB_MIN_BLOCKS 4
+#endif
+constexpr int SDB_STAGES = SDB_STAGES_OVERRIDE;  // (build-time knobs for experiments: -DSDB_STAGES_OVERRIDE=2 -DSDB_MIN_BLOCKS=5)
 constexpr int SDB_PLANE_BYTES = SDB_WARP_MOLS * 4;                       // 1 KB: one f32 plane of a tile
 constexpr int SDB_STAGE_BYTES = 3 * SDB_PLANE_BYTES + SDB_WARP_MOLS;     // dx, dy, dtheta planes + flag bytes
 struct alignas(128) StepWarpShared {
@@ -674,7 +680,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
 
 // grid = (warp tiles / 4, segments).  The partial last tile (if any) takes the bounds-checked path.
 template <bool SUMS, bool OV, bool TRACK, bool PRE>
-__global__ void __launch_bounds__(SDB_BLOCK_THREADS, 4) dyn_step_kernel(const __grid_constant__ StepArgs a)
+__global__ void __launch_bounds__(SDB_BLOCK_THREADS, SDB_MIN_BLOCKS) dyn_step_kernel(const __grid_constant__ StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StepWarpShared& sh = reinterpret_cast<StepWarpShared*>(smem_raw)[threadIdx.x >> 5];

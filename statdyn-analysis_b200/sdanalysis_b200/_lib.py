@@ -43,6 +43,7 @@ EXPORTS = (
     "sdb_multicast_copy",
     "sdb_frame_step",
     "sdb_rdf_histogram",
+    "sdb_voronoi_counts",
     "sdb_isf_origins",
     "sdb_isf",
     "sdb_profile_enable",
@@ -153,6 +154,7 @@ def load():
              c_int32, POINTER(c_float), c_int32, ctypes.c_double, c_int32, POINTER(c_void_p), POINTER(c_uint32),
              c_int32, P, c_int32, P],
         ),
+        "sdb_voronoi_counts": (c_int32, [POINTER(c_float), c_int32, P, P, c_int32, c_float, P, P, P]),
         "sdb_rdf_histogram": (c_int32, [POINTER(c_float), c_int32, c_int32, P, c_float, c_float, c_int32, P, P]),
         "sdb_isf_origins": (c_int32, [P, c_int32, c_int32, c_int32, c_double, c_int32, P, P]),
         "sdb_isf": (c_int32, [P, P, c_int32, c_int32, c_double, c_int32, P, P]),

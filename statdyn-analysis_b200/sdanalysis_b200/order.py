@@ -196,6 +196,42 @@ def relative_distances(box, position, max_radius: float = 3.5, max_neighbours: i
     return np.sqrt(distances)
 
 
+def compute_voronoi_neighs(box, position) -> np.ndarray:
+    """Number of Voronoi neighbours of every molecule (reference ``order.py:312-315``, which asks
+    ``freud.voronoi.Voronoi(box, buff=5).computeNeighbors(position)`` for ``nlist.neighbor_counts``).
+
+    The 16 nearest neighbours within ~4 mean spacings come from the cell-list kernel; ``csrc/voronoi.cu``
+    clips every molecule's cell by their bisectors in order of distance until no farther molecule can cut
+    it, and redoes the few molecules whose list ends too early against all molecules."""
+    torch = _lib.torch()
+    device = _lib.require_cuda()
+    lib = _lib.load()
+    box6 = _box6(box)
+    if box6[3] != 0:
+        raise NotImplementedError("Voronoi neighbour counts cover orthorhombic 2D boxes only")
+    with torch.cuda.device(device):
+        pos = _to_device(position, 3, torch, device)
+        n = pos.shape[0]
+        if n == 0:
+            raise RuntimeError("Position must contain values, has length of 0.")
+        k = _lib.SDB_MAX_K
+        spacing = float(np.sqrt(float(box6[0]) * float(box6[1]) / n))
+        rmax = min(4.0 * spacing, 0.49 * float(min(box6[0], box6[1])))
+        found = neighbour_analysis(box6, pos, None, rmax, k, want=("nlist",), device=device, to_host=False)
+        counts = torch.empty(n, dtype=torch.int32, device=device)
+        scratch = torch.empty(n + 1, dtype=torch.int32, device=device)
+        _lib.check(
+            lib.sdb_voronoi_counts(
+                _lib.float_array(box6), n, pos.data_ptr(), found["nlist"].data_ptr(), k, float(rmax),
+                counts.data_ptr(), scratch.data_ptr(), _lib.stream_ptr(device),
+            )
+        )
+        out = counts.cpu().numpy().view(np.uint32)
+    if (out == 2 ** 32 - 1).any():
+        raise RuntimeError("a Voronoi cell reaches the molecule's own periodic images (too few molecules for the box)")
+    return out
+
+
 def create_orient_ordering(threshold: float):
     """Reference ``order.py:126-147``."""
 
