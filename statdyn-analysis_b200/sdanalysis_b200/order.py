@@ -239,3 +239,27 @@ def create_orient_ordering(threshold: float):
         return orientational_order(snap.box, snap.position, snap.orientation) > threshold
 
     return compute_orient_ordering
+
+
+def create_neigh_ordering(neighbours: int):
+    """Reference ``order.py:150-171``: a molecule is ordered when it has exactly ``neighbours`` Voronoi
+    neighbours."""
+
+    def compute_neigh_ordering(snap) -> np.ndarray:
+        return compute_voronoi_neighs(snap.box, snap.position) == neighbours
+
+    return compute_neigh_ordering
+
+
+def create_ml_ordering(model):
+    """Reference ``order.py:89-123``: classify the relative orientations of the 8 nearest neighbours
+    within 3.5 with a pickled scikit-learn model (loaded with joblib like the reference)."""
+    import joblib
+
+    ml_model = joblib.load(model)
+
+    def compute_ml_order(snap) -> np.ndarray:
+        orientations = relative_orientations(snap.box, snap.position, snap.orientation, 3.5, 8)
+        return ml_model.predict(orientations)
+
+    return compute_ml_order

@@ -94,3 +94,22 @@ def test_process_file_writes_tables(trajectory, tmp_path):
         for name, col in want.items():
             mask = ~near[key][name]
             assert np.array_equal(got[name].to_numpy()[mask], col[mask]), (key, name)
+
+
+def test_run_analysis_order(trajectory, tmp_path):
+    """reference run_analysis.py:20-42: one CSV row per frame, fraction of particles with order > 0.9."""
+    from oracle import order as oorder
+    from sdanalysis_b200 import run_analysis
+    from sdanalysis_b200.gsdio import open_gsd
+
+    out = tmp_path / "order.csv"
+    run_analysis.order(trajectory, out)
+    lines = out.read_text().strip().splitlines()
+    assert lines[0] == "Timestep, OrientOrder"
+    with open_gsd(trajectory) as traj:
+        assert len(lines) == len(traj) + 1
+        snap = traj[len(traj) - 1]
+        step, _, value = lines[-1].split()
+        want = oorder.orientational_order(snap.box, snap._position, snap._orientation)
+        assert int(step) == snap.step
+        assert np.isclose(float(value), np.sum(want > 0.9) / len(want), atol=2.0 / len(want))

@@ -91,3 +91,28 @@ def test_cuda_voronoi_synthetic_liquid_euler_relation():
     counts = order.compute_voronoi_neighs(walk.box, pos)
     assert counts.sum() == 6 * len(counts)
     assert counts.min() >= 3 and counts.max() <= 12
+
+
+@pytest.mark.gpu
+def test_ordering_factories(golden_dir, tmp_path):
+    """reference order.py:89-171: the three classifier factories on a crystal frame."""
+    import joblib
+    from sklearn.tree import DecisionTreeClassifier
+
+    from sdanalysis_b200 import order
+    from sdanalysis_b200.frame import HoomdFrame  # noqa: F401  (the factories take any object with box/position/orientation)
+
+    g = np.load(golden_dir / "crystal_p2.npz")
+
+    class Snap:
+        box, position, orientation = g["box"], g["position"], g["orientation"]
+
+    assert np.all(order.create_neigh_ordering(6)(Snap))
+    assert not np.any(order.create_neigh_ordering(5)(Snap))
+    assert np.all(order.create_orient_ordering(0.6)(Snap))  # reference test/order_test.py:58-63
+    features = order.relative_orientations(Snap.box, Snap.position, Snap.orientation, 3.5, 8)
+    labels = (np.arange(len(features)) % 2).astype(int)
+    path = tmp_path / "model.pkl"
+    joblib.dump(DecisionTreeClassifier(max_depth=3, random_state=0).fit(features, labels), path)
+    predicted = order.create_ml_ordering(path)(Snap)
+    assert predicted.shape == (len(features),) and set(np.unique(predicted)) <= {0, 1}
