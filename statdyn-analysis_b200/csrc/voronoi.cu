@@ -15,7 +15,8 @@
 
 namespace {
 
-constexpr int VOR_MAXV = 40;
+constexpr int VOR_MAXV = 40;         // first kernel: neighbours arrive in order of distance, cells stay small
+constexpr int VOR_MAXV_BRUTE = 128;  // second kernel: arbitrary order inside a shell
 constexpr uint32_t VOR_MISSING = 0xFFFFFFFFu;
 
 struct VorArgs {
@@ -29,13 +30,16 @@ struct VorArgs {
     uint32_t* unresolved;   // [0] = count, [1..] = molecule indices
 };
 
-struct Poly {
-    double x[VOR_MAXV], y[VOR_MAXV];
-    int tag[VOR_MAXV];  // generator of the edge leaving vertex v (-1: the initial square)
+template <int CAP>
+struct PolyT {
+    double x[CAP], y[CAP];
+    int tag[CAP];  // generator of the edge leaving vertex v (-1: the initial square)
     int nv;
 };
+using Poly = PolyT<VOR_MAXV>;
 
-__device__ __forceinline__ void poly_square(Poly& p, double b)
+template <int CAP>
+__device__ __forceinline__ void poly_square(PolyT<CAP>& p, double b)
 {
     p.nv = 4;
     p.x[0] = -b; p.y[0] = -b;
@@ -47,7 +51,8 @@ __device__ __forceinline__ void poly_square(Poly& p, double b)
 
 // Keep the part of the convex polygon with x . d <= |d|^2 / 2 (closer to the origin than to d).
 // Returns false when the vertex buffer would overflow.
-__device__ bool poly_clip(const Poly& in, Poly& out, double dx, double dy, int newtag)
+template <int CAP>
+__device__ bool poly_clip(const PolyT<CAP>& in, PolyT<CAP>& out, double dx, double dy, int newtag)
 {
     const double c = 0.5 * (dx * dx + dy * dy);
     int m = 0;
@@ -56,12 +61,12 @@ __device__ bool poly_clip(const Poly& in, Poly& out, double dx, double dy, int n
         const double sa = in.x[v] * dx + in.y[v] * dy - c, sb = in.x[w] * dx + in.y[w] * dy - c;
         const bool ina = sa <= 0.0, inb = sb <= 0.0;
         if (ina) {
-            if (m >= VOR_MAXV) return false;
+            if (m >= CAP) return false;
             out.x[m] = in.x[v]; out.y[m] = in.y[v]; out.tag[m] = in.tag[v];
             ++m;
         }
         if (ina != inb) {
-            if (m >= VOR_MAXV) return false;
+            if (m >= CAP) return false;
             const double t = sa / (sa - sb);
             out.x[m] = in.x[v] + t * (in.x[w] - in.x[v]);
             out.y[m] = in.y[v] + t * (in.y[w] - in.y[v]);
@@ -73,14 +78,16 @@ __device__ bool poly_clip(const Poly& in, Poly& out, double dx, double dy, int n
     return true;
 }
 
-__device__ __forceinline__ double poly_radius2(const Poly& p)
+template <int CAP>
+__device__ __forceinline__ double poly_radius2(const PolyT<CAP>& p)
 {
     double r2 = 0.0;
     for (int v = 0; v < p.nv; ++v) r2 = fmax(r2, p.x[v] * p.x[v] + p.y[v] * p.y[v]);
     return r2;
 }
 
-__device__ __forceinline__ bool poly_closed(const Poly& p)
+template <int CAP>
+__device__ __forceinline__ bool poly_closed(const PolyT<CAP>& p)
 {
     for (int v = 0; v < p.nv; ++v)
         if (p.tag[v] < 0) return false;
@@ -139,27 +146,39 @@ __global__ void __launch_bounds__(128) voronoi_kernel(const VorArgs a)
     }
 }
 
-// Unresolved molecules against every other molecule (any order: clipping commutes; a molecule farther
-// than twice the current farthest vertex cannot cut the current polygon, which contains the cell).
+// Unresolved molecules against every other molecule, in shells of doubling radius: within a shell the order
+// is arbitrary (clipping commutes; a molecule farther than twice the current farthest vertex cannot cut
+// the current polygon, which contains the cell), but going outwards shell by shell keeps the intermediate
+// polygons small -- clipping by a far-away row of molecules first would give a cell with one edge per
+// molecule of the row.  After a shell of outer radius R everything closer than R has been seen, so the cell
+// is final once its farthest vertex is within R / 2.
 __global__ void __launch_bounds__(64) voronoi_brute_kernel(const VorArgs a)
 {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= a.unresolved[0]) return;
     const int i = (int)a.unresolved[1 + u];
-    Poly buf[2];
+    PolyT<VOR_MAXV_BRUTE> buf[2];
     int cur = 0;
     const double b = 0.5 * fmin(a.lx, a.ly);  // beyond this a cell would meet its own periodic images
     poly_square(buf[0], b);
     double r2 = 2.0 * b * b;
     bool ok = true;
-    for (int j = 0; j < a.n && ok; ++j) {
-        if (j == i) continue;
-        double dx, dy;
-        min_image(a, i, j, dx, dy);
-        if (dx * dx + dy * dy >= 4.0 * r2) continue;
-        ok = poly_clip(buf[cur], buf[cur ^ 1], dx, dy, j);
-        cur ^= 1;
-        r2 = poly_radius2(buf[cur]);
+    double rin2 = 0.0, rout = a.rmax;
+    while (ok) {
+        const double rout2 = rout * rout;
+        for (int j = 0; j < a.n && ok; ++j) {
+            if (j == i) continue;
+            double dx, dy;
+            min_image(a, i, j, dx, dy);
+            const double d2 = dx * dx + dy * dy;
+            if (d2 < rin2 || d2 >= rout2 || d2 >= 4.0 * r2) continue;
+            ok = poly_clip(buf[cur], buf[cur ^ 1], dx, dy, j);
+            cur ^= 1;
+            r2 = poly_radius2(buf[cur]);
+        }
+        if (4.0 * r2 <= rout2 || rout2 >= 2.0 * b * b) break;
+        rin2 = rout2;
+        rout *= 2.0;
     }
     // a cell that still touches the starting square is bounded by the molecule's own periodic images:
     // not representable here (freud's buffer would not cover it either); reported as VOR_MISSING

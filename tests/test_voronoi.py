@@ -81,6 +81,23 @@ def test_cuda_voronoi_sparse_and_clustered_points():
 
 
 @pytest.mark.gpu
+def test_cuda_voronoi_void_strip():
+    """A lattice with its last rows missing (32 768 molecules on a 182 x 182 grid): the molecules along the
+    void are closed by far-away neighbours in the second kernel; rows of molecules at similar distance must
+    not blow up the intermediate cells."""
+    from sdanalysis_b200 import order
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    walk = SyntheticTrimer(32768, seed=3)
+    pos, _ = walk.frame()
+    counts = order.compute_voronoi_neighs(walk.box, pos)
+    assert counts.sum() == 6 * len(counts)
+    query = oorder.compute_voronoi_neighs(walk.box, pos, return_query=True, buff=20)
+    ok = ~_ambiguous(query, len(counts))
+    assert np.array_equal(counts[ok], query.nlist.neighbor_counts[ok])
+
+
+@pytest.mark.gpu
 def test_cuda_voronoi_synthetic_liquid_euler_relation():
     """Full-size property: 1 M molecules, the counts sum to 6 N (every vertex of a generic diagram has degree 3)."""
     from sdanalysis_b200 import order
