@@ -74,7 +74,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(gpu_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
         except OSError:
@@ -463,6 +463,9 @@ def run_gpu(args):
                   "kernels serialised; in the timed region dyn_step, struct and the overlap resolve of different origin groups overlap)",
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": _ncu_traffic("dyn_step_kernel", a_local * n),
+        "traffic_frac": (
+            (_ncu_traffic("dyn_step_kernel", a_local * n) or 0.0) / (dyn_ms * 1e-3) / 1e9 / peak if dyn_ms > 0 else None
+        ),  # DRAM bytes actually moved / time / peak: what the kernel really draws from HBM
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/ncu_traffic.json), "
                           "scaled by the updates of this launch",
         "algorithmic_bytes_per_update": bytes_per_update,
