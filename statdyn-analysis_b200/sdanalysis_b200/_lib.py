@@ -5,7 +5,7 @@ functions here raise, loudly.  ``torch`` is used only as the owner of device mem
 """
 
 import ctypes
-from ctypes import POINTER, c_double, c_float, c_int32, c_int64, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, c_double, c_float, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 from pathlib import Path
 
 LIB_NAME = "libsdb200.so"

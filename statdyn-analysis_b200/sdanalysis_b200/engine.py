@@ -429,9 +429,6 @@ class DynamicsEngine:
         self._sums_dev_ptr = [t.data_ptr() for t in self._sums_dev]
         self._partials_ptr = self._partials.data_ptr()
 
-    def _stream_ptr(self):
-        return _lib.stream_ptr(self.device)
-
     def _inc_args(self, inc_sets):
         """ctypes arguments (h_prev, h_flags, n_sets, d_ws) of the per-frame increments pass."""
         import ctypes
