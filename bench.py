@@ -162,7 +162,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 16))
+    workers = max(1, min(cores, 64))
     n_mols = args.molecules
     # bounded sample: every step is one frame of `workers` origins (of the 200) at full N
     steps, warmup = min(args.steps, 6), min(args.warmup, 1)
