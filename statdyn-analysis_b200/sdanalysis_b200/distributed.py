@@ -473,7 +473,8 @@ class ShardedDynamics:
                 return []
             if self._batch_host is None:
                 self._batch_host = torch.empty((self.world,) + tuple(self._batch_buf.shape), dtype=torch.float64, pin_memory=True)
-            self._batch_host[:, :count].copy_(self._rows_r0[parity][:, :count])
+            # the whole (small, contiguous) buffer: a strided slice would go through a staging copy
+            self._batch_host.copy_(self._rows_r0[parity])
             return self._assemble(meta, self._batch_host.numpy())
         send = self._batch_buf[:count]  # leading rows of a contiguous buffer: contiguous
         if self.rank == 0:
