@@ -119,13 +119,13 @@ class GSDTrajectory:
         used = np.flatnonzero(index["location"] == 0)
         index = index[: used[0]] if len(used) else index
         self._frames = {}
-        for e in index:
-            self._frames.setdefault(int(e["frame"]), {})[self._names[int(e["id"])]] = (
-                int(e["location"]),
-                int(e["N"]),
-                int(e["M"]),
-                int(e["type"]),
-            )
+        names = self._names
+        # column-wise .tolist(): per-element access to a structured array costs microseconds per field
+        for frame, name_id, loc, n, m, typ in zip(
+            index["frame"].tolist(), index["id"].tolist(), index["location"].tolist(), index["N"].tolist(),
+            index["M"].tolist(), index["type"].tolist(),
+        ):
+            self._frames.setdefault(frame, {})[names[name_id]] = (loc, n, m, typ)
         self._nframes = (max(self._frames) + 1) if self._frames else 0
 
     def __len__(self):
