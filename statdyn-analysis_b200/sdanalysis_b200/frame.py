@@ -53,6 +53,48 @@ class HoomdFrame(Frame):
         return self._num_mols
 
 
+class LammpsFrame(Frame):
+    """A frame of a ``.lammpstrj`` dump: a dict of per-atom float32 columns plus ``box`` (three lengths)
+    and ``timestep`` (reference ``frame.py:75-125``): no orientations (identity quaternions), 2D."""
+
+    def __init__(self, frame):
+        self.frame = frame
+
+    @property
+    def position(self):
+        return np.array([self.frame["x"], self.frame["y"], self.frame["z"]], dtype=np.float32).T
+
+    @property
+    def image(self):
+        return None
+
+    @property
+    def orientation(self):
+        orient = np.zeros((len(self), 4), dtype=np.float32)
+        orient[:, 0] = 1
+        return orient
+
+    @property
+    def timestep(self):
+        return self.frame["timestep"]
+
+    @property
+    def box(self):
+        box = np.zeros(6, dtype=np.float32)
+        for index, value in enumerate(self.frame["box"]):
+            if index > 5:
+                break
+            box[index] = value
+        return box
+
+    @property
+    def dimensions(self):
+        return 2
+
+    def __len__(self):
+        return len(self.frame["x"])
+
+
 class ArrayFrame(Frame):
     """A frame held in plain arrays (synthetic trajectories, tests)."""
 

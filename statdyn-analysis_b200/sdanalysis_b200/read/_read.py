@@ -22,6 +22,7 @@ from ..gsdio import open_gsd
 from ..molecules import Trimer
 from ..util import get_filename_vars
 from ._gsd import FileIterator, read_gsd_trajectory
+from ._lammps import parse_lammpstrj, read_lammps_trajectory
 
 logger = logging.getLogger(__name__)
 
@@ -187,8 +188,10 @@ def process_file(
             keyframe_interval=keyframe_interval,
             keyframe_max=keyframe_max,
         )
+    elif infile.suffix == ".lammpstrj":  # reference _read.py:121-122
+        file_iterator = read_lammps_trajectory(infile, steps_max)
     else:
-        raise ValueError(f"unsupported trajectory format {infile.suffix!r}: only .gsd is on the accelerated path")
+        raise ValueError(f"unsupported trajectory format {infile.suffix!r}")
 
     engine = process_frames(
         file_iterator,
@@ -219,8 +222,11 @@ def process_file(
 
 
 def open_trajectory(filename: Path, progressbar=None, frame_interval=1) -> Iterator[Frame]:
-    """Frames of a GSD trajectory, skipping corrupt ones (reference ``_read.py:198-241``)."""
+    """Frames of a GSD (skipping corrupt ones) or ``.lammpstrj`` trajectory (reference ``_read.py:198-241``)."""
     filename = Path(filename)
+    if filename.suffix == ".lammpstrj":
+        yield from parse_lammpstrj(filename)
+        return
     if filename.suffix != ".gsd":
         raise ValueError(f"unsupported trajectory format {filename.suffix!r}")
     with open_gsd(filename) as trj:

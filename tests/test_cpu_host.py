@@ -132,7 +132,7 @@ def test_open_trajectory(gsd_trajectory):
     frames = list(open_trajectory(gsd_trajectory, frame_interval=50))
     assert [f.timestep for f in frames][:3] == [0, 50, 100]
     with pytest.raises(ValueError):
-        next(open_trajectory("x.lammpstrj"))
+        next(open_trajectory("x.xyz"))
 
 
 def test_write_cache(tmp_path):
@@ -211,3 +211,43 @@ def test_molecule2particles_reproduces_the_reference_pairing():
         assert np.allclose(out[row], sites[row // n] + position[row // 3], atol=1e-6)
     with pytest.raises(ValueError):
         molecule2particles(position, (1, 0, 0, 0), mol.positions)
+
+
+def _write_lammpstrj(path, steps, n=7, seed=0):
+    rng = np.random.default_rng(seed)
+    frames = []
+    with open(path, "w") as dst:
+        for step in steps:
+            pos = rng.uniform(-5, 5, (n, 3)).astype(np.float32)
+            order = rng.permutation(n)  # rows in arbitrary order: the id column decides the slot
+            dst.write(f"ITEM: TIMESTEP\n{step}\nITEM: NUMBER OF ATOMS\n{n}\n")
+            dst.write("ITEM: BOX BOUNDS pp pp pp\n-5.0 5.0\n-6.0 6.0\n-0.5 0.5\n")
+            dst.write("ITEM: ATOMS id type x y z\n")
+            for j in order:
+                dst.write(f"{j + 1} 1 {pos[j, 0]:.6f} {pos[j, 1]:.6f} {pos[j, 2]:.6f}\n")
+            frames.append(pos)
+    return frames
+
+
+def test_lammps_trajectory(tmp_path):
+    """reference read/_lammps.py:28-95 and frame.py:75-125: rows placed by id, box from the bounds, identity
+    orientations, one time-origin, steps_max cut-off; open_trajectory dispatches on the suffix."""
+    from sdanalysis_b200.read import open_trajectory, parse_lammpstrj, read_lammps_trajectory
+
+    path = tmp_path / "short.lammpstrj"
+    written = _write_lammpstrj(path, [0, 10, 20, 30])
+    frames = list(parse_lammpstrj(path))
+    assert [f.timestep for f in frames] == [0, 10, 20, 30]
+    for frame, pos in zip(frames, written):
+        assert frame.position.dtype == np.float32 and frame.position.shape == (7, 3)
+        np.testing.assert_allclose(frame.position, pos, atol=1e-6)
+        np.testing.assert_array_equal(frame.box, np.array([10, 12, 1, 0, 0, 0], dtype=np.float32))
+        assert frame.orientation.shape == (7, 4) and np.all(frame.orientation[:, 0] == 1) and len(frame) == 7
+        assert frame.dimensions == 2 and frame.image is None
+    pairs = list(read_lammps_trajectory(path, steps_max=20))
+    assert [f.timestep for _, f in pairs] == [0, 10, 20] and all(ix == [0] for ix, _ in pairs)
+    assert [f.timestep for f in open_trajectory(path)] == [0, 10, 20, 30]
+    bad = tmp_path / "bad.lammpstrj"
+    bad.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF MOLECULES\n3\n")
+    with pytest.raises(RuntimeError):
+        list(parse_lammpstrj(bad))
