@@ -1,5 +1,7 @@
-"""Run an analysis on a trajectory (reference ``run_analysis.py:20-42``)."""
+"""Per-frame order analysis of a whole trajectory (host loop around ``order.orientational_order``;
+counterpart of reference ``run_analysis.py:20-42``)."""
 
+import csv
 import logging
 
 import numpy as np
@@ -9,21 +11,27 @@ from .order import orientational_order
 
 logger = logging.getLogger(__name__)
 
+ORDERED_ABOVE = 0.9  # a particle counts as orientationally ordered above this value
+
+
+def _ordered_fractions(trajectory):
+    """``(timestep, fraction of ordered particles)`` of every readable frame.  Like the reference this
+    looks at every particle record of a snapshot (``snapshot.particles``), not only at molecule centres."""
+    for number in range(len(trajectory)):
+        try:
+            snapshot = trajectory[number]
+        except RuntimeError:
+            logger.info("Frame %s corrupted, continuing...", number)
+            continue
+        values = orientational_order(box=snapshot.box, position=snapshot._position, orientation=snapshot._orientation)
+        yield snapshot.step, np.count_nonzero(values > ORDERED_ABOVE) / len(values)
+
 
 def order(infile, outfile):
-    """Orientational order of each frame of a trajectory: writes ``Timestep, OrientOrder`` rows, the
-    second column being the fraction of particles with an order parameter above 0.9.  Like the reference
-    it works on every particle record of the snapshot (``snapshot.particles.position``), not on the
-    molecule centres, and skips frames that cannot be read."""
-    with open_gsd(infile) as trajectory, open(outfile, "w") as dst:
-        print("Timestep, OrientOrder", file=dst)
-        for index in range(len(trajectory)):
-            try:
-                snapshot = trajectory[index]
-            except RuntimeError:
-                logger.info("Frame %s corrupted, continuing...", index)
-                continue
-            orient_order = orientational_order(
-                box=snapshot.box, position=snapshot._position, orientation=snapshot._orientation
-            )
-            print(snapshot.step, ",", np.sum(orient_order > 0.9) / len(orient_order), file=dst)
+    """Write ``Timestep, OrientOrder`` rows -- the fraction of particles whose orientational order
+    parameter exceeds 0.9 -- for each frame of the GSD trajectory ``infile``."""
+    with open_gsd(infile) as trajectory, open(outfile, "w", newline="") as dst:
+        writer = csv.writer(dst, delimiter=" ", lineterminator="\n")
+        dst.write("Timestep, OrientOrder\n")
+        for step, fraction in _ordered_fractions(trajectory):
+            writer.writerow([step, ",", fraction])  # "step , fraction": the reference's print(step, ",", value)
