@@ -87,6 +87,7 @@ class ShardedDynamics:
         self._last_active, self._last_local = None, None
         self.stalls = [] if os.environ.get("SDB_SHARD_PROFILE") == "1" else None
         self.exchange_times = []
+        self.exchange_note = ""
 
         if exchange is None:
             exchange = os.environ.get("SDB_SHARD_EXCHANGE", "multicast" if self._cuda and self.world > 1 else "collective")
@@ -96,9 +97,18 @@ class ShardedDynamics:
             try:
                 self._setup_symmetric()
             except Exception as exc:  # no symmetric memory on this system: collectives still work
-                import warnings
+                # LOUD: the data plane changes (NCCL broadcast instead of multicast stores); callers that
+                # report the exchange (bench.py's config.parallelism) read self.exchange / exchange_note
+                import sys
 
-                warnings.warn(f"symmetric-memory frame exchange unavailable ({exc}); using collectives")
+                self.exchange_note = f"multicast unavailable: {type(exc).__name__}: {exc}"
+                print(
+                    f"[sdanalysis_b200 rank {self.rank}] WARNING: symmetric-memory multicast frame exchange unavailable "
+                    f"({type(exc).__name__}: {exc}); falling back to torch.distributed.broadcast",
+                    file=sys.stderr, flush=True,
+                )
+                if os.environ.get("SDB_SHARD_STRICT", "0") == "1":
+                    raise
                 self.exchange = "collective"
         if self.exchange == "collective":
             self.frames = [
@@ -203,12 +213,18 @@ class ShardedDynamics:
             and pos_t.is_contiguous() and quat_t.is_contiguous()
             and (hi - lo) % 4 == 0 and pos_t.data_ptr() % 16 == 0 and quat_t.data_ptr() % 16 == 0
         )
-        if not direct and pos_t.shape[0] != self.n:
+        own_rows = pos_t.shape[0] == hi - lo and quat_t.shape[0] == hi - lo and self.world > 1
+        if not direct and not own_rows and pos_t.shape[0] != self.n:
+            # every rank reaches the barrier below or none does: a rank that cannot take part says so
+            # BEFORE anybody waits (all ranks evaluate the same shape test on their own argument)
             raise ValueError("post_frame_sliced needs the whole frame in host memory or this rank's rows on the device")
+        # the multicast copy moves whole 16-byte words: the last rank's rows (n need not be a multiple of
+        # 4) are staged in a buffer padded to 4 rows; the pad lands in the slot's own padding before qoff
+        rows_pad = (hi - lo + 3) // 4 * 4
         if not direct and self._slice_stage is None:
             self._slice_stage = [
-                (torch.empty((hi - lo, 3), dtype=torch.float32, device=self.device),
-                 torch.empty((hi - lo, 4), dtype=torch.float32, device=self.device))
+                (torch.zeros((rows_pad, 3), dtype=torch.float32, device=self.device),
+                 torch.zeros((rows_pad, 4), dtype=torch.float32, device=self.device))
                 for _ in range(2)
             ]
             self._slice_free = [None, None]
@@ -232,9 +248,16 @@ class ShardedDynamics:
                 free = self._slice_free[self._slice_i]
                 if free is not None:
                     self._side.wait_event(free)
-                spos.copy_(pos_t[lo:hi], non_blocking=True)
-                squat.copy_(quat_t[lo:hi], non_blocking=True)
-            _lib.check(lib.sdb_multicast_copy(spos.data_ptr(), base + 12 * lo, 12 * (hi - lo), self._mc_blocks, self._side.cuda_stream))
+                if own_rows:  # this rank's rows, but not 16-byte tileable (n % 4 != 0 on the last rank): staged
+                    if pos_t.is_cuda:
+                        self._side.wait_event(_lib.current_stream(self.device).record_event())
+                    spos[: hi - lo].copy_(pos_t, non_blocking=True)
+                    squat[: hi - lo].copy_(quat_t, non_blocking=True)
+                else:
+                    spos[: hi - lo].copy_(pos_t[lo:hi], non_blocking=True)
+                    squat[: hi - lo].copy_(quat_t[lo:hi], non_blocking=True)
+            pos_bytes = (12 * (hi - lo) + 15) // 16 * 16  # <= 4 * qoff - 12 * lo: stays inside the position part
+            _lib.check(lib.sdb_multicast_copy(spos.data_ptr(), base + 12 * lo, pos_bytes, self._mc_blocks, self._side.cuda_stream))
             _lib.check(lib.sdb_multicast_copy(squat.data_ptr(), base + 4 * self.qoff + 16 * lo, 16 * (hi - lo), self._mc_blocks, self._side.cuda_stream))
             if not direct:
                 self._slice_free[self._slice_i] = self._side.record_event()

@@ -245,6 +245,16 @@ class TrackedMotion:
             self._to_general()
         result = None
         if self._engine is not None:
+            if not want_sums and orientation is not None and self.previous_orientation is not None:
+                # rowan.to_euler rejects quotients that are not unit quaternions (reference _util.py:151-153
+                # raises ValueError out of TrackedMotion.add / Relaxations.add).  With sums the device counts
+                # them (SDB_S_BADQUAT, checked when the row is read); without sums nothing is read back, so
+                # the per-object API validates here, before any state changes.
+                n_cur = np.linalg.norm(np.asarray(orientation, dtype=np.float64), axis=1)
+                n_prev = np.linalg.norm(np.asarray(self.previous_orientation, dtype=np.float64), axis=1)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    if not np.allclose(n_cur / n_prev, 1.0):
+                        raise ValueError("Arguments must be unit quaternions")
             ts = self.timestep if timestep is None else timestep
             result = self._engine.step(ts, position, orientation, [0], want_sums=want_sums)
         else:

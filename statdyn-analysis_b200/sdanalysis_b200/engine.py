@@ -544,6 +544,11 @@ class DynamicsEngine:
     def set_trackers(self, definitions):
         """Replace the tracker set; every origin's passage state starts afresh while its accumulated
         motion is kept (``Relaxations.set_mol_relax``, ``relaxations.py:108-133``)."""
+        # a cached steady-state plan holds the per-origin records (previous sample, update count,
+        # largest time difference) of the frames stepped since it was made: bring them up to date
+        # before dropping it, or the next step would group origins by a released previous sample
+        if getattr(self, "_plan", None) is not None:
+            self._flush_plan()
         self.trackers = build_trackers(definitions) if definitions else []
         p = self.params
         p.n_trackers = len(self.trackers)
@@ -619,7 +624,8 @@ class DynamicsEngine:
                 and not zero_step
                 and plan["active"] == active
                 and plan["has_quat"] == (quat is not None)
-                and int(timestep) >= plan["timestep"]
+                and int(timestep) > plan["timestep"]  # time moves forward: no origin needs ORIGIN_LITERAL
+                and plan["monotone"]
                 and chunk is None
             ):
                 # steady state of the dense schedule: same origins, all sharing the previous frame --
@@ -834,6 +840,9 @@ class DynamicsEngine:
                             "prev": new_prev,
                             "has_quat": quat is not None,
                             "timestep": int(timestep),
+                            # every origin's largest time difference so far is the current one: from here
+                            # on a later timestep is later for every origin (relaxations.py:215-218)
+                            "monotone": all(t >= org.max_timediff for org, t in zip(ordered, timediffs)),
                             "steps": 0,
                             "ov_steps": 0,
                         }

@@ -110,6 +110,7 @@ def process_frames(
     ``(indexes, frame)`` pairs.  Rows are passed to ``sink(row)``; returns the engine (per-origin
     passage times stay on the device until ``engine.summary(key)`` is called)."""
     engine = None
+    box_warned = False
     pending = deque()
 
     def drain(limit):
@@ -143,6 +144,17 @@ def process_frames(
                 ring_depth=pipeline_depth + 1,
                 compute_isf=scattering_function,
             )
+        elif not box_warned and not np.array_equal(np.asarray(frame.box, dtype=np.float32)[:2], engine.box[:2]):
+            # The reference builds every keyframe's Dynamics / Relaxations with the box of that keyframe's
+            # own first frame (_read.py:135-141); this engine wraps every origin with the box of the first
+            # frame of the file.  On constant-volume trajectories the two are the same; on NPT files the
+            # minimum-image step of later origins uses a slightly different L (results differ only for
+            # steps within |dL| of L/2).  Documented deviation.
+            logger.warning(
+                "box changes along the trajectory (%s -> %s): all origins are wrapped with the first frame's box",
+                engine.box[:2], np.asarray(frame.box)[:2],
+            )
+            box_warned = True
         try:
             pending.append(engine.step(frame.timestep, frame.position, frame.orientation, list(indexes)))
         except (ValueError, RuntimeError) as e:

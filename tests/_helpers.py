@@ -11,15 +11,26 @@ RATIO_KEYS = ("alpha", "alpha_rot", "gamma")  # value = ratio - 1: compared on t
 RTOL = 1e-5  # BASELINE.json north_star: floating-point dynamics quantities within rtol 1e-5
 
 
-def oracle_process(frames, wave_number=WAVE_NUMBER, ulps=2, scattering_function=False):
+def oracle_process(frames, wave_number=WAVE_NUMBER, ulps=1, scattering_function=False, only=None):
     """frames: iterable of (indexes, frame).  Returns (rows, summaries, near) where ``near[key]`` is
     a dict tracker-name -> bool mask of molecules that ever came within ``ulps`` ulp of a cutoff of
-    that tracker (those are excluded from the bit-exact comparison, as north_star allows)."""
+    that tracker (those are excluded from the bit-exact comparison, as north_star allows: "excluding
+    pairs within 1 ulp of the cutoff").  ``only``: restrict the oracle to these origins (the others are
+    independent of them: subsampling origins at the sizes where the oracle needs 0.1 - 20 s per pair); a dict
+    ``origin -> number of frames`` also bounds how long an origin is followed (None: to the end)."""
     keyframes = {}
     rows = []
     near = {}
+    done = {}
     for indexes, frame in frames:
         for index in indexes:
+            if only is not None:
+                if index not in only:
+                    continue
+                budget = only[index] if isinstance(only, dict) else None
+                if budget is not None and done.get(index, 0) >= budget:
+                    continue  # rows of the first `budget` frames of this origin only
+                done[index] = done.get(index, 0) + 1
             if index not in keyframes:
                 keyframes[index] = (
                     odyn.Dynamics(frame.timestep, frame.box, frame.position, frame.orientation, "trimer", wave_number),
@@ -32,16 +43,25 @@ def oracle_process(frames, wave_number=WAVE_NUMBER, ulps=2, scattering_function=
             row["keyframe"] = index
             row["_tie"] = _overlap_tie(dyn)
             rows.append(row)
-            disp = np.linalg.norm(relax.motion.delta_translation, axis=1)
-            rot = np.linalg.norm(relax.motion.delta_rotation, axis=1)
-            for name, func in relax.mol_relax.items():
-                value = rot if func.relaxation_type == "rotation" else disp
-                cuts = [func.threshold] + ([func._irreversibility] if hasattr(func, "_irreversibility") else [])
-                for cut in cuts:
-                    c = np.float32(cut)
-                    near[index][name] |= np.abs(value - c) <= ulps * np.spacing(c)
+            near[index] = near_cutoff(relax, near[index], ulps)
     summaries = {index: relax.summary() for index, (_, relax) in keyframes.items()}
     return rows, summaries, near, keyframes
+
+
+def near_cutoff(relax, near=None, ulps=1):
+    """Accumulate, per tracker of the oracle ``relax``, the mask of molecules whose current distance lies
+    within ``ulps`` ulp (f32) of a cutoff of that tracker."""
+    if near is None:
+        near = {name: np.zeros(relax._num_elements, dtype=bool) for name in relax.mol_relax}
+    disp = np.linalg.norm(relax.motion.delta_translation, axis=1)
+    rot = np.linalg.norm(relax.motion.delta_rotation, axis=1)
+    for name, func in relax.mol_relax.items():
+        value = rot if func.relaxation_type == "rotation" else disp
+        cuts = [func.threshold] + ([func._irreversibility] if hasattr(func, "_irreversibility") else [])
+        for cut in cuts:
+            c = np.float32(cut)
+            near[name] |= np.abs(value - c) <= ulps * np.spacing(c)
+    return near
 
 
 def _overlap_tie(dyn):

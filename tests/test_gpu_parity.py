@@ -1,14 +1,14 @@
 """Parity of the CUDA hot path with the CPU oracle on seeded synthetic Trimer trajectories.
 
 All tests call through the C-ABI library (via the Python host layer).  Bars (BASELINE.json
-north_star): relaxation times bit-exact except molecules within 2 ulp of a cutoff, displacement
+north_star): relaxation times bit-exact except molecules within 1 ulp of a cutoff, displacement
 accumulators bit-exact, floating-point quantities within rtol 1e-5.
 """
 
 import numpy as np
 import pytest
 
-from _helpers import WAVE_NUMBER, compare_rows, oracle_process
+from _helpers import WAVE_NUMBER, compare_rows, near_cutoff, oracle_process
 
 pytestmark = pytest.mark.gpu
 
@@ -94,6 +94,7 @@ def test_per_object_api_matches_oracle(golden_dir):
     relax = dynamics.Relaxations(0, box, pos0, quat0, molecule=Trimer(), wave_number=WAVE_NUMBER)
     ref_dyn = odyn.Dynamics(0, box, pos0, quat0, "trimer", WAVE_NUMBER)
     ref_relax = odyn.Relaxations(0, box, pos0, quat0, "trimer", wave_number=WAVE_NUMBER)
+    near = None
     for step in range(1, 9):
         xy += rng.normal(0, 0.15, xy.shape)
         theta += rng.normal(0, 0.3, n)
@@ -106,6 +107,7 @@ def test_per_object_api_matches_oracle(golden_dir):
         want = ref_dyn.compute_all(step * 10, pos, quat)
         relax.add(step * 10, pos, quat)
         ref_relax.add(step * 10, pos, quat)
+        near = near_cutoff(ref_relax, near)
         got["keyframe"] = want["keyframe"] = 0
         want["_tie"] = False
         compare_rows([got], [want], n)
@@ -115,7 +117,10 @@ def test_per_object_api_matches_oracle(golden_dir):
     assert np.array_equal(dyn.compute_displacement(), ref_dyn.compute_displacement())
     summary, ref_summary = relax.summary(), ref_relax.summary()
     for name, want in ref_summary.items():
-        assert np.mean(summary[name].to_numpy() != want) <= 2 / n, name
+        # bit-exact except molecules that came within 1 ulp of a cutoff of that tracker (north_star)
+        mask = ~near[name]
+        assert np.array_equal(summary[name].to_numpy()[mask], want[mask]), name
+        assert (~mask).sum() <= 2, name
     assert sorted(summary.columns) == sorted(ref_summary)
 
 
