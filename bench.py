@@ -236,10 +236,10 @@ def run_gpu(args):
         engine = make_engine()
         sharded = None
         if world > 1:
-            def step_fn(ts, pos, quat, keys):
-                return engine.step(ts, pos, quat, keys, to_host=False)
+            def step_fn(ts, pos, quat, keys, rows_out=0):
+                return engine.step(ts, pos, quat, keys, to_host=False, rows_out=rows_out)
 
-            sharded = ShardedDynamics(n, step_fn, max_local=len(local_keys) + 1, device=device, batch=n_frames + 1)
+            sharded = ShardedDynamics(n, step_fn, max_local=len(local_keys) + 1, device=device, batch=n_frames + 1, direct_rows=True)
         # origin creation: origin k starts at frame k (linear schedule, keyframe_interval = 1)
         timestep = 0
         # frames: a random walk generated on rank 0's GPU
@@ -258,8 +258,8 @@ def run_gpu(args):
             else:
                 pos, quat = walk.frame()
                 engine.step(timestep, pos, quat, active, want_sums=False)
-            walk.advance(1)
-            timestep += 1
+            walk.advance(args.age_stride)
+            timestep += args.age_stride
         torch.cuda.synchronize()
         # the frames of the measured steps
         frames = []
@@ -537,6 +537,7 @@ def main():
     ap.add_argument("--molecules", type=int, default=N_MOLS)
     ap.add_argument("--origins", type=int, default=N_ORIGINS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--age-stride", type=int, default=1, help="timesteps between the creation of consecutive origins")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -324,6 +324,119 @@ int sdb_profile_collect(double* h_ms, int64_t* h_steps, int64_t* h_origin_steps)
  * (torch symmetric memory: handle.multicast_ptr + offset).  blocks <= 0 picks a default grid. */
 int sdb_multicast_copy(const void* d_src, void* d_multicast_dst, size_t bytes, int32_t blocks, void* stream);
 
+/* ==== native engine: the whole hot loop behind one call per frame =====================================
+ * Replaces the body of reference read/_read.py:128-168 *including its bookkeeping*: the dict of per-keyframe
+ * (Dynamics, Relaxations) objects (_read.py:117,135-141), TrackedMotion.previous_* (_util.py:155-156, here
+ * reference-counted planar frames), the grouping of the active keyframes by previous sample, the descriptor
+ * rings, the staging of a host frame through pinned memory (frame.py:162-184 -> device) and the asynchronous
+ * download of the result rows.  A host in any language calls
+ *     sdb_engine_step(engine, &frame, stream)  ->  ticket          (asynchronous, ~10 CUDA calls inside)
+ *     sdb_engine_wait(engine, ticket, rows, ...)                   (blocks until that frame's rows are on the host)
+ * once per frame with HOST or DEVICE buffers; no torch types, no Python between the kernels.
+ * The engine owns its device memory (cudaMalloc): per-origin state, previous-sample pool, rings, workspaces.
+ * One engine = one device = one host thread at a time. */
+typedef struct SdbEngine SdbEngine;
+
+#define SDB_MEM_DEVICE 0 /* frame pointers are device pointers (16-byte aligned), used in place */
+#define SDB_MEM_HOST 1   /* pageable host memory (numpy array, memory-mapped trajectory file): copied into the
+                            engine's pinned ring by a small pool of host threads, then uploaded on a copy stream */
+#define SDB_MEM_PINNED 2 /* page-locked host memory: uploaded on the copy stream directly; the caller keeps it
+                            unchanged until the step has completed */
+
+#define SDB_ENGINE_DRY 1u        /* test hook: no CUDA calls at all (bookkeeping and descriptors only) */
+#define SDB_ENGINE_NO_PREDICT 2u /* sampled overlap brackets every frame (no SDB_ORIGIN_HISTORY) */
+#define SDB_ENGINE_NO_INCREMENTS 4u /* never run the per-frame increments pass */
+
+typedef struct {
+    int32_t n;                /* molecules */
+    float box[6];             /* Lx, Ly, Lz, xy, xz, yz of frame.py:190-196 (2D: Lz, xz, yz unused) */
+    double wave_number;       /* <= 0: none (com_struct, struct stay unset: dynamics.py:369-372,385-390) */
+    float com_cut_lt;         /* disp2 < com_cut_lt <=> |dr| < pi / (2 wave_number) in f32 (see SdbDynParams) */
+    int32_t n_trackers;       /* pre-digested trackers (see SdbTracker); 0: Dynamics only */
+    SdbTracker trackers[SDB_MAX_TRACKERS];
+    int32_t compute_sums;     /* 0: Relaxations.add only */
+    int32_t overlap_k;        /* int(0.1 N) of dynamics.py:441; 0: no `overlap` */
+    int32_t n_sites;          /* sites of the molecule for `struct` (molecules.py:136-152); 0: no `struct` */
+    float sites_xy[16];
+    int32_t struct_mode;      /* 0 reference pairing, 1 physical (see sdb_struct) */
+    int32_t compute_isf;      /* != 0: scattering_function column (dynamics.py:364-366) */
+    int32_t angular_resolution;
+    int32_t ring_depth;       /* frames in flight (>= 2) */
+    int32_t inc_max_per_segment; /* <= 0: default 40 (see sdb_dyn_increments) */
+    int32_t chunk;            /* > 0: fixed number of origins per segment (tests); 0: automatic */
+    uint32_t flags;           /* SDB_ENGINE_* */
+} SdbEngineConfig;
+
+#define SDB_FRAME_NO_SUMS 1u     /* Relaxations.add only for this frame (no rows) */
+#define SDB_FRAME_ZERO_STEP 2u   /* no new sample: recompute the rows of the current state (pos/quat ignored) */
+#define SDB_FRAME_ROWS_DEVICE 4u /* rows stay on the device (d_rows_out and/or sdb_engine_device_rows) */
+
+typedef struct {
+    int64_t timestep;         /* frame.timestep */
+    const float* pos;         /* float[n][3] */
+    const float* quat;        /* float[n][4] (w, x, y, z) or NULL */
+    int32_t where;            /* SDB_MEM_* */
+    uint32_t flags;           /* SDB_FRAME_* */
+    const int64_t* keys;      /* the active keyframes (`indexes` of read/_read.py:128); unknown keys are
+                                 created at this frame (Dynamics.from_frame, _read.py:135-141) */
+    int32_t n_keys;
+    int32_t reserved;
+    double* d_rows_out;       /* optional DEVICE destination of the n_keys x SDB_NSUM rows, in `keys` order
+                                 (may be peer memory of another GPU: multi-GPU row collection) */
+} SdbFrame;
+
+int sdb_engine_create(const SdbEngineConfig* config, SdbEngine** out);
+void sdb_engine_destroy(SdbEngine* engine);
+/* Relaxations.set_mol_relax (relaxations.py:108-133): new tracker set, every origin's passage state afresh. */
+int sdb_engine_set_trackers(SdbEngine* engine, const SdbTracker* trackers, int32_t n_trackers);
+/* One frame.  Returns a ticket >= 0, or a negative SDB_E* code. */
+int64_t sdb_engine_step(SdbEngine* engine, const SdbFrame* frame, void* stream);
+/* Wait for a step and copy its rows out, in the order of the step's `keys`: h_rows double[n_keys][SDB_NSUM]
+ * (NULL for steps without host rows), h_timediffs int64[n_keys], h_isf double[n_keys] (any may be NULL).
+ * A ticket stays valid for ring_depth - 1 further steps (SDB_EINVAL afterwards). */
+int sdb_engine_wait(SdbEngine* engine, int64_t ticket, double* h_rows, int64_t* h_timediffs, double* h_isf);
+/* Device copy of the rows of a step (valid like the ticket), in the engine's internal origin order;
+ * h_perm int32[n_keys] (may be NULL): position of keys[i] in that order. */
+int sdb_engine_device_rows(SdbEngine* engine, int64_t ticket, double** d_rows, int32_t* h_perm);
+/* A whole batch of frames in one call (the frame loop itself in native code): steps frames[0..n_frames) in
+ * order, keeping ring_depth - 1 of them in flight, and writes the rows of frame f at
+ * h_rows + SDB_NSUM * (sum of n_keys of the frames before f), likewise h_timediffs / h_isf (may be NULL).
+ * Frames flagged NO_SUMS or ROWS_DEVICE leave their rows untouched. */
+int sdb_engine_run(SdbEngine* engine, const SdbFrame* frames, int32_t n_frames, double* h_rows, int64_t* h_timediffs,
+                   double* h_isf, void* stream);
+/* Drop a keyframe and recycle its state. */
+int sdb_engine_drop(SdbEngine* engine, int64_t key);
+
+typedef struct {
+    int64_t timestep;         /* of the origin's first frame */
+    int64_t updates;          /* samples added since (0: just created) */
+    int64_t max_timediff;
+    float* d_delta;           /* float[3][stride] (+ SDB_HISTORY_WORDS words) */
+    uint8_t* d_flags;         /* uint8[stride] or NULL */
+    uint32_t* d_status;       /* uint32[n_trackers][stride] or NULL */
+    const float* d_prev;      /* float[4][stride] planes of the previous sample */
+    int32_t prev_has_orientation;
+    int32_t stride;
+} SdbOriginInfo;
+int sdb_engine_origin(SdbEngine* engine, int64_t key, SdbOriginInfo* out); /* SDB_EINVAL: unknown key */
+int32_t sdb_engine_num_origins(SdbEngine* engine);
+int32_t sdb_engine_keys(SdbEngine* engine, int64_t* h_keys, int32_t capacity); /* in creation order */
+
+typedef struct {
+    int64_t frames, updates;          /* frames stepped, molecule x origin updates performed */
+    int64_t h2d_bytes, d2h_bytes;     /* of the last step */
+    int64_t pool_frames, pool_free;   /* previous-sample pool */
+    int64_t device_bytes;             /* device memory owned by the engine */
+    int32_t last_segments, last_inc_sets, last_step_flags, capacity;
+    void* d_ov_ws;                    /* overlap workspace (for sdb_overlap_stats) */
+    void* d_inc_ws;
+} SdbEngineStats;
+int sdb_engine_stats(SdbEngine* engine, SdbEngineStats* out);
+/* Test hook (dry engines): the descriptor block of the last step -- n_origins SdbOrigin records followed, at
+ * byte *segments_offset, by n_segments SdbSegment records.  Returns the number of bytes copied. */
+int32_t sdb_engine_last_descriptors(SdbEngine* engine, void* h_out, int32_t capacity, int32_t* n_origins,
+                                    int32_t* n_segments, int32_t* segments_offset);
+
 #ifdef __cplusplus
 }
 #endif

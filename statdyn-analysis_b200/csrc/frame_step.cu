@@ -110,6 +110,13 @@ extern "C" int sdb_profile_collect(double* h_ms, int64_t* h_steps, int64_t* h_or
     return SDB_OK;
 }
 
+int sdb_frame_step_impl(const SdbDynParams* h_params, const float* d_pos, const float* d_quat, float* d_cur_compact,
+                        const void* h_desc, void* d_desc, int32_t desc_bytes, int32_t segments_offset, int32_t n_origins,
+                        int32_t n_segments, int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
+                        void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy, int32_t n_sites,
+                        double struct_dist, int32_t struct_mode, const void* const* h_inc_prev, const uint32_t* h_inc_flags,
+                        int32_t inc_sets, void* d_inc_ws, int32_t step_flags, void* stream);
+
 extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
                               float* d_cur_compact, const void* h_desc, void* d_desc, int32_t desc_bytes,
                               int32_t segments_offset, int32_t n_origins, int32_t n_segments,
@@ -117,6 +124,20 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
                               void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy,
                               int32_t n_sites, double struct_dist, int32_t struct_mode, const void* const* h_inc_prev,
                               const uint32_t* h_inc_flags, int32_t inc_sets, void* d_inc_ws, int32_t step_flags, void* stream)
+{
+    return sdb_frame_step_impl(h_params, d_pos, d_quat, d_cur_compact, h_desc, d_desc, desc_bytes, segments_offset, n_origins,
+                               n_segments, max_segment_count, d_partials, d_sums, h_sums, d_ov_ws, ov_ws_origins, overlap_k,
+                               h_sites_xy, n_sites, struct_dist, struct_mode, h_inc_prev, h_inc_flags, inc_sets, d_inc_ws,
+                               step_flags, stream);
+}
+
+// (the native engine of csrc/engine.cu calls this directly)
+int sdb_frame_step_impl(const SdbDynParams* h_params, const float* d_pos, const float* d_quat, float* d_cur_compact,
+                        const void* h_desc, void* d_desc, int32_t desc_bytes, int32_t segments_offset, int32_t n_origins,
+                        int32_t n_segments, int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
+                        void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy, int32_t n_sites,
+                        double struct_dist, int32_t struct_mode, const void* const* h_inc_prev, const uint32_t* h_inc_flags,
+                        int32_t inc_sets, void* d_inc_ws, int32_t step_flags, void* stream)
 {
     if (!h_params || !h_desc || !d_desc || desc_bytes <= 0 || segments_offset <= 0 || segments_offset >= desc_bytes) {
         sdb_set_error("sdb_frame_step: bad descriptor arguments");

@@ -61,6 +61,19 @@ EXPORTS = (
     "sdb_launch_count",
     "sdb_test_rot_increment",
     "sdb_test_wrap2d",
+    "sdb_engine_create",
+    "sdb_engine_destroy",
+    "sdb_engine_set_trackers",
+    "sdb_engine_step",
+    "sdb_engine_wait",
+    "sdb_engine_device_rows",
+    "sdb_engine_run",
+    "sdb_engine_drop",
+    "sdb_engine_origin",
+    "sdb_engine_num_origins",
+    "sdb_engine_keys",
+    "sdb_engine_stats",
+    "sdb_engine_last_descriptors",
 )
 
 
@@ -106,6 +119,80 @@ class SdbSegment(ctypes.Structure):
         ("count", c_int32),
         ("flags", c_uint32),
         ("reserved", c_uint32),
+    ]
+
+
+# ---- native engine (csrc/engine.cu) -------------------------------------------------------------------
+SDB_MEM_DEVICE, SDB_MEM_HOST, SDB_MEM_PINNED = 0, 1, 2
+SDB_ENGINE_DRY, SDB_ENGINE_NO_PREDICT, SDB_ENGINE_NO_INCREMENTS = 1, 2, 4
+SDB_FRAME_NO_SUMS, SDB_FRAME_ZERO_STEP, SDB_FRAME_ROWS_DEVICE = 1, 2, 4
+
+
+class SdbEngineConfig(ctypes.Structure):
+    _fields_ = [
+        ("n", c_int32),
+        ("box", c_float * 6),
+        ("wave_number", c_double),
+        ("com_cut_lt", c_float),
+        ("n_trackers", c_int32),
+        ("trackers", SdbTracker * SDB_MAX_TRACKERS),
+        ("compute_sums", c_int32),
+        ("overlap_k", c_int32),
+        ("n_sites", c_int32),
+        ("sites_xy", c_float * 16),
+        ("struct_mode", c_int32),
+        ("compute_isf", c_int32),
+        ("angular_resolution", c_int32),
+        ("ring_depth", c_int32),
+        ("inc_max_per_segment", c_int32),
+        ("chunk", c_int32),
+        ("flags", c_uint32),
+    ]
+
+
+class SdbFrame(ctypes.Structure):
+    _fields_ = [
+        ("timestep", c_int64),
+        ("pos", c_void_p),
+        ("quat", c_void_p),
+        ("where", c_int32),
+        ("flags", c_uint32),
+        ("keys", c_void_p),
+        ("n_keys", c_int32),
+        ("reserved", c_int32),
+        ("d_rows_out", c_void_p),
+    ]
+
+
+class SdbOriginInfo(ctypes.Structure):
+    _fields_ = [
+        ("timestep", c_int64),
+        ("updates", c_int64),
+        ("max_timediff", c_int64),
+        ("d_delta", c_void_p),
+        ("d_flags", c_void_p),
+        ("d_status", c_void_p),
+        ("d_prev", c_void_p),
+        ("prev_has_orientation", c_int32),
+        ("stride", c_int32),
+    ]
+
+
+class SdbEngineStats(ctypes.Structure):
+    _fields_ = [
+        ("frames", c_int64),
+        ("updates", c_int64),
+        ("h2d_bytes", c_int64),
+        ("d2h_bytes", c_int64),
+        ("pool_frames", c_int64),
+        ("pool_free", c_int64),
+        ("device_bytes", c_int64),
+        ("last_segments", c_int32),
+        ("last_inc_sets", c_int32),
+        ("last_step_flags", c_int32),
+        ("capacity", c_int32),
+        ("d_ov_ws", c_void_p),
+        ("d_inc_ws", c_void_p),
     ]
 
 
@@ -173,6 +260,19 @@ def load():
         "sdb_launch_count": (c_uint64, []),
         "sdb_test_rot_increment": (c_double, [c_float, c_float, c_float, c_float, POINTER(c_int32)]),
         "sdb_test_wrap2d": (None, [c_float, c_float, c_float, c_float, c_float, POINTER(c_float), POINTER(c_float)]),
+        "sdb_engine_create": (c_int32, [POINTER(SdbEngineConfig), POINTER(c_void_p)]),
+        "sdb_engine_destroy": (None, [P]),
+        "sdb_engine_set_trackers": (c_int32, [P, POINTER(SdbTracker), c_int32]),
+        "sdb_engine_step": (c_int64, [P, POINTER(SdbFrame), P]),
+        "sdb_engine_wait": (c_int32, [P, c_int64, P, P, P]),
+        "sdb_engine_device_rows": (c_int32, [P, c_int64, POINTER(c_void_p), POINTER(c_int32)]),
+        "sdb_engine_run": (c_int32, [P, POINTER(SdbFrame), c_int32, P, P, P, P]),
+        "sdb_engine_drop": (c_int32, [P, c_int64]),
+        "sdb_engine_origin": (c_int32, [P, c_int64, POINTER(SdbOriginInfo)]),
+        "sdb_engine_num_origins": (c_int32, [P]),
+        "sdb_engine_keys": (c_int32, [P, POINTER(c_int64), c_int32]),
+        "sdb_engine_stats": (c_int32, [P, POINTER(SdbEngineStats)]),
+        "sdb_engine_last_descriptors": (c_int32, [P, P, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -60,7 +60,7 @@ class ShardedDynamics:
     ``batch`` frames -- nothing but the frame exchange happens per frame.
     """
 
-    def __init__(self, num_mols, step_fn, max_local, *, device, group=None, depth=3, exchange=None, batch=64):
+    def __init__(self, num_mols, step_fn, max_local, *, device, group=None, depth=3, exchange=None, batch=64, direct_rows=False):
         import os
 
         import torch
@@ -73,6 +73,10 @@ class ShardedDynamics:
         self.n = int(num_mols)
         self.device = torch.device(device)
         self.step_fn = step_fn
+        # direct_rows: step_fn(timestep, pos, quat, keys, rows_out=ptr) writes the rows of the frame in `keys`
+        # order straight to the device address `ptr` -- with the native engine that is one peer copy into
+        # rank 0's row buffer, enqueued by the same native call as the kernels
+        self.direct_rows = bool(direct_rows)
         self.max_local = int(max_local)
         self.depth = int(depth)
         self.qoff = (3 * self.n + 3) // 4 * 4
@@ -386,7 +390,22 @@ class ShardedDynamics:
             for k in active:
                 self._start.setdefault(k, int(timestep))
             self._last_active, self._last_local = list(active), local
-        keys, timediffs, sums = self.step_fn(timestep, pos, quat, local) if local else ([], [], None)
+        rows_ptr = 0
+        if self.direct_rows and gather == "batch" and self.world > 1:
+            if self._batch_buf is None:
+                self._setup_batch_rows()
+            i = len(self._batch_meta)
+            row_bytes = self.max_local * SDB_NSUM * 8
+            if self._rows_r0 is not None:
+                rows_ptr = self._rows_r0_ptr[self._rows_parity] + (self.rank * self.batch + i) * row_bytes
+            else:
+                rows_ptr = self._batch_buf.data_ptr() + i * row_bytes
+        if not local:
+            keys, timediffs, sums = [], [], None
+        elif rows_ptr:
+            keys, timediffs, sums = self.step_fn(timestep, pos, quat, local, rows_out=rows_ptr)
+        else:
+            keys, timediffs, sums = self.step_fn(timestep, pos, quat, local)
         if keys != local:
             # the engine may reorder origins (grouping by previous sample): restore `local` order
             order = [keys.index(k) for k in local]
@@ -400,7 +419,9 @@ class ShardedDynamics:
             if self._batch_buf is None:
                 self._setup_batch_rows()
             i = len(self._batch_meta)
-            if keys and sums is not None:
+            if rows_ptr:
+                pass  # already written by step_fn
+            elif keys and sums is not None:
                 if self._rows_r0 is not None:
                     # straight into rank 0's row buffer over NVLink (symmetric memory): flush() then needs no
                     # collective, only a barrier and one device-to-host copy on rank 0
@@ -466,6 +487,7 @@ class ShardedDynamics:
                 full = (2, self.world) + shape
                 on_r0 = self._rows_sym.view(full) if self.rank == 0 else self._rows_hdl.get_buffer(0, full, torch.float64)
                 self._rows_r0 = [on_r0[0], on_r0[1]]
+                self._rows_r0_ptr = [on_r0[0].data_ptr(), on_r0[1].data_ptr()]
                 self._rows_parity = 0
                 torch.cuda.synchronize(self.device)
                 self.dist.barrier(group=self.group)

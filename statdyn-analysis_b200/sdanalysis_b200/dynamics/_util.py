@@ -217,14 +217,13 @@ class TrackedMotion:
     def _to_general(self):
         """Move a planar state into the general layout (first non-planar quaternion seen)."""
         eng = self._engine
-        eng._flush_plan()
         org = eng.origins[0]
         trans, rot = eng.delta_arrays(0)
-        prev = org.prev.planes[:, : self.num_particles].cpu().numpy()
+        prev = org.prev_planes[:, : self.num_particles].cpu().numpy()
         pos = np.zeros((self.num_particles, 3), dtype=F32)
         pos[:, 0], pos[:, 1] = prev[0], prev[1]
         quat = None
-        if org.prev.has_orientation:
+        if org.prev_has_orientation:
             quat = np.zeros((self.num_particles, 4), dtype=F32)
             quat[:, 0], quat[:, 3] = prev[2], prev[3]
         gen = _GeneralState(self.box, pos, quat, self._device)

@@ -6,6 +6,12 @@ The reference keeps one ``(Dynamics, Relaxations)`` pair of Python objects per t
 :meth:`DynamicsEngine.step` advances every active origin with the fused CUDA kernel
 (``csrc/dyn_step.cu``) plus the ``struct`` and ``overlap`` kernels.
 
+Since round 2 the engine itself is native code (``csrc/engine.cu``, C-ABI ``sdb_engine_*``): origin
+records, the pool of previous samples, segment grouping, descriptor / result rings, staging of host
+frames.  This module is the thin Python face of it: argument checking with the reference's error
+conventions, threshold digestion, and the closed forms that turn the 16 sums of a (frame, origin)
+into the 15 quantities of ``compute_all``.
+
 Per-origin state (N molecules, ``stride`` = N rounded up to 4):
 
 =============  ======================  =========================================================
@@ -20,18 +26,15 @@ was active points at it, so in the dense (linear) schedule one frame is shared b
 the exponential schedule at most one frame per origin is alive.
 """
 
-import math
-from collections import OrderedDict
+import ctypes
+import weakref
+from collections import deque
 
 import numpy as np
 
 from . import _lib
 from ._lib import (
-    HISTORY_WORDS,
     ORIGIN_DTYPE,
-    ORIGIN_HISTORY,
-    ORIGIN_LITERAL,
-    ORIGIN_NEW,
     S_BADQUAT,
     S_COMSTRUCT,
     S_COS,
@@ -47,10 +50,7 @@ from ._lib import (
     S_STRUCT,
     SDB_MAX_TRACKERS,
     SDB_NSUM,
-    SEG_NO_ROTATION,
-    SEG_ZERO_STEP,
     SEGMENT_DTYPE,
-    SdbDynParams,
 )
 
 F32 = np.float32
@@ -228,71 +228,137 @@ def finalize_table(sums, timediffs, n, *, distance=None, overlap_k=None, n_sites
 
 
 # ----------------------------------------------------------------------------------------------
-class _PoolFrame:
-    __slots__ = ("planes", "refs", "has_orientation", "ptr")
+class _CudaArray:
+    """Minimal ``__cuda_array_interface__`` carrier: lets torch view memory owned by the native engine."""
 
-    def __init__(self, planes):
-        self.planes = planes
-        self.ptr = planes.data_ptr()
-        self.refs = 0
-        self.has_orientation = True
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(int(v) for v in shape), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None,
+        }
 
 
-class _Origin:
-    __slots__ = ("key", "timestep", "delta", "flags", "status", "prev", "max_timediff", "updates", "ptrs")
+class _OriginView:
+    """One origin of the native engine: torch views of its device state (no copies)."""
 
-    def __init__(self, key, timestep):
+    def __init__(self, engine, key, info):
+        self._engine = engine
         self.key = key
-        self.timestep = int(timestep)
-        self.delta = self.flags = self.status = None
-        self.prev = None
-        self.max_timediff = -1
-        self.updates = 0
-        self.ptrs = (0, 0, 0)  # raw device pointers of delta / flags / status (cached: data_ptr() is slow)
+        self.timestep = int(info.timestep)
+        self.updates = int(info.updates)
+        self.max_timediff = int(info.max_timediff)
+        self._info = info
+
+    def _view(self, ptr, shape, typestr):
+        if not ptr:
+            return None
+        eng = self._engine
+        t = eng.torch.as_tensor(_CudaArray(ptr, shape, typestr), device=eng.device)
+        t._sdb_owner = eng  # the engine owns the memory
+        return t
+
+    @property
+    def delta(self):
+        return self._view(self._info.d_delta, (3, self._engine.stride), "<f4")
+
+    @property
+    def flags(self):
+        return self._view(self._info.d_flags, (self._engine.stride,), "|u1")
+
+    @property
+    def status(self):
+        n_tr = len(self._engine.trackers)
+        return self._view(self._info.d_status, (n_tr, self._engine.stride), "<i4") if n_tr else None
+
+    @property
+    def prev_planes(self):
+        """(x, y, qw, qz) planes of the previous sample (``TrackedMotion.previous_*``)."""
+        return self._view(self._info.d_prev, (4, self._engine.stride), "<f4")
+
+    @property
+    def prev_has_orientation(self):
+        return bool(self._info.prev_has_orientation)
+
+    @property
+    def ptrs(self):
+        return (self._info.d_delta or 0, self._info.d_flags or 0, self._info.d_status or 0)
 
 
-class _Ring:
-    """A small ring of pinned host buffers, each guarded by a CUDA event."""
+class _Origins:
+    """Mapping view of the engine's origins, keyed like ``process_file``'s ``keyframes`` dict."""
 
-    def __init__(self, torch, depth, make):
-        self.bufs = [make() for _ in range(depth)]
-        self.events = [None] * depth
-        self.torch = torch
-        self.i = 0
+    def __init__(self, engine):
+        self._engine = engine
 
-    def acquire(self):
-        self.i = (self.i + 1) % len(self.bufs)
-        ev = self.events[self.i]
-        if ev is not None:
-            ev.synchronize()
-        return self.i, self.bufs[self.i]
+    def __getitem__(self, key):
+        eng = self._engine
+        info = _lib.SdbOriginInfo()
+        if key not in eng._ids or eng.lib.sdb_engine_origin(eng._handle, eng._ids[key], ctypes.byref(info)) != 0:
+            raise KeyError(key)
+        return _OriginView(eng, key, info)
 
-    def release(self, i, stream=None):
-        ev = self.events[i]
-        if ev is None:
-            ev = self.events[i] = self.torch.cuda.Event()
-        if stream is None:
-            ev.record()
-        else:
-            ev.record(stream)  # with an explicit stream torch skips its (slow) current-stream lookup
-        return ev
+    def __contains__(self, key):
+        return key in self._engine._t0
+
+    def __len__(self):
+        return int(self._engine.lib.sdb_engine_num_origins(self._engine._handle))
+
+    def keys(self):
+        eng = self._engine
+        count = len(self)
+        buf = (ctypes.c_int64 * max(count, 1))()
+        eng.lib.sdb_engine_keys(eng._handle, buf, count)
+        return [eng._keys_by_id[int(buf[i])] for i in range(count)]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
 
 
 class StepResult:
-    """Handle to the sums of one engine step; ``rows()`` waits for the device and finalises."""
+    """Handle to the rows of one engine step; ``rows()`` / ``table()`` wait for the device and finalise."""
 
-    def __init__(self, engine, keys, timediffs, sums_host, event, isf_host=None):
+    def __init__(self, engine, keys, timestep, ticket, has_rows, has_isf):
         self.engine = engine
         self.keys = keys
-        self.timediffs = timediffs
-        self._sums = sums_host
-        self._event = event
-        self._isf = isf_host  # per-origin sums of the angular mean of cos(k . dr), or None
+        self._timestep = timestep
+        self._ticket = ticket
+        self._has_rows = has_rows
+        self._has_isf = has_isf
+        self._sums = None
+        self._isf = None
+        self._timediffs = None
+
+    @property
+    def timediffs(self):
+        if self._timediffs is None:
+            t0 = self.engine._t0
+            self._timediffs = [self._timestep - t0[k] for k in self.keys]
+        return self._timediffs
+
+    def _materialize(self):
+        """Copy the rows out of the engine's ring (called before the ring slot is reused, or on demand)."""
+        if self._ticket is None:
+            return
+        ticket, self._ticket = self._ticket, None
+        eng = self.engine
+        n = len(self.keys)
+        if not self._has_rows or n == 0:
+            self._sums = np.zeros((n, SDB_NSUM))
+            return
+        sums = np.empty((n, SDB_NSUM), dtype=np.float64)
+        isf = np.empty(n, dtype=np.float64) if self._has_isf else None
+        _lib.check(
+            eng.lib.sdb_engine_wait(eng._handle, ticket, sums.ctypes.data, None, isf.ctypes.data if isf is not None else None)
+        )
+        self._sums, self._isf = sums, isf
 
     def sums(self):
-        if self._event is not None:
-            self._event.synchronize()
-            self._event = None
+        self._materialize()
         return self._sums
 
     def rows(self, check=True, strict=True):
@@ -315,6 +381,8 @@ class StepResult:
 
 
 class DynamicsEngine:
+    """All time-origins of one GPU.  ``step`` = one frame of ``read/_read.py:128-168`` for every active origin."""
+
     def __init__(
         self,
         num_mols,
@@ -332,10 +400,18 @@ class DynamicsEngine:
         overlap_fraction=0.1,
         compute_isf=False,
         angular_resolution=360,
+        chunk=None,
+        dry=False,
     ):
-        self.torch = torch = _lib.torch()
-        self.device = _lib.require_cuda(device)
+        import os
+
         self.lib = _lib.load()
+        self._dry = bool(dry)  # test hook: bookkeeping only, no CUDA call (CPU test-suite)
+        if self._dry:
+            self.torch, self.device = None, None
+        else:
+            self.torch = _lib.torch()
+            self.device = _lib.require_cuda(device)
         self.n = int(num_mols)
         if self.n <= 0:
             raise RuntimeError("Position must contain values, has length of 0.")
@@ -362,499 +438,291 @@ class DynamicsEngine:
         if struct_mode not in ("reference", "physical"):
             raise ValueError("struct_mode must be 'reference' or 'physical'")
         self.struct_mode = 0 if struct_mode == "reference" else 1
+        self.trackers = build_trackers(trackers) if trackers else []
+        self.ring_depth = max(2, int(ring_depth))
 
-        p = SdbDynParams()
-        p.n, p.stride = self.n, self.stride
-        p.lx, p.ly, p.xy = float(self.box[0]), float(self.box[1]), float(self.box[3])
-        p.com_cut_lt = float(_cut_sqrt(self.distance, False)) if self.distance is not None else -1.0
-        p.do_sums = int(self.compute_sums)
-        self.params = p
-        self.origins = OrderedDict()
-        self.set_trackers(trackers)
+        cfg = _lib.SdbEngineConfig()
+        cfg.n = self.n
+        for i in range(6):
+            cfg.box[i] = float(self.box[i])
+        cfg.wave_number = float(wave_number) if wave_number is not None else 0.0
+        cfg.com_cut_lt = float(_cut_sqrt(self.distance, False)) if self.distance is not None else -1.0
+        self._fill_trackers(cfg.trackers)
+        cfg.n_trackers = len(self.trackers)
+        cfg.compute_sums = int(self.compute_sums)
+        cfg.overlap_k = self.overlap_k if self.compute_overlap else 0
+        if self.compute_struct:
+            cfg.n_sites = len(self.mol_sites)
+            for i, v in enumerate(self.mol_sites.reshape(-1)):
+                cfg.sites_xy[i] = float(v)
+        cfg.struct_mode = self.struct_mode
+        cfg.compute_isf = int(self.compute_isf)
+        cfg.angular_resolution = self.angular_resolution
+        cfg.ring_depth = self.ring_depth
+        # SDB_INCREMENTS=0: every segment recomputes the frame increments itself (no per-frame pass); the pass
+        # costs about one phase 1 plus 76 B per molecule of traffic: it pays when several segments share a
+        # previous sample and each has few origins to amortise its own phase 1 over (measured: 25 origins in 3
+        # segments -11 % on dyn_step, 200 origins in 3 segments +3 %)
+        cfg.inc_max_per_segment = int(os.environ.get("SDB_INCREMENTS_MAX_PER_SEGMENT", "40"))
+        cfg.chunk = int(chunk or 0)
+        flags = 0
+        if self._dry:
+            flags |= _lib.SDB_ENGINE_DRY
+        if os.environ.get("SDB_OV_PREDICT", "1") == "0":  # sampled overlap brackets every frame
+            flags |= _lib.SDB_ENGINE_NO_PREDICT
+        if os.environ.get("SDB_INCREMENTS", "1") == "0":
+            flags |= _lib.SDB_ENGINE_NO_INCREMENTS
+        cfg.flags = flags
+        self._handle = ctypes.c_void_p()
+        if self._dry:
+            _lib.check(self.lib.sdb_engine_create(ctypes.byref(cfg), ctypes.byref(self._handle)))
+        else:
+            with _lib.device_context(self.device):
+                _lib.check(self.lib.sdb_engine_create(ctypes.byref(cfg), ctypes.byref(self._handle)))
+        self.origins = _Origins(self)
+        self._t0 = {}          # key -> timestep of the origin's first frame
+        self._ids = {}         # key -> int64 id handed to the native engine
+        self._keys_by_id = {}
+        self._frame = _lib.SdbFrame()
+        self._last_active = None
+        self._last_ids = None
+        self._next_ticket = 0
+        self._outstanding = deque()  # (ticket, weakref to StepResult): materialised before their slot is reused
+        self._keepalive = deque()    # host tensors whose upload may still be in flight
 
-        self._free_frames = []
-        self._n_parts = int(self.lib.sdb_dyn_num_parts(self.n))
-        self._ring_depth = ring_depth
-        self._cap = 0  # capacity (origins) of the per-step scratch
-        self._frame_ring = None
-        self._dev_frames = None
-        self._frame_i = 0
-        self._staged_slot = None
-        self.h2d_bytes = self.d2h_bytes = 0
-        self._plan = None
-        # SDB_OV_PREDICT=0 disables the history-predicted overlap brackets (sampled brackets every frame)
-        import os
-
-        self._origin_flags = ORIGIN_HISTORY if os.environ.get("SDB_OV_PREDICT", "1") != "0" else 0
-        # SDB_INCREMENTS=0: every segment recomputes the frame increments itself (no per-frame pass)
-        self._inc_ok = os.environ.get("SDB_INCREMENTS", "1") != "0"
-        # the per-frame pass costs about one phase 1 plus 76 B per molecule of traffic: it pays when
-        # several segments share a previous sample and each has few origins to amortise its own phase 1
-        # over (measured: 25 origins in 3 segments -11 % on dyn_step, 200 origins in 3 segments +3 %)
-        self._inc_max_per_segment = int(os.environ.get("SDB_INCREMENTS_MAX_PER_SEGMENT", "40"))
-        self._inc_ws = None
-        self._sites_c = None if self.mol_sites is None else _lib.float_array(self.mol_sites.reshape(-1))
-        self.frames_seen = 0
-        self.updates = 0  # molecule x origin updates performed
+    def __del__(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            try:
+                self.lib.sdb_engine_destroy(handle)
+            except Exception:
+                pass
 
     # ------------------------------------------------------------------------------------------
-    def _ensure_capacity(self, n_active):
-        if n_active <= self._cap:
-            return
-        torch = self.torch
-        cap = max(16, 1 << (n_active - 1).bit_length())
-        dev = self.device
-        self._cap = cap
-        n_desc = cap * 32 + (cap + 8) * 24  # origins (32 B) + segments (24 B), generous
-        self._desc_ring = _Ring(torch, self._ring_depth, lambda: torch.empty(n_desc, dtype=torch.uint8).pin_memory())
-        self._desc_dev = [torch.empty(n_desc, dtype=torch.uint8, device=dev) for _ in range(self._ring_depth)]
-        self._sums_ring = _Ring(
-            torch, self._ring_depth, lambda: torch.zeros((cap, SDB_NSUM), dtype=torch.float64).pin_memory()
-        )
-        self._sums_dev = [torch.zeros((cap, SDB_NSUM), dtype=torch.float64, device=dev) for _ in range(self._ring_depth)]
-        self._partials = torch.empty((cap, self._n_parts, SDB_NSUM), dtype=torch.float64, device=dev)
-        self._ov_ws_ptr = 0
-        if self.compute_overlap and self.overlap_k > 0:
-            nbytes = int(self.lib.sdb_overlap_ws_bytes(cap, self.n))
-            self._ov_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            self._ov_ws_ptr = self._ov_ws.data_ptr()
-        if self.compute_isf:
-            self._isf_dev = [torch.zeros(cap, dtype=torch.float64, device=dev) for _ in range(self._ring_depth)]
-            self._isf_host = [torch.zeros(cap, dtype=torch.float64).pin_memory() for _ in range(self._ring_depth)]
-        # raw pointers / numpy views used every frame (tensor.data_ptr() and .numpy() are slow)
-        self._desc_host = [t.numpy() for t in self._desc_ring.bufs]
-        self._desc_host_ptr = [t.data_ptr() for t in self._desc_ring.bufs]
-        self._desc_dev_ptr = [t.data_ptr() for t in self._desc_dev]
-        self._sums_host_ptr = [t.data_ptr() for t in self._sums_ring.bufs]
-        self._sums_dev_ptr = [t.data_ptr() for t in self._sums_dev]
-        self._partials_ptr = self._partials.data_ptr()
-
-    def _inc_args(self, inc_sets):
-        """ctypes arguments (h_prev, h_flags, n_sets, d_ws) of the per-frame increments pass."""
-        import ctypes
-
-        if not inc_sets:
-            return None, None, 0, 0
-        if self._inc_ws is None:
-            nbytes = int(self.lib.sdb_dyn_increments_bytes(self.n, self.stride, _lib.SDB_MAX_INC_SETS))
-            self._inc_ws = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
-        k = len(inc_sets)
-        prev = (ctypes.c_void_p * _lib.SDB_MAX_INC_SETS)(*[p for p, _ in inc_sets])
-        flags = (ctypes.c_uint32 * _lib.SDB_MAX_INC_SETS)(*[f for _, f in inc_sets])
-        # the workspace is laid out for exactly k sets by both calls
-        return prev, flags, k, self._inc_ws.data_ptr()
-
-    def _stage_frame(self, position, orientation):
-        """Return device tensors (pos (N,3) f32, quat (N,4) f32 or None).
-
-        Device tensors are used in place.  Host input (numpy arrays or CPU tensors) is copied to a
-        ring of device frame buffers on a dedicated copy stream, so the upload of frame t+1 overlaps
-        the kernels of frame t; numpy arrays first go through a ring of pinned staging buffers, pinned
-        CPU tensors are uploaded directly."""
-        torch = self.torch
-        if isinstance(position, torch.Tensor) and position.is_cuda:
-            pos = position
-            quat = orientation
-            if pos.dtype != torch.float32 or not pos.is_contiguous():
-                pos = pos.to(torch.float32).contiguous()
-            if quat is not None and (quat.dtype != torch.float32 or not quat.is_contiguous()):
-                quat = quat.to(torch.float32).contiguous()
-            if pos.data_ptr() % 16:
-                pos = pos.clone()
-            if quat is not None and quat.data_ptr() % 16:
-                quat = quat.clone()
-            self.h2d_bytes = 0
-            return pos, quat
-        n = self.n
-        qoff = (3 * n + 3) // 4 * 4  # quaternions start 16-byte aligned (float4 loads)
-        if self._dev_frames is None:
-            self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._dev_frames = [
-                torch.empty(qoff + 4 * n, dtype=torch.float32, device=self.device) for _ in range(self._ring_depth)
-            ]
-            self._dev_consumed = [None] * self._ring_depth
-        if isinstance(position, torch.Tensor):
-            if tuple(position.shape) != (n, 3) or (orientation is not None and tuple(orientation.shape) != (n, 4)):
-                raise RuntimeError("frame tensors must have shapes (N,3) and (N,4)")
-            src_pos, src_quat, ring_i = position, orientation, None
-        else:
-            position = np.asarray(position)
-            if position.shape != (n, 3):
-                raise RuntimeError(f"position has shape {position.shape}, expected {(n, 3)}")
-            if orientation is not None:
-                orientation = np.asarray(orientation)
-                if orientation.shape != (n, 4):
-                    raise RuntimeError(f"orientation has shape {orientation.shape}, expected {(n, 4)}")
-            if self._frame_ring is None:
-                self._frame_ring = _Ring(
-                    torch, self._ring_depth, lambda: torch.zeros(qoff + 4 * n, dtype=torch.float32).pin_memory()
-                )
-            ring_i, pinned = self._frame_ring.acquire()
-            host = pinned.numpy()
-            np.copyto(host[: 3 * n].reshape(n, 3), position, casting="same_kind")
-            src_pos = pinned[: 3 * n].view(n, 3)
-            src_quat = None
-            if orientation is not None:
-                np.copyto(host[qoff : qoff + 4 * n].reshape(n, 4), orientation, casting="same_kind")
-                src_quat = pinned[qoff : qoff + 4 * n].view(n, 4)
-        self._frame_i = (self._frame_i + 1) % self._ring_depth
-        dev = self._dev_frames[self._frame_i]
-        pos = dev[: 3 * n].view(n, 3)
-        quat = dev[qoff : qoff + 4 * n].view(n, 4) if src_quat is not None else None
-        main = self._main
-        with torch.cuda.stream(self._copy_stream):
-            consumed = self._dev_consumed[self._frame_i]
-            if consumed is not None:
-                self._copy_stream.wait_event(consumed)  # kernels that read this buffer are done
-            pos.copy_(src_pos, non_blocking=True)
-            if quat is not None:
-                quat.copy_(src_quat, non_blocking=True)
-            uploaded = torch.cuda.Event()
-            uploaded.record(self._copy_stream)
-        if ring_i is not None:
-            self._frame_ring.events[ring_i] = uploaded
-        main.wait_event(uploaded)
-        self._staged_slot = self._frame_i
-        self.h2d_bytes = 4 * (7 * n if src_quat is not None else 3 * n)
-        return pos, quat
-
-    def _new_pool_frame(self):
-        if self._free_frames:
-            return self._free_frames.pop()
-        return _PoolFrame(self.torch.zeros((4, self.stride), dtype=self.torch.float32, device=self.device))
-
-    def _release(self, frame):
-        if frame is None:
-            return
-        frame.refs -= 1
-        if frame.refs == 0:
-            self._free_frames.append(frame)
-
-    def _alloc_origin(self, org):
-        torch, dev = self.torch, self.device
-        # three planes followed by the threshold history of the overlap selection (SDB_ORIGIN_HISTORY)
-        buf = torch.empty(3 * self.stride + HISTORY_WORDS, dtype=torch.float32, device=dev)
-        buf[3 * self.stride :].zero_()
-        org.delta = buf[: 3 * self.stride].view(3, self.stride)
-        if self.trackers:
-            org.flags = torch.empty(self.stride, dtype=torch.uint8, device=dev)
-            org.status = torch.empty((len(self.trackers), self.stride), dtype=torch.int32, device=dev)
-        org.ptrs = (org.delta.data_ptr(), _lib.ptr(org.flags), _lib.ptr(org.status))
-
-    def set_trackers(self, definitions):
-        """Replace the tracker set; every origin's passage state starts afresh while its accumulated
-        motion is kept (``Relaxations.set_mol_relax``, ``relaxations.py:108-133``)."""
-        # a cached steady-state plan holds the per-origin records (previous sample, update count,
-        # largest time difference) of the frames stepped since it was made: bring them up to date
-        # before dropping it, or the next step would group origins by a released previous sample
-        if getattr(self, "_plan", None) is not None:
-            self._flush_plan()
-        self.trackers = build_trackers(definitions) if definitions else []
-        p = self.params
-        p.n_trackers = len(self.trackers)
+    def _fill_trackers(self, array):
         for i, spec in enumerate(self.trackers):
             cut = _cut_direct if spec.type == "rotation" else _cut_sqrt
-            t = p.trackers[i]
+            t = array[i]
             t.is_rotation = int(spec.type == "rotation")
             t.is_last = int(spec.last_passage)
             t.bit = spec.bit
             t.cut_gt = float(cut(spec.threshold, True))
             t.cut_lt = float(cut(spec.threshold, False))
             t.cut_irr = float(cut(spec.cutoff, True))
-        torch, dev = self.torch, self.device
-        for org in self.origins.values():
-            if self.trackers:
-                org.flags = torch.zeros(self.stride, dtype=torch.uint8, device=dev)
-                org.status = torch.full((len(self.trackers), self.stride), -1, dtype=torch.int32, device=dev)
-            else:
-                org.flags = org.status = None
-            org.ptrs = (org.delta.data_ptr(), _lib.ptr(org.flags), _lib.ptr(org.status))
-        self._plan = None
 
-    def _release_many(self, frame, count):
-        if frame is None:
-            return
-        frame.refs -= count
-        if frame.refs == 0:
-            self._free_frames.append(frame)
+    def set_trackers(self, definitions):
+        """Replace the tracker set; every origin's passage state starts afresh while its accumulated
+        motion is kept (``Relaxations.set_mol_relax``, ``relaxations.py:108-133``)."""
+        self.trackers = build_trackers(definitions) if definitions else []
+        array = (_lib.SdbTracker * SDB_MAX_TRACKERS)()
+        self._fill_trackers(array)
+        _lib.check(self.lib.sdb_engine_set_trackers(self._handle, array, len(self.trackers)))
 
     def _flush_plan(self):
-        """Bring the per-origin records up to date after a run of steady-state steps."""
-        plan, self._plan = self._plan, None
-        if plan is None or plan["steps"] == 0:
-            return
-        last = plan["timestep"]
-        for org in plan["ordered"]:
-            org.prev = plan["prev"]
-            org.updates += plan["steps"]
-            org.max_timediff = max(org.max_timediff, last - org.timestep)
+        """(kept for callers of round 1: the native engine has no deferred bookkeeping)"""
 
     def drop_origin(self, key):
-        self._flush_plan()
-        org = self.origins.pop(key)
-        self._release(org.prev)
+        _lib.check(self.lib.sdb_engine_drop(self._handle, self._ids[key]))
+        ident = self._ids.pop(key)
+        self._keys_by_id.pop(ident, None)
+        self._t0.pop(key, None)
+        self._last_active = None
+
+    def _key_ids(self, active, timestep):
+        """int64 ids of ``active`` for the native engine (cached while the list does not change)."""
+        if active == self._last_active:
+            return self._last_ids
+        ids = self._ids
+        for key in active:
+            if key not in ids:
+                ident = int(key) if isinstance(key, (int, np.integer)) and not isinstance(key, bool) else None
+                if ident is None or ident in self._keys_by_id or not -(2 ** 62) < ident < 2 ** 62:
+                    ident = 2 ** 62 + len(ids)  # arbitrary hashable keys get ids outside the plain-integer range
+                ids[key] = ident
+                self._keys_by_id[ident] = key
+                self._t0[key] = int(timestep)
+        arr = (ctypes.c_int64 * max(len(active), 1))(*[ids[k] for k in active])
+        self._last_active, self._last_ids = list(active), arr
+        return arr
+
+    def _forget_failed_keys(self, active):
+        """After a failed step: keys the native engine did not create lose their Python-side record."""
+        info = _lib.SdbOriginInfo()
+        for key in active:
+            ident = self._ids.get(key)
+            if ident is not None and self.lib.sdb_engine_origin(self._handle, ident, ctypes.byref(info)) != 0:
+                self._ids.pop(key, None)
+                self._keys_by_id.pop(ident, None)
+                self._t0.pop(key, None)
+        self._last_active = None
+
+    def _frame_pointers(self, position, orientation):
+        """(pos pointer, quat pointer, SDB_MEM_* kind, objects to keep alive) of a frame in any of the accepted forms."""
+        torch, n = self.torch, self.n
+        if torch is not None and isinstance(position, torch.Tensor):
+            pos, quat = position, orientation
+            if tuple(pos.shape) != (n, 3) or (quat is not None and tuple(quat.shape) != (n, 4)):
+                raise RuntimeError("frame tensors must have shapes (N,3) and (N,4)")
+            if pos.dtype != torch.float32 or not pos.is_contiguous():
+                pos = pos.to(torch.float32).contiguous()
+            if quat is not None and (quat.dtype != torch.float32 or not quat.is_contiguous()):
+                quat = quat.to(torch.float32).contiguous()
+            if pos.is_cuda:
+                if pos.data_ptr() % 16:
+                    pos = pos.clone()
+                if quat is not None and quat.data_ptr() % 16:
+                    quat = quat.clone()
+                return pos.data_ptr(), _lib.ptr(quat), _lib.SDB_MEM_DEVICE, (pos, quat)
+            kind = _lib.SDB_MEM_PINNED if pos.is_pinned() and (quat is None or quat.is_pinned()) else _lib.SDB_MEM_HOST
+            return pos.data_ptr(), _lib.ptr(quat), kind, (pos, quat)
+        position = np.asarray(position)
+        if position.shape != (n, 3):
+            raise RuntimeError(f"position has shape {position.shape}, expected {(n, 3)}")
+        if position.dtype != F32 or not position.flags.c_contiguous:
+            position = np.ascontiguousarray(position, dtype=F32)
+        quat_ptr = 0
+        if orientation is not None:
+            orientation = np.asarray(orientation)
+            if orientation.shape != (n, 4):
+                raise RuntimeError(f"orientation has shape {orientation.shape}, expected {(n, 4)}")
+            if orientation.dtype != F32 or not orientation.flags.c_contiguous:
+                orientation = np.ascontiguousarray(orientation, dtype=F32)
+            quat_ptr = orientation.ctypes.data
+        # pageable host memory is copied into the engine's pinned ring inside the call: the (possibly converted)
+        # arrays only have to outlive the call itself
+        return position.ctypes.data, quat_ptr, _lib.SDB_MEM_HOST, (position, orientation)
 
     # ------------------------------------------------------------------------------------------
-    def step(self, timestep, position, orientation, active, *, zero_step=False, want_sums=None, chunk=None, to_host=True):
+    def step(self, timestep, position, orientation, active, *, zero_step=False, want_sums=None, to_host=True, rows_out=0):
         """Advance every origin in ``active`` (iterable of hashable keys) with one frame.
 
         Unknown keys are created at this frame (``Dynamics.from_frame`` + first ``compute_all``,
-        ``read/_read.py:135-152``).  Returns a :class:`StepResult` (asynchronous).
+        ``read/_read.py:135-152``).  Returns a :class:`StepResult` (asynchronous; rows in the order of
+        ``active``).  ``to_host=False`` keeps the rows on the device: returns ``(keys, timediffs, rows)``
+        with ``rows`` a device tensor view valid for ``ring_depth - 1`` further steps; ``rows_out`` (a raw
+        device pointer, possibly peer memory) additionally receives the rows in ``active`` order.
         """
-        torch, lib = self.torch, self.lib
-        active = list(active)
+        active = active if isinstance(active, list) else list(active)
         n_active = len(active)
         if n_active == 0:
-            return StepResult(self, [], [], np.zeros((0, SDB_NSUM)), None)
-        self._ensure_capacity(n_active)
-        do_sums = self.compute_sums if want_sums is None else bool(want_sums)
-
-        with _lib.device_context(self.device):
-            self._staged_slot = None
-            main = self._main = _lib.current_stream(self.device)
-            if zero_step:
-                pos = quat = None
-            else:
-                pos, quat = self._stage_frame(position, orientation)
-
-            # ---- descriptors: origins grouped into segments by previous sample ------------------
-            plan = self._plan
-            if (
-                plan is not None
-                and not zero_step
-                and plan["active"] == active
-                and plan["has_quat"] == (quat is not None)
-                and int(timestep) > plan["timestep"]  # time moves forward: no origin needs ORIGIN_LITERAL
-                and plan["monotone"]
-                and chunk is None
-            ):
-                # steady state of the dense schedule: same origins, all sharing the previous frame --
-                # only the time differences and the previous-sample pointer change
-                ordered = plan["ordered"]
-                odesc = plan["odesc"]
-                odesc["timediff"] = int(timestep) - plan["t0"]
-                odesc["flags"] = self._origin_flags
-                timediffs = odesc["timediff"].tolist()
-                if timediffs and max(timediffs) >= MAX_STATUS:
-                    raise OverflowError("time difference outside [0, 2**32-1): passage times are 32-bit on the device")
-                sdesc = plan["sdesc"]
-                sdesc["d_prev"] = plan["prev"].ptr
-                seg_count_max = plan["seg_count_max"]
-                n_segments = len(sdesc)
-                fast = True
-                # every segment shares the previous frame: its increments are computed once per frame
-                inc_sets = []
-                if n_segments > 1 and self._inc_ok and n_active <= self._inc_max_per_segment * n_segments:
-                    inc_sets = [(plan["prev"].ptr, int(sdesc["flags"][0]))]
-                    sdesc["reserved"] = 1
-                else:
-                    sdesc["reserved"] = 0
-            else:
-                fast = False
-                self._flush_plan()
-                groups = OrderedDict()
-                fresh = []
-                for key in active:
-                    org = self.origins.get(key)
-                    if org is None:
-                        org = _Origin(key, timestep)
-                        self._alloc_origin(org)
-                        self.origins[key] = org
-                        fresh.append(org)
-                    else:
-                        groups.setdefault(id(org.prev), (org.prev, []))[1].append(org)
-                if zero_step and fresh:
+            return StepResult(self, [], int(timestep), None, False, False)
+        timestep = int(timestep)
+        do_sums = self.compute_sums if want_sums is None else (bool(want_sums) and self.compute_sums)
+        if zero_step:
+            for key in active:
+                if key not in self._ids:
                     raise RuntimeError("zero_step on an origin that does not exist")
-
-                target_blocks = 148 * 16
-                blocks_per_segment = (self._n_parts + 3) // 4
-                seg_rows = []  # (previous planes pointer, flags, first, count)
-                ordered = []
-                for prev, members in groups.values():
-                    flags = 0
-                    if zero_step:
-                        flags |= SEG_ZERO_STEP
-                    elif quat is None or prev is None or not prev.has_orientation:
-                        flags |= SEG_NO_ROTATION
-                    size = chunk or max(8, math.ceil(len(members) * blocks_per_segment / target_blocks))
-                    size = math.ceil(len(members) / math.ceil(len(members) / size))  # equal shares
-                    for first in range(0, len(members), size):
-                        part = members[first : first + size]
-                        seg_rows.append((0 if prev is None else prev.ptr, flags, len(ordered), len(part)))
-                        ordered.extend(part)
-                if fresh:
-                    flags = SEG_NO_ROTATION if quat is None else 0
-                    seg_rows.append((0, flags, len(ordered), len(fresh)))
-                    ordered.extend(fresh)
-
-                odesc = np.zeros(n_active, dtype=ORIGIN_DTYPE)
-                t0 = np.fromiter((org.timestep for org in ordered), dtype=np.int64, count=n_active)
-                td = int(timestep) - t0
-                if td.min() < 0 or td.max() >= MAX_STATUS:
-                    raise OverflowError(
-                        f"time difference outside [0, 2**32-1): passage times are 32-bit on the device"
-                    )
-                ptrs = np.array([org.ptrs for org in ordered], dtype=np.uint64)
-                odesc["d_delta"], odesc["d_flags"], odesc["d_status"] = ptrs[:, 0], ptrs[:, 1], ptrs[:, 2]
-                odesc["timediff"] = td
-                odesc["flags"] = [
-                    self._origin_flags
-                    | (ORIGIN_NEW if org.updates == 0 else (ORIGIN_LITERAL if t < org.max_timediff else 0))
-                    for org, t in zip(ordered, td.tolist())
-                ]
-                timediffs = td.tolist()
-                # previous samples shared by several segments: their increments are computed once per frame
-                inc_sets, set_of = [], {}
-                if self._inc_ok and not zero_step:
-                    counts = {}
-                    for (p, fl, f, c) in seg_rows:
-                        if p:
-                            counts[(p, fl)] = counts.get((p, fl), 0) + 1
-                    for key, cnt in counts.items():
-                        members = sum(c for (p, fl, f, c) in seg_rows if (p, fl) == key)
-                        if cnt > 1 and members <= self._inc_max_per_segment * cnt and len(inc_sets) < _lib.SDB_MAX_INC_SETS:
-                            set_of[key] = len(inc_sets) + 1
-                            inc_sets.append(key)
-                sdesc = np.array([(p, f, c, fl, set_of.get((p, fl), 0)) for (p, fl, f, c) in seg_rows], dtype=SEGMENT_DTYPE)
-                seg_count_max = max(row[3] for row in seg_rows)
-                n_segments = len(seg_rows)
-
-            ri, pinned = self._desc_ring.acquire()
-            ob, sb = odesc.nbytes, sdesc.nbytes
-            seg_off = (ob + 15) // 16 * 16
-            host = self._desc_host[ri]
-            host[:ob] = odesc.view(np.uint8)
-            host[seg_off : seg_off + sb] = sdesc.view(np.uint8)
-
-            # ---- the frame that becomes everybody's previous sample ---------------------------
-            new_prev = None
-            if not zero_step:
-                new_prev = self._new_pool_frame()
-                new_prev.has_orientation = quat is not None
-
-            si, sums_pinned = self._sums_ring.acquire()
-            sums_dev = self._sums_dev[si]
-            params = self.params
-            params.do_sums = int(do_sums)
-            use_ov = do_sums and self.compute_overlap and self.overlap_k > 0
-            want_host = do_sums and to_host
-            # steady state with three or more preceding overlap selections at increasing times: every
-            # origin's bracket is predicted from its threshold history, the sample kernels are skipped
-            step_flags = 0
-            if fast:
-                if use_ov and self._origin_flags and plan["ov_steps"] >= 3 and int(timestep) > plan["timestep"]:
-                    step_flags |= _lib.SDB_STEP_PREDICTED
-                plan["ov_steps"] = plan["ov_steps"] + 1 if (use_ov and int(timestep) > plan["timestep"]) else 0
-            # one native call enqueues the whole frame: descriptor upload, overlap sampling/brackets, the
-            # fused dynamics kernel, struct, overlap resolve, download of the sums (csrc/frame_step.cu)
-            _lib.check(
-                lib.sdb_frame_step(
-                    params,
-                    _lib.ptr(pos),
-                    _lib.ptr(quat),
-                    0 if new_prev is None else new_prev.ptr,
-                    self._desc_host_ptr[ri],
-                    self._desc_dev_ptr[ri],
-                    seg_off + sb,
-                    seg_off,
-                    n_active,
-                    n_segments,
-                    seg_count_max,
-                    self._partials_ptr,
-                    self._sums_dev_ptr[si],
-                    self._sums_host_ptr[si] if want_host else 0,
-                    self._ov_ws_ptr if use_ov else 0,
-                    self._cap,
-                    self.overlap_k if use_ov else 0,
-                    self._sites_c if (do_sums and self.compute_struct) else None,
-                    len(self.mol_sites) if (do_sums and self.compute_struct) else 0,
-                    float(self.distance) if self.distance is not None else 0.0,
-                    self.struct_mode,
-                    *self._inc_args(inc_sets),
-                    step_flags,
-                    main.cuda_stream,
-                )
-            )
-            self._desc_ring.release(ri, main)
-            isf_host = None
-            if do_sums and self.compute_isf:
-                _lib.check(
-                    lib.sdb_isf_origins(
-                        self._desc_dev_ptr[ri], n_active, self.n, self.stride, float(self.wave_number),
-                        self.angular_resolution, self._isf_dev[si].data_ptr(), _lib.stream_ptr(self.device),
-                    )
-                )
-                if want_host:
-                    self._isf_host[si][:n_active].copy_(self._isf_dev[si][:n_active], non_blocking=True)
-                    isf_host = self._isf_host[si].numpy()[:n_active]
-            if self._staged_slot is not None:
-                consumed = torch.cuda.Event()
-                consumed.record(main)
-                self._dev_consumed[self._staged_slot] = consumed
-            event = None
-            if want_host:
-                event = self._sums_ring.release(si, main)
-                self.d2h_bytes = n_active * SDB_NSUM * 8
-
-            # ---- bookkeeping -------------------------------------------------------------------
-            if not zero_step:
-                if fast:
-                    # the per-origin records are brought up to date lazily (_flush_plan)
-                    plan["steps"] += 1
-                    plan["timestep"] = int(timestep)
-                    new_prev.refs += n_active
-                    self._release_many(plan["prev"], n_active)
-                    plan["prev"] = new_prev
-                else:
-                    for org, td in zip(ordered, timediffs):
-                        self._release(org.prev)
-                        org.prev = new_prev
-                        org.updates += 1
-                        if td > org.max_timediff:
-                            org.max_timediff = td
-                    new_prev.refs += n_active
-                    # a plan for the next frame: valid if the same origins come again
-                    if len({id(o) for o in ordered}) == n_active:
-                        plan_odesc = odesc.copy()
-                        plan_sdesc_rows = []
-                        target_blocks = 148 * 16
-                        blocks_per_segment = (self._n_parts + 3) // 4
-                        size = max(8, math.ceil(n_active * blocks_per_segment / target_blocks))
-                        size = math.ceil(n_active / math.ceil(n_active / size))  # equal shares
-                        flags = 0 if quat is not None else SEG_NO_ROTATION
-                        for first in range(0, n_active, size):
-                            plan_sdesc_rows.append((0, first, min(size, n_active - first), flags, 0))
-                        by_key = {org.key: org for org in ordered}
-                        plan_order = [by_key[k] for k in active]
-                        order_ptrs = np.array([org.ptrs for org in plan_order], dtype=np.uint64)
-                        plan_odesc["d_delta"], plan_odesc["d_flags"], plan_odesc["d_status"] = (
-                            order_ptrs[:, 0], order_ptrs[:, 1], order_ptrs[:, 2],
-                        )
-                        self._plan = {
-                            "active": list(active),
-                            "ordered": plan_order,
-                            "odesc": plan_odesc,
-                            "t0": np.fromiter((org.timestep for org in plan_order), dtype=np.int64, count=n_active),
-                            "sdesc": np.array(plan_sdesc_rows, dtype=SEGMENT_DTYPE),
-                            "seg_count_max": max(r[2] for r in plan_sdesc_rows),
-                            "prev": new_prev,
-                            "has_quat": quat is not None,
-                            "timestep": int(timestep),
-                            # every origin's largest time difference so far is the current one: from here
-                            # on a later timestep is later for every origin (relaxations.py:215-218)
-                            "monotone": all(t >= org.max_timediff for org, t in zip(ordered, timediffs)),
-                            "steps": 0,
-                            "ov_steps": 0,
-                        }
-                self.frames_seen += 1
-                self.updates += n_active * self.n
-
-        keys = [org.key for org in ordered]
+        ids = self._key_ids(active, timestep)
+        f = self._frame
+        f.timestep = timestep
+        f.keys = ctypes.addressof(ids)
+        f.n_keys = n_active
+        flags = 0
+        keep = None
+        if zero_step:
+            flags |= _lib.SDB_FRAME_ZERO_STEP
+            f.pos = f.quat = None
+            f.where = _lib.SDB_MEM_DEVICE
+        else:
+            pos_ptr, quat_ptr, kind, keep = self._frame_pointers(position, orientation)
+            f.pos, f.quat, f.where = pos_ptr, quat_ptr or None, kind
+        if not do_sums:
+            flags |= _lib.SDB_FRAME_NO_SUMS
         if not to_host:
-            # device-resident result (multi-GPU gather path): valid until ring_depth further steps
-            return keys, timediffs, (sums_dev[:n_active] if do_sums else None)
-        sums_host = sums_pinned.numpy()[:n_active] if do_sums else None
-        return StepResult(self, keys, timediffs, sums_host, event, isf_host)
+            flags |= _lib.SDB_FRAME_ROWS_DEVICE
+        f.flags = flags
+        f.d_rows_out = rows_out or None
+
+        # results about to lose their ring slot are copied out first
+        out = self._outstanding
+        horizon = self._next_ticket - self.ring_depth
+        while out and out[0][0] <= horizon:
+            _, ref = out.popleft()
+            res = ref()
+            if res is not None:
+                res._materialize()
+        stream = 0 if self._dry else _lib.stream_ptr(self.device)
+        ticket = int(self.lib.sdb_engine_step(self._handle, ctypes.byref(f), stream))
+        if ticket < 0:
+            message = self.lib.sdb_last_error().decode()
+            self._forget_failed_keys(active)
+            if "time difference" in message:
+                raise OverflowError(message)
+            raise _lib.SdbError(f"libsdb200 error {ticket}: {message}")
+        self._next_ticket = ticket + 1
+        if keep is not None and self.torch is not None and isinstance(keep[0], self.torch.Tensor) and not keep[0].is_cuda:
+            # pinned host tensors are read by the copy stream after this call returns
+            self._keepalive.append(keep)
+            if len(self._keepalive) > self.ring_depth + 1:
+                self._keepalive.popleft()
+        if not to_host:
+            timediffs = [timestep - self._t0[k] for k in active]
+            rows = None
+            if do_sums and not self._dry and not rows_out:  # (with rows_out the rows are already where they belong)
+                d_rows = ctypes.c_void_p()
+                perm = (ctypes.c_int32 * n_active)()
+                _lib.check(self.lib.sdb_engine_device_rows(self._handle, ticket, ctypes.byref(d_rows), perm))
+                rows = self.torch.as_tensor(_CudaArray(d_rows.value, (n_active, SDB_NSUM), "<f8"), device=self.device)
+                order = list(perm)
+                if order != list(range(n_active)):
+                    rows = rows[self.torch.tensor(order, device=self.device)]
+            return active, timediffs, rows
+        result = StepResult(self, active, timestep, ticket, do_sums, do_sums and self.compute_isf)
+        out.append((ticket, weakref.ref(result)))
+        return result
+
+    def run(self, frames, *, want_sums=True):
+        """A batch of frames in ONE native call (``sdb_engine_run``): ``frames`` is a sequence of
+        ``(timestep, position, orientation, active)`` with host arrays (numpy, memory-mapped or pinned) or
+        device tensors.  Returns one :class:`StepResult`-like table per frame, already on the host.  This is
+        the loop of ``read/_read.py:128-168`` with no Python between the frames."""
+        frames = list(frames)
+        count = len(frames)
+        if count == 0:
+            return []
+        arr = (_lib.SdbFrame * count)()
+        keep, key_arrays, actives = [], [], []
+        total = 0
+        for i, (timestep, position, orientation, active) in enumerate(frames):
+            active = list(active)
+            ids = self._key_ids(active, int(timestep))
+            pos_ptr, quat_ptr, kind, alive = self._frame_pointers(position, orientation)
+            keep.append((alive, position, orientation))
+            key_arrays.append(ids)
+            actives.append(active)
+            f = arr[i]
+            f.timestep = int(timestep)
+            f.pos, f.quat, f.where = pos_ptr, quat_ptr or None, kind
+            f.flags = 0 if (want_sums and self.compute_sums) else _lib.SDB_FRAME_NO_SUMS
+            f.keys, f.n_keys = ctypes.addressof(ids), len(active)
+            f.d_rows_out = None
+            total += len(active)
+        for _, ref in self._outstanding:
+            res = ref()
+            if res is not None:
+                res._materialize()
+        self._outstanding.clear()
+        sums = np.zeros((max(total, 1), SDB_NSUM), dtype=np.float64)
+        isf = np.zeros(max(total, 1), dtype=np.float64) if self.compute_isf else None
+        stream = 0 if self._dry else _lib.stream_ptr(self.device)
+        rc = self.lib.sdb_engine_run(self._handle, arr, count, sums.ctypes.data, None, isf.ctypes.data if isf is not None else None, stream)
+        self._next_ticket += count
+        if rc != 0:
+            message = self.lib.sdb_last_error().decode()
+            for active in actives:
+                self._forget_failed_keys(active)
+            if "time difference" in message:
+                raise OverflowError(message)
+            raise _lib.SdbError(f"libsdb200 error {rc}: {message}")
+        del keep, key_arrays
+        results, off = [], 0
+        for (timestep, _, _, _), active in zip(frames, actives):
+            res = StepResult(self, active, int(timestep), None, True, False)
+            res._sums = sums[off : off + len(active)]
+            res._isf = isf[off : off + len(active)] if (isf is not None and want_sums) else None
+            results.append(res)
+            off += len(active)
+        return results
 
     # ------------------------------------------------------------------------------------------
     def finalize_rows(self, sums, timediffs, check=True, strict=True):
@@ -893,10 +761,31 @@ class DynamicsEngine:
         )
 
     # ------------------------------------------------------------------------------------------
+    def stats(self):
+        st = _lib.SdbEngineStats()
+        _lib.check(self.lib.sdb_engine_stats(self._handle, ctypes.byref(st)))
+        return st
+
+    h2d_bytes = property(lambda self: int(self.stats().h2d_bytes))
+    d2h_bytes = property(lambda self: int(self.stats().d2h_bytes))
+    frames_seen = property(lambda self: int(self.stats().frames))
+    updates = property(lambda self: int(self.stats().updates))
+    _inc_ws = property(lambda self: self.stats().d_inc_ws or None)
+
+    def last_descriptors(self):
+        """(origin records, segment records) of the last step as numpy struct arrays (test hook)."""
+        n_org, n_seg, seg_off = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        size = self.lib.sdb_engine_last_descriptors(self._handle, None, 0, ctypes.byref(n_org), ctypes.byref(n_seg), ctypes.byref(seg_off))
+        buf = np.zeros(max(seg_off.value + 24 * n_seg.value, 1), dtype=np.uint8)
+        self.lib.sdb_engine_last_descriptors(self._handle, buf.ctypes.data, buf.nbytes, None, None, None)
+        del size
+        origins = buf[: 32 * n_org.value].view(ORIGIN_DTYPE).copy()
+        segments = buf[seg_off.value : seg_off.value + 24 * n_seg.value].view(SEGMENT_DTYPE).copy()
+        return origins, segments
+
     def delta_arrays(self, key):
         """(delta_translation (N,3), delta_rotation (N,3)) of one origin as host arrays."""
-        org = self.origins[key]
-        planes = org.delta[:, : self.n].cpu().numpy()
+        planes = self.origins[key].delta[:, : self.n].cpu().numpy()
         trans = np.zeros((self.n, 3), dtype=F32)
         rot = np.zeros((self.n, 3), dtype=F32)
         trans[:, 0], trans[:, 1], rot[:, 0] = planes[0], planes[1], planes[2]
@@ -905,14 +794,11 @@ class DynamicsEngine:
     def norms(self, key):
         """(|dr|, |dtheta|) per molecule, computed on the device."""
         torch = self.torch
-        org = self.origins[key]
-        with torch.cuda.device(self.device):
+        ptr = self.origins[key].ptrs[0]
+        with _lib.device_context(self.device):
             out = torch.empty((2, self.n), dtype=torch.float32, device=self.device)
             _lib.check(
-                self.lib.sdb_dyn_norms(
-                    org.delta.data_ptr(), self.n, self.stride, out[0].data_ptr(), out[1].data_ptr(),
-                    _lib.stream_ptr(self.device),
-                )
+                self.lib.sdb_dyn_norms(ptr, self.n, self.stride, out[0].data_ptr(), out[1].data_ptr(), _lib.stream_ptr(self.device))
             )
             host = out.cpu().numpy()
         return host[0], host[1]
@@ -940,12 +826,11 @@ class DynamicsEngine:
 
     def overlap_stats(self, n_active):
         """(origins that needed the exact kernel, candidates per origin) of the last step (diagnostics)."""
+        st = self.stats()
         out = np.zeros(1 + n_active, dtype=np.uint32)
-        with self.torch.cuda.device(self.device):
+        with _lib.device_context(self.device):
             _lib.check(
-                self.lib.sdb_overlap_stats(
-                    self._ov_ws.data_ptr(), self._cap, self.n, n_active, out.ctypes.data, _lib.stream_ptr(self.device)
-                )
+                self.lib.sdb_overlap_stats(st.d_ov_ws, st.capacity, self.n, n_active, out.ctypes.data, _lib.stream_ptr(self.device))
             )
         return int(out[0]), out[1:]
 

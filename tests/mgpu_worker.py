@@ -41,10 +41,10 @@ def main():
     def sharded_run(mode):
         engine = DynamicsEngine(n, box_for(n), WAVE_NUMBER, mol_sites=Trimer().positions, device=device)
 
-        def step_fn(ts, pos, quat, keys):
-            return engine.step(ts, pos, quat, keys, to_host=False)
+        def step_fn(ts, pos, quat, keys, rows_out=0):
+            return engine.step(ts, pos, quat, keys, to_host=False, rows_out=rows_out)
 
-        sharded = ShardedDynamics(n, step_fn, max_local=16, device=device, batch=16)
+        sharded = ShardedDynamics(n, step_fn, max_local=16, device=device, batch=16, direct_rows=True)
         rows = []
         for indexes, frame in frames:
             if mode == "sliced":  # every rank holds the frame in host memory and uploads its slice
