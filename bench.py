@@ -1,20 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the per-frame dynamics hot path (BASELINE.json: molecule*origin updates/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--regime aged|early|both]
 
 Workload (BASELINE.json configs[3], the configuration the target is quoted on): synthetic 2D Trimer
-liquid, 1,000,000 molecules, 200 time-origins, dense (linear) schedule in its steady state -- every
-frame updates all 200 origins (Dynamics.compute_all + Relaxations.add each).  A *step* is one frame:
-200 x 1e6 molecule*origin updates.  With N GPUs the 200 origins are sharded round-robin over the
-ranks and each frame is broadcast from rank 0 over NCCL (strong scaling: total work is fixed).
+liquid, 1,000,000 molecules, 200 time-origins, dense (linear) schedule -- every frame updates all 200
+origins (Dynamics.compute_all + Relaxations.add each).  A *step* is one frame: 200 x 1e6
+molecule*origin updates.  With N GPUs the 200 origins are sharded round-robin over the ranks and each
+frame reaches every rank over NVLink (strong scaling: total work is fixed).
 
-* ``value``  frames already resident in HBM (rank 0) when the timed region starts.
-* ``e2e``    the same loop through the public host API with frames in pinned HOST memory: the H2D
-             copy of every frame and the D2H read of its result rows are inside the timed region.
+Two regimes of that workload are timed (``regimes`` in the JSON line; ``--headline`` picks ``value``):
+
+* ``aged``   (headline) origins created 10 timesteps apart, i.e. aged 0 ... 2000 steps like in the last
+             frames of the 2000-frame run: |dr| is of the order of the relaxation distance, `struct` ~ 0.5,
+             passage trackers fire continuously.
+* ``early``  origins aged 1 ... 225 steps (round 1's only regime): almost nothing is near a threshold.
+
+* ``value``  frames already resident in HBM when the timed region starts.  The K-step region (barrier +
+             synchronize on both sides) is repeated until >= 1 s has been timed; ``value`` is the median.
+* ``e2e``    the same loop fed from a GSD trajectory FILE through the package's reader (mmap -> pinned
+             staging -> H2D copy per frame) and the public engine API, rows read back to the host.
 * ``roofline``      dominant kernel (``dyn_step_kernel``) timed with CUDA events on its stream.
+* ``parity``        rows and per-molecule state of two aged origins of THIS run against the CPU oracle.
 * ``cpu_baseline``  the CPU oracle (a numpy restatement of the reference; the reference itself cannot
-             run here: freud/rowan/gsd are not installed) on a bounded sample, one core.
+             run here: freud/rowan/gsd are not installed) on the same frames, one core.
+* ``configs``       BASELINE.json configs[1] (32 k molecules, log-spaced and linear schedules) and configs[2]
+             (neighbours + orientational order + num_neighbours per frame) as sub-records (1 GPU only).
 * ``--impl reference``  the CPU arm alone: origin-parallel oracle processes on all host cores.
 """
 
@@ -39,9 +50,11 @@ N_ORIGINS = 200
 WAVE_NUMBER = 2.9
 PIPELINE = int(os.environ.get("SDB_BENCH_PIPELINE", "2"))  # frames in flight before the oldest result is read
 SIGMA_R, SIGMA_T = 0.01, 0.02
+POOL = int(os.environ.get("SDB_BENCH_POOL", "16"))  # distinct frames of the measured steps (walked back and forth)
+AGE_STRIDE = {"aged": 10, "early": 1}
 WORKLOAD = (
     "configs[3]: synthetic 2D Trimer liquid, 1M molecules, 200 time-origins, dense linear schedule "
-    "(steady state: all origins active every frame), Dynamics.compute_all + Relaxations.add"
+    "(all origins active every frame), Dynamics.compute_all + Relaxations.add"
 )
 
 
@@ -52,14 +65,23 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _ncu_traffic(kernel, updates):
-    """DRAM bytes per launch of ``kernel`` from the committed ncu capture, scaled to ``updates`` per launch."""
+def _ncu_traffic(regime, kernel, updates):
+    """DRAM bytes per launch of ``kernel`` from the committed ncu capture of ``regime``, scaled to ``updates``."""
     path = REPO / "profiles" / "ncu_traffic.json"
     try:
-        rec = json.loads(path.read_text())[kernel]
-        return (rec["dram_bytes_read"] + rec["dram_bytes_write"]) * updates / rec["updates_in_launch"]
+        rec = json.loads(path.read_text())[regime][kernel]
+        return (rec["dram_bytes_read"] + rec["dram_bytes_write"]) * updates / rec["updates_in_launch"], rec.get("source")
     except (OSError, KeyError, ValueError):
-        return None
+        return None, None
+
+
+def pingpong(i, p):
+    """0, 1, ..., p-1, p-2, ..., 1, 0, 1, ...: consecutive frames of the pool are one walk step apart."""
+    if p <= 1:
+        return 0
+    period = 2 * (p - 1)
+    j = i % period
+    return j if j < p else period - j
 
 
 class ClockSampler:
@@ -164,8 +186,9 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
     n_mols = args.molecules
-    # bounded sample: every step is one frame of `workers` origins (of the 200) at full N
-    steps, warmup = min(args.steps, 6), min(args.warmup, 1)
+    # every step is one frame of `workers` origins (of the 200) at full N: a bounded sample of the workload,
+    # per-origin cost being independent of the other origins; --steps / --warmup as given
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
     value, ms = cpu_arm(n_mols, workers, steps, warmup)
     sample = (
         f"{steps} timed frames x {workers} of {N_ORIGINS} origins at N={n_mols} "
@@ -189,6 +212,8 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    import ctypes
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -213,278 +238,355 @@ def run_gpu(args):
     from sdanalysis_b200 import _lib
     from sdanalysis_b200.distributed import ShardedDynamics, partition
     from sdanalysis_b200.engine import DynamicsEngine
+    from sdanalysis_b200.gsdio import GSDWriter, open_gsd
     from sdanalysis_b200.molecules import Trimer
-    from sdanalysis_b200.synthetic import SyntheticTrimer
+    from sdanalysis_b200.synthetic import SyntheticTrimer, box_for
 
+    lib = _lib.load()
     n, n_origins = args.molecules, args.origins
     steps, warmup = args.steps, max(args.warmup, 3)
     all_keys = list(range(n_origins))
     local_keys = partition(all_keys, rank, world)
-
-    from sdanalysis_b200.synthetic import box_for
-
-    def make_engine():
-        return DynamicsEngine(n, box_for(n), WAVE_NUMBER, mol_sites=Trimer().positions, device=device, ring_depth=PIPELINE + 2)
-
-    # after the timed region a few more steps run with per-kernel-group CUDA events (sdb_profile_*) for the
-    # roofline: with the events in place the library serialises the kernels it otherwise overlaps
+    peak, peak_kind = _peaks()
+    pool_size = max(2, min(POOL, 4096))
     prof_steps = max(2, min(steps, 8))
-    n_frames = warmup + steps + prof_steps
+    want_parity = args.parity == "on" or (args.parity == "auto" and world == 1 and not args.no_cpu_baseline)
+    if n_origins < 3:
+        want_parity = False
 
-    def phase(host_frames):
-        """Create the origins (untimed), then W warm-up + K timed steps.  Returns timing info."""
-        engine = make_engine()
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(value):
+        if world == 1:
+            return value
+        t = torch.tensor([value], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def summary(times):
+        ordered = sorted(times)
+        return {
+            "regions": len(times), "median_ms": statistics.median(times), "min_ms": ordered[0], "max_ms": ordered[-1],
+            "p10_ms": ordered[int(0.1 * (len(times) - 1))], "p90_ms": ordered[int(0.9 * (len(times) - 1) + 0.5)],
+            "timed_seconds": sum(times) / 1e3,
+        }
+
+    def measure(regime, with_parity):
+        """Create the origins of ``regime`` (untimed), then time the device-resident loop, the kernel groups and
+        the end-to-end loop fed from a GSD file.  Returns a dict of measurements."""
+        age_stride = AGE_STRIDE[regime]
+        engine = DynamicsEngine(n, box_for(n), WAVE_NUMBER, mol_sites=Trimer().positions, device=device, ring_depth=PIPELINE + 2)
         sharded = None
         if world > 1:
             def step_fn(ts, pos, quat, keys, rows_out=0):
                 return engine.step(ts, pos, quat, keys, to_host=False, rows_out=rows_out)
 
-            sharded = ShardedDynamics(n, step_fn, max_local=len(local_keys) + 1, device=device, batch=n_frames + 1, direct_rows=True)
-        # origin creation: origin k starts at frame k (linear schedule, keyframe_interval = 1)
-        timestep = 0
-        # frames: a random walk generated on rank 0's GPU
-        # (several GPUs: every rank runs the same seeded walk on its own device, so that the frames of the
-        # device-resident phase can be held sharded by rows -- rank r keeps rows slice_bounds(r) of each frame)
+            sharded = ShardedDynamics(
+                n, step_fn, max_local=len(local_keys) + 1, device=device, batch=max(steps, warmup, prof_steps, 25 * steps) + 1,
+                direct_rows=True,
+            )
+        # every rank runs the same seeded walk on its own device (the frames of the device-resident phase are
+        # held sharded by rows when there are several ranks)
         walk = SyntheticTrimer(n, seed=4, sigma_r=SIGMA_R, sigma_theta=SIGMA_T, device=device)
-        sharded_resident = (
-            world > 1 and not host_frames and sharded.exchange == "multicast" and bool(getattr(sharded, "_mc_ptr", 0))
-            and n % (4 * world) == 0 and os.environ.get("SDB_BENCH_RESIDENT", "sharded") == "sharded"
-        )
+        box = walk.box
+        sparse = {0, 1} if with_parity else set()  # the two origins followed by the oracle see few frames while they age
+        oracle_frames = []  # (timestep, pos, quat, origins of `sparse` taking part) in order, host copies on rank 0
+        timestep = 0
         for k in range(n_origins):
-            active = all_keys[: k + 1]
+            last = k == n_origins - 1
+            active = [j for j in range(k + 1) if j not in sparse or j == k or last]
+            pos, quat = walk.frame()
             if world > 1:
-                h = sharded.post_frame(*(walk.frame() if rank == 0 else (None, None)))
+                h = sharded.post_frame(*((pos, quat) if rank == 0 else (None, None)))
                 sharded.step(timestep, active, h, gather=False)
             else:
-                pos, quat = walk.frame()
                 engine.step(timestep, pos, quat, active, want_sums=False)
-            walk.advance(args.age_stride)
-            timestep += args.age_stride
+            followed = [j for j in active if j in sparse]
+            if followed and rank == 0:
+                oracle_frames.append((timestep, pos.cpu().numpy(), quat.cpu().numpy(), followed))
+            walk.advance(age_stride)
+            timestep += age_stride
         torch.cuda.synchronize()
-        # the frames of the measured steps
-        frames = []
-        shared_host = host_frames and world > 1
-        if shared_host:
-            # e2e with several GPUs: the frames sit in page-locked HOST memory that every rank can read
-            # (a shared mapping, like a memory-mapped trajectory file); each rank uploads its 1/R slice
-            # over its own PCIe link inside the timed region and multicasts it to all ranks over NVLink
-            path = f"/dev/shm/sdb_bench_{os.environ.get('MASTER_PORT', '0')}.bin"
-            per_frame = 7 * n
-            if rank == 0:
-                mm = np.lib.format.open_memmap(path, mode="w+", dtype=np.float32, shape=(n_frames, per_frame))
-                for i in range(n_frames):
-                    pos, quat = walk.frame()
-                    walk.advance(1)
-                    mm[i, : 3 * n] = pos.cpu().numpy().reshape(-1)
-                    mm[i, 3 * n :] = quat.cpu().numpy().reshape(-1)
-                mm.flush()
-                del mm
-            dist.barrier()
-            mm = np.load(path, mmap_mode="r+")
-            shared = torch.from_numpy(mm)
-            rc = torch.cuda.cudart().cudaHostRegister(shared.data_ptr(), shared.numel() * 4, 0)
-            assert int(rc) == 0, f"cudaHostRegister failed: {rc}"
-            frames = [(shared[i, : 3 * n].view(n, 3), shared[i, 3 * n :].view(n, 4)) for i in range(n_frames)]
-        elif sharded_resident:
-            lo, hi = sharded.slice_bounds()
-            for _ in range(n_frames):
-                pos, quat = walk.frame()
-                walk.advance(1)
-                frames.append((pos[lo:hi].clone(), quat[lo:hi].clone()))
-        elif rank == 0:
-            for _ in range(n_frames):
-                pos, quat = walk.frame()
-                walk.advance(1)
-                if host_frames:
-                    frames.append((pos.cpu().pin_memory(), quat.cpu().pin_memory()))
-                else:
-                    frames.append((pos.clone(), quat.clone()))
-        else:
-            frames = [(None, None)] * n_frames
+        t_first = timestep  # timestep of measured step 0
+
+        # ---- the frames of the measured steps: a pool walked back and forth ---------------------------------
+        sharded_resident = (
+            world > 1 and sharded.exchange == "multicast" and bool(getattr(sharded, "_mc_ptr", 0))
+            and os.environ.get("SDB_BENCH_RESIDENT", "sharded") == "sharded"
+        )
+        lo, hi = sharded.slice_bounds() if sharded is not None else (0, n)
+        pool_dev, pool_host = [], []
+        tag = os.environ.get("MASTER_PORT", str(os.getpid())) if world > 1 else str(os.getpid())
+        gsd_path = Path(args.tmpdir) / f"sdb_bench_{tag}_{regime}.gsd"
+        writer = GSDWriter(gsd_path) if (rank == 0 and not args.no_e2e) else None
+        for j in range(pool_size):
+            pos, quat = walk.frame()
+            if sharded_resident:
+                pool_dev.append((pos[lo:hi].clone(), quat[lo:hi].clone()))
+            elif world == 1 or rank == 0:
+                pool_dev.append((pos.clone(), quat.clone()))
+            else:
+                pool_dev.append((None, None))
+            if rank == 0 and (writer is not None or (with_parity and j <= warmup)):
+                hp, hq = pos.cpu().numpy(), quat.cpu().numpy()
+                if writer is not None:
+                    writer.append(t_first + j, box, hp, hq, dimensions=2)
+                if with_parity and j <= warmup:
+                    pool_host.append((hp, hq))
+            walk.advance(1)
+        if writer is not None:
+            writer.close()
         torch.cuda.synchronize()
+        barrier()
 
-        results = []
+        # ---- stepping ---------------------------------------------------------------------------------------
+        state = {"i": 0}  # index of the next measured step
+        results, tables, posted = [], [], {}
+        keep_tables = warmup + 1 if with_parity else 0
+        trj = {"gsd": None}
 
-        posted = {}
+        def frame_of(source, i):
+            if source == "gsd":
+                snap = trj["gsd"][pingpong(i, pool_size)]
+                return snap.position, snap.orientation
+            return pool_dev[pingpong(i, pool_size)]
 
-        def one_step(i, ts):
+        def collect(item):
+            i, res = item
+            table = res.table()
+            if i < keep_tables:
+                tables.append((i, table))
+            return table
+
+        def one_step(source):
+            i = state["i"]
+            state["i"] = i + 1
+            ts = t_first + i
             if world > 1:
-                # software pipeline: the exchange of frame i + 1 is enqueued (side stream) before the
-                # kernels of frame i, so it overlaps them
-                post = sharded.post_frame_sliced if (shared_host or sharded_resident) else sharded.post_frame
+                # software pipeline: the exchange of frame i + 1 is enqueued (side stream) before the kernels of
+                # frame i, so it overlaps them
+                post = sharded.post_frame_sliced if (source == "gsd" or sharded_resident) else sharded.post_frame
                 if i not in posted:
-                    posted[i] = post(*frames[i])
-                if i + 1 < n_frames:
-                    posted[i + 1] = post(*frames[i + 1])
-                # rows stay on the device; one gather per batch of frames (and at the end of the region)
+                    posted[i] = post(*frame_of(source, i))
+                posted[i + 1] = post(*frame_of(source, i + 1))
                 sharded.step(ts, all_keys, posted.pop(i), gather="batch")
                 return
-            pos, quat = frames[i]
-            results.append(engine.step(ts, pos, quat, all_keys))
+            pos, quat = frame_of(source, i)
+            results.append((i, engine.step(ts, pos, quat, all_keys)))
             if len(results) > PIPELINE:
-                results.pop(0).table()
+                collect(results.pop(0))
 
         def drain():
             last = None
             if world > 1:
                 flushed = sharded.flush()
-                if flushed:
-                    keys, timediffs, sums = flushed[-1]
-                    last = engine.finalize_table(sums, timediffs)
+                first_i = state["i"] - len(flushed)
+                for off, (keys, timediffs, sums) in enumerate(flushed):
+                    if first_i + off < keep_tables or off == len(flushed) - 1:
+                        last = engine.finalize_table(sums, timediffs)
+                        last["keyframe"] = list(keys)
+                        if first_i + off < keep_tables:
+                            tables.append((first_i + off, last))
                 return last
             while results:
-                last = results.pop(0).table()
+                last = collect(results.pop(0))
             return last
 
-        for i in range(warmup):
-            one_step(i, timestep)
-            timestep += 1
-        drain()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        lib = _lib.load()
+        def block(source, count):
+            """`count` steps bracketed by barrier + synchronize on both sides; ms as the max over ranks."""
+            barrier()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            h0 = time.perf_counter()
+            for _ in range(count):
+                one_step(source)
+            host_ms = 1e3 * (time.perf_counter() - h0) / count
+            last = drain()
+            t1.record()
+            torch.cuda.synchronize()
+            return max_over_ranks(t0.elapsed_time(t1)), host_ms, last
+
+        def timed(source, min_seconds):
+            """Repeat the K-step region until >= min_seconds have been timed (at least 3, at most 400 regions)."""
+            times, host = [], []
+            last = None
+            while True:
+                ms, host_ms, last = block(source, steps)
+                times.append(ms)
+                host.append(host_ms)
+                if (len(times) >= 3 and sum(times) >= 1e3 * min_seconds) or len(times) >= 400:
+                    break
+            return times, host, last
+
+        # device-resident phase
+        block("dev", warmup)
+        snapshots = {}
+        if with_parity:
+            torch.cuda.synchronize()
+            for key in sparse:
+                if key in local_keys:
+                    org = engine.origins[key]
+                    snapshots[key] = (org.delta.clone(), org.flags.clone(), org.status.clone())
         launches0 = _lib.launch_count()
         sampler = ClockSampler(local_rank) if rank == 0 else None
-        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        cuprof = os.environ.get("SDB_BENCH_CUPROFILE") == "1" and not host_frames
-        if cuprof:  # `ncu --profile-from-start off`: the launch list then holds exactly the timed region
+        cuprof = os.environ.get("SDB_BENCH_CUPROFILE") == "1"
+        if cuprof:  # `ncu --profile-from-start off`: the capture then holds the timed regions only
             torch.cuda.cudart().cudaProfilerStart()
-        t_start.record()
-        host_t0 = time.perf_counter()
-        pyprof = None
-        if os.environ.get("SDB_BENCH_PYPROFILE") == "1" and rank == 0:
-            import cProfile
-
-            pyprof = cProfile.Profile()
-            pyprof.enable()
-        shard_prof = os.environ.get("SDB_SHARD_PROFILE") == "1"
-        step_events, host_marks = [], []
-        for i in range(steps):
-            one_step(warmup + i, timestep)
-            timestep += 1
-            if shard_prof:  # diagnostics: device time and host time of every step
-                ev = torch.cuda.Event(enable_timing=True)
-                ev.record()
-                step_events.append(ev)
-                host_marks.append(time.perf_counter())
-        if pyprof is not None:
-            import pstats
-
-            pyprof.disable()
-            pstats.Stats(pyprof, stream=sys.stderr).sort_stats("tottime").print_stats(35)
-        host_ms = 1e3 * (time.perf_counter() - host_t0) / steps
-        drain_t0 = time.perf_counter()
-        last_rows = drain()
-        t_end.record()
-        torch.cuda.synchronize()
-        if shard_prof and len(step_events) > 2:
-            dev_ms = sorted(a.elapsed_time(b) for a, b in zip(step_events[:-1], step_events[1:]))
-            host_ms_l = sorted(1e3 * (b - a) for a, b in zip(host_marks[:-1], host_marks[1:]))
-            print(f"[rank {rank}] host_frames={host_frames} per-step device interval ms: median {dev_ms[len(dev_ms)//2]:.3f} "
-                  f"p90 {dev_ms[int(0.9*len(dev_ms))]:.3f} max {dev_ms[-1]:.3f}; host interval: median {host_ms_l[len(host_ms_l)//2]:.3f} "
-                  f"p90 {host_ms_l[int(0.9*len(host_ms_l))]:.3f} max {host_ms_l[-1]:.3f}; first-step-to-start {t_start.elapsed_time(step_events[0]):.3f} "
-                  f"drain (host) {1e3*(time.perf_counter()-drain_t0):.3f} ms, last step to end {step_events[-1].elapsed_time(t_end):.3f} ms",
-                  file=sys.stderr, flush=True)
+        dev_times, dev_host, last_table = timed("dev", args.min_seconds)
         if cuprof:
             torch.cuda.cudart().cudaProfilerStop()
-        if world > 1:
-            dist.barrier()
         clocks = sampler.stop() if sampler else None
-        ms = t_start.elapsed_time(t_end)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        launches = _lib.launch_count() - launches0
-        import ctypes
+        launches = (_lib.launch_count() - launches0) // len(dev_times)
+        # one long region (no per-region synchronisation): what a long run sustains
+        n_sustained = min(len(dev_times), 25) * steps
+        sustained_ms, _, _ = block("dev", n_sustained)
 
-        # ---- kernel timing pass (untimed for `value`): per-kernel-group CUDA events, kernels serialised
-        lib.sdb_profile_collect(None, None, None)  # drop anything collected so far
+        # kernel timing pass: per-kernel-group CUDA events, kernels serialised
+        lib.sdb_profile_collect(None, None, None)
         lib.sdb_profile_enable(1)
-        for i in range(prof_steps):
-            one_step(warmup + steps + i, timestep)
-            timestep += 1
-        drain()
-        torch.cuda.synchronize()
+        block("dev", prof_steps)
         group_ms = (ctypes.c_double * 4)()
         n_steps, n_origin_steps = ctypes.c_int64(0), ctypes.c_int64(0)
         lib.sdb_profile_enable(0)
         _lib.check(lib.sdb_profile_collect(group_ms, ctypes.byref(n_steps), ctypes.byref(n_origin_steps)))
-        if world > 1:
-            dist.barrier()
         count = max(int(n_steps.value), 1)
         kern = {
-            "dyn": group_ms[1], "struct": group_ms[2], "overlap": group_ms[0] + group_ms[3], "count": count,
+            "dyn": group_ms[1] / count, "struct": group_ms[2] / count, "overlap": (group_ms[0] + group_ms[3]) / count,
             "origins": int(n_origin_steps.value) // count,
         }
-        if sharded is not None and sharded.stalls:
-            import time as _t
-            st = [a.elapsed_time(b) for a, b in sharded.stalls[-steps:]]
-            xt = [a.elapsed_time(b) for a, b in sharded.exchange_times[-steps:]]
-            print(f"[rank {rank}] host_frames={host_frames} frame-wait stall per step: mean {sum(st)/len(st):.3f} ms max {max(st):.3f} ms; "
-                  f"exchange (side stream) mean {sum(xt)/max(len(xt),1):.3f} ms max {max(xt):.3f}\n", file=sys.stderr, flush=True)
-        h2d, d2h = engine.h2d_bytes, engine.d2h_bytes
-        if world > 1:  # every rank uploads its slice of the frame (28 B per molecule in total); rows leave through rank 0
-            h2d = 28 * n if host_frames else 0
-            d2h = n_origins * 16 * 8
-        if shared_host:
+
+        # end-to-end phase: the same loop fed from the GSD file
+        e2e = None
+        if not args.no_e2e:
+            posted.clear()
+            trj["gsd"] = open_gsd(gsd_path)
+            pinned_file = bool(os.environ.get("SDB_BENCH_PIN_FILE", "1") == "1" and trj["gsd"].pin())
+            block("gsd", warmup)
+            e2e_times, e2e_host, _ = timed("gsd", args.min_seconds)
+            h2d = engine.h2d_bytes if world == 1 else 28 * n
+            d2h = engine.d2h_bytes if world == 1 else n_origins * 16 * 8
+            e2e = {"times": e2e_times, "host_ms": statistics.median(e2e_host), "h2d": h2d, "d2h": d2h, "pinned_file": pinned_file}
+            posted.clear()
             torch.cuda.synchronize()
-            torch.cuda.cudart().cudaHostUnregister(shared.data_ptr())
-            del frames, shared, mm
-            dist.barrier()
+            barrier()
+            trj["gsd"].close()
+        barrier()
+        if rank == 0 and not args.no_e2e:
+            try:
+                os.unlink(gsd_path)
+            except OSError:
+                pass
+
+        # ---- parity of two aged origins of this run against the CPU oracle (and the CPU baseline) ------------
+        parity = cpu = None
+        if with_parity:
+            state_np = {}
+            for key, (delta, flags, status) in snapshots.items():
+                planes = delta[:, :n].cpu().numpy()
+                trans = np.zeros((n, 3), dtype=np.float32)
+                rot = np.zeros((n, 3), dtype=np.float32)
+                trans[:, 0], trans[:, 1], rot[:, 0] = planes[0], planes[1], planes[2]
+                st = status[:, :n].cpu().numpy().view(np.uint32)
+                fl = flags[:n].cpu().numpy()
+                summ = {}
+                for t_i, spec in enumerate(engine.trackers):
+                    col = st[t_i].astype(np.int64)
+                    if spec.last_passage:
+                        col[((fl >> spec.bit) & 3) != 2] = 2 ** 32 - 1
+                    summ[spec.name] = col
+                state_np[key] = (trans, rot, summ)
+            if world > 1:
+                gathered = [None] * world
+                dist.gather_object(state_np, gathered if rank == 0 else None, dst=0)
+                if rank == 0:
+                    state_np = {}
+                    for part in gathered:
+                        state_np.update(part)
             if rank == 0:
-                os.unlink(path)
+                parity, cpu = _oracle_parity(np, n, box, oracle_frames, pool_host, t_first, warmup, tables, state_np, sorted(sparse))
+        exchange = None if sharded is None else sharded.exchange
+        exchange_note = "" if sharded is None else sharded.exchange_note
         del engine, sharded
         torch.cuda.empty_cache()
-        if os.environ.get("SDB_SHARD_PROFILE") == "1":
-            print(f"[rank {rank}] host enqueue time per step {host_ms:.3f} ms", file=sys.stderr, flush=True)
-        return {"ms": ms, "clocks": clocks, "launches": launches, "kern": kern, "h2d": h2d, "d2h": d2h, "rows": last_rows,
-                "sharded_resident": sharded_resident}
+        return {
+            "regime": regime, "dev_times": dev_times, "dev_host_ms": statistics.median(dev_host), "sustained_ms": sustained_ms,
+            "n_sustained": n_sustained, "clocks": clocks, "launches": launches, "kern": kern, "e2e": e2e,
+            "last_table": last_table, "parity": parity, "cpu": cpu, "sharded_resident": sharded_resident,
+            "exchange": exchange, "exchange_note": exchange_note,
+        }
 
-    dev = phase(host_frames=False)
-    e2e = phase(host_frames=True)
-
+    regimes = ["aged", "early"] if args.regime == "both" else [args.regime]
+    if args.regime == "both" and args.headline == "early":
+        regimes = ["early", "aged"]
+    measured = {}
+    for regime in regimes:
+        measured[regime] = measure(regime, with_parity=want_parity and regime == regimes[0])
+    head = measured[regimes[0]]
     updates_per_step = n * n_origins
-    value = updates_per_step * steps / (dev["ms"] * 1e-3)
-    e2e_value = updates_per_step * steps / (e2e["ms"] * 1e-3)
 
-    # ---- roofline of the dominant kernel (this rank's share) --------------------------------------
-    peak, peak_kind = _peaks()
-    a_local = dev["kern"]["origins"]
-    dyn_ms = dev["kern"]["dyn"] / max(dev["kern"]["count"], 1)
-    bytes_per_update = 49.0 + 56.0 / max(a_local, 1)  # SURVEY 8(d), linear (dense) schedule
-    algo_bytes = bytes_per_update * a_local * n
-    achieved = algo_bytes / (dyn_ms * 1e-3) / 1e9 if dyn_ms > 0 else 0.0
-    roofline = {
-        "kernel": "dyn_step_kernel (+ dyn_increments_kernel when the per-frame pass is used)",
-        "timing": f"CUDA events around the kernel group in {prof_steps} extra steps right after the timed region (same data, "
-                  "kernels serialised; in the timed region dyn_step, struct and the overlap resolve of different origin groups overlap)",
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": _ncu_traffic("dyn_step_kernel", a_local * n),
-        "traffic_frac": (
-            (_ncu_traffic("dyn_step_kernel", a_local * n) or 0.0) / (dyn_ms * 1e-3) / 1e9 / peak if dyn_ms > 0 else None
-        ),  # DRAM bytes actually moved / time / peak: what the kernel really draws from HBM
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/ncu_traffic.json), "
-                          "scaled by the updates of this launch",
-        "algorithmic_bytes_per_update": bytes_per_update,
-        "updates_per_launch": a_local * n,
-        "launch_ms": dyn_ms,
-        "peak_source": peak_kind,
-        "other_kernels_ms_per_step": {
-            "struct_kernel": dev["kern"]["struct"] / max(dev["kern"]["count"], 1),
-            "overlap_sample_bracket_resolve": dev["kern"]["overlap"] / max(dev["kern"]["count"], 1),
-        },
-    }
+    def regime_record(m):
+        s = summary(m["dev_times"])
+        a_local = m["kern"]["origins"]
+        dyn_ms = m["kern"]["dyn"]
+        bytes_per_update = 49.0 + 56.0 / max(a_local, 1)  # SURVEY 8(d), linear (dense) schedule
+        achieved = bytes_per_update * a_local * n / (dyn_ms * 1e-3) / 1e9 if dyn_ms > 0 else 0.0
+        traffic, source = _ncu_traffic(m["regime"], "dyn_step_kernel", a_local * n)
+        step_frac = (49.0 + 56.0 / n_origins) * updates_per_step * steps / (s["median_ms"] * 1e-3) / 1e9 / peak / world
+        rec = {
+            "value": updates_per_step * steps / (s["median_ms"] * 1e-3),
+            "ms_per_step": s["median_ms"] / steps,
+            "regions": s,
+            "sustained": {
+                "steps": m["n_sustained"], "ms_per_step": m["sustained_ms"] / m["n_sustained"],
+                "value": updates_per_step * m["n_sustained"] / (m["sustained_ms"] * 1e-3),
+                "note": "one region of this many steps, synchronised only at its ends",
+            },
+            "host_enqueue_ms_per_step": m["dev_host_ms"],
+            "roofline": {
+                "kernel": "dyn_step_kernel (+ dyn_increments_kernel when the per-frame pass is used)",
+                "timing": f"CUDA events around the kernel group in {prof_steps} extra steps right after the timed regions (same "
+                          "state, kernels serialised; in the timed regions dyn_step, struct and the overlap resolve overlap)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic,
+                "traffic_frac": (traffic / (dyn_ms * 1e-3) / 1e9 / peak) if (traffic and dyn_ms > 0) else None,
+                "traffic_source": source,
+                "algorithmic_bytes_per_update": bytes_per_update,
+                "updates_per_launch": a_local * n,
+                "launch_ms": dyn_ms,
+                "peak_source": peak_kind,
+                "other_kernels_ms_per_step": {"struct_kernel": m["kern"]["struct"], "overlap_bracket_resolve": m["kern"]["overlap"]},
+                "step_algorithmic_frac": step_frac,
+                "step_note": "whole step (all kernels" + (", all ranks" if world > 1 else "") + "): algorithmic bytes / time / peak"
+                             + (" / ranks" if world > 1 else ""),
+            },
+            "check": {k: float(m["last_table"][k][0]) for k in ("time", "msd", "alpha", "rot1", "overlap", "struct", "com_struct")}
+            if isinstance(m["last_table"], dict) else None,
+        }
+        if m["e2e"] is not None:
+            es = summary(m["e2e"]["times"])
+            rec["e2e"] = {
+                "value": updates_per_step * steps / (es["median_ms"] * 1e-3), "unit": UNIT, "ms_per_step": es["median_ms"] / steps,
+                "h2d_bytes_per_step": m["e2e"]["h2d"], "d2h_bytes_per_step": m["e2e"]["d2h"], "regions": es,
+                "host_ms_per_step": m["e2e"]["host_ms"],
+                "source": "GSD trajectory file read through sdanalysis_b200.gsdio (mmap) inside the timed region"
+                          + (", file mapping page-locked (cudaHostRegister)" if m["e2e"]["pinned_file"] else
+                             ", frames copied to the engine's pinned ring by its host threads"),
+            }
+        return rec
+
+    records = {r: regime_record(m) for r, m in measured.items()}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    head_rec = records[regimes[0]]
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 runs only) -----------------------------------
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    # ---- CPU baseline -----------------------------------------------------------------------------------
+    cpu = head["cpu"]
+    if cpu is None and world == 1 and not args.no_cpu_baseline:
         sample_steps = 4
         v, _ = cpu_arm(n, 1, sample_steps, 1)
         cpu = {
@@ -492,40 +594,132 @@ def run_gpu(args):
             "sample": f"{sample_steps} (frame, origin) pairs at N={n}: oracle Dynamics.compute_all + Relaxations.add, 1 process",
         }
 
+    # ---- the other BASELINE configurations (one GPU) -------------------------------------------------------------
+    configs = None
+    if world == 1 and not args.no_configs:
+        import bench_configs
+
+        configs = bench_configs.run_all(device, peak, cpu_baseline=not args.no_cpu_baseline)
+
+    if world > 1:
+        if head["exchange"] == "multicast":
+            parallelism = (
+                f"origin-sharded x{world}; frame exchange: multicast stores over NVSwitch into every rank's frame ring"
+                + (" (every rank holds 1/R of the rows of each frame and multicasts them)" if head["sharded_resident"]
+                   else " (from the reader rank)")
+                + "; rows written by every rank straight into rank 0's row buffer (peer copy enqueued by the native step)"
+            )
+        else:
+            parallelism = (
+                f"origin-sharded x{world}; frame exchange: torch.distributed.broadcast (NCCL) -- {head['exchange_note'] or 'requested'}; "
+                "rows gathered once per region (NCCL)"
+            )
+    else:
+        parallelism = "single GPU"
+
+    keep = ("value", "ms_per_step", "regions", "sustained", "host_enqueue_ms_per_step", "e2e", "check")
+    roof_keep = ("frac", "traffic_frac", "launch_ms", "achieved", "other_kernels_ms_per_step", "step_algorithmic_frac")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": dev["ms"] / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "metric": METRIC, "value": head_rec["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": head_rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": WORKLOAD, "molecules": n, "origins": n_origins, "origins_per_gpu": len(local_keys),
-            "parallelism": (
-                f"origin-sharded x{world}, frame pushed to every rank by multicast stores over NVSwitch "
-                + ("(device-resident phase: every rank holds 1/R of the rows of each frame in HBM and multicasts them), "
-                   if dev["sharded_resident"] else "(from the reader rank), ")
-                + "rows gathered once per batch (NCCL)"
-                if world > 1 else "single GPU"
-            ),
+            "workload": WORKLOAD, "regime": regimes[0], "molecules": n, "origins": n_origins, "origins_per_gpu": len(local_keys),
+            "parallelism": parallelism,
             "l2": "inputs larger than L2 (>= 25 MB of state per origin and step)",
+            "timing": f"{steps}-step region (barrier + synchronize on both sides) repeated {head_rec['regions']['regions']} times "
+                      f"= {head_rec['regions']['timed_seconds']:.2f} s; value = median region",
+            "frames": f"pool of {pool_size} consecutive frames walked back and forth",
         },
-        "e2e": {
-            "value": e2e_value, "unit": UNIT, "ms_per_step": e2e["ms"] / steps,
-            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-        },
-        "gpu_launches": dev["launches"],
-        "roofline": roofline,
+        "e2e": head_rec.get("e2e"),
+        "gpu_launches": head["launches"],
+        "roofline": head_rec["roofline"],
         "cpu_baseline": cpu,
-        "clocks": dev["clocks"],
-        "check": {k: float(dev["rows"][k][0]) for k in ("time", "msd", "alpha", "rot1", "overlap", "struct")}
-        if isinstance(dev["rows"], dict) else None,
-        # the end-to-end phase replays the same frames from host memory: its rows must be identical
-        "e2e_rows_identical": bool(
-            isinstance(dev["rows"], dict) and isinstance(e2e["rows"], dict)
-            and all(np.array_equal(dev["rows"][k], e2e["rows"][k], equal_nan=True) for k in dev["rows"] if k != "keyframe")
-        ),
+        "clocks": head["clocks"],
+        "check": head_rec["check"],
+        "parity": head["parity"],
+        "regimes": {
+            r: {**{k: rec[k] for k in keep if k in rec}, "roofline": {k: rec["roofline"][k] for k in roof_keep}}
+            for r, rec in records.items()
+        },
+        "configs": configs,
     }
     print(json.dumps(line), flush=True)
+    parity_failed = head["parity"] is not None and not head["parity"]["ok"]
+    if parity_failed:
+        print("PARITY FAILURE: " + json.dumps(head["parity"]), file=sys.stderr, flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity_failed:
+        raise SystemExit(3)
+
+
+def _oracle_parity(np, n, box, oracle_frames, pool_host, t_first, warmup, tables, state_np, followed):
+    """Replay the frames the two followed origins saw through the CPU oracle; compare the rows of the warm-up
+    steps and of the first timed step, and the per-molecule state after the warm-up.  Also the CPU baseline:
+    the oracle's time for exactly these (frame, origin) pairs."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import parity as opar
+
+    run = opar.OracleRun(WAVE_NUMBER)
+    report = {
+        "checked_rows": 0, "max_rel": 0.0, "failed_rows": [], "origins": followed, "molecules": n,
+        "delta_translation_mismatch": 0, "delta_rotation_differs": 0, "delta_rotation_beyond_1ulp": 0,
+        "passage_mismatch": 0, "passage_excluded_1ulp": 0, "state_checked": [],
+    }
+    t0 = time.perf_counter()
+    for ts, pos, quat, keys in oracle_frames:
+        run.frame(ts, box, pos, quat, keys)
+    creation_rows = len(run.rows)
+    for i, (pos, quat) in enumerate(pool_host):
+        run.frame(t_first + i, box, pos, quat, followed)
+        if i == warmup - 1:  # the device state was copied after the warm-up steps
+            seconds_before = time.perf_counter()
+            for key in followed:
+                if key in state_np:
+                    trans, rot, summ = state_np[key]
+                    dyn, relax = run.keyframes[key]
+                    res = opar.compare_state(trans, rot, summ, dyn, relax.summary(), run.near[key])
+                    for k_, v_ in res.items():
+                        report[k_] += v_
+                    report["state_checked"].append(key)
+            t0 += time.perf_counter() - seconds_before  # (the comparison is not oracle work)
+    seconds = time.perf_counter() - t0
+    # rows: origin `key` at measured step i has time difference t_first + i - t0(key)
+    by_step = dict(tables)
+    t0_of = {key: run.keyframes[key][0].timestep for key in followed}
+    for row in run.rows[creation_rows:]:
+        key = row["keyframe"]
+        i = int(row["time"]) + t0_of[key] - t_first
+        table = by_step.get(i)
+        if table is None:
+            continue
+        col = list(table["keyframe"]).index(key)
+        got = {q: table[q][col] for q in row if q not in ("keyframe", "_tie")}
+        max_rel, failed = opar.compare_row(got, row, n)
+        report["checked_rows"] += 1
+        report["max_rel"] = max(report["max_rel"], max_rel)
+        if failed:
+            report["failed_rows"].append({"origin": key, "step": i, "quantities": failed})
+    report["passage_times_set_origin0"] = {
+        name: int((col != 2 ** 32 - 1).sum()) for name, col in run.keyframes[followed[0]][1].summary().items()
+    }
+    report["ok"] = bool(
+        report["checked_rows"] == len(followed) * (warmup + 1) and not report["failed_rows"]
+        and report["delta_translation_mismatch"] == 0 and report["delta_rotation_beyond_1ulp"] == 0
+        and report["delta_rotation_differs"] <= max(1, int(1e-5 * n * len(report["state_checked"])))
+        and report["passage_mismatch"] == 0 and len(report["state_checked"]) == len(followed)
+    )
+    report["bar"] = (
+        "rows rtol 1e-5 (counts exact, struct +-2 rows); dr bit-exact; dtheta <= 1 ulp on <= 1e-5 of the molecules; "
+        "passage times bit-exact outside 1 ulp of a cutoff"
+    )
+    cpu = {
+        "value": run.pairs * n / seconds, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"{run.pairs} (frame, origin) pairs at N={n} -- the frames two aged origins of this run saw: oracle "
+                  f"Dynamics.compute_all + Relaxations.add, 1 process, {seconds:.1f} s",
+    }
+    return report, cpu
 
 
 def main():
@@ -536,8 +730,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--molecules", type=int, default=N_MOLS)
     ap.add_argument("--origins", type=int, default=N_ORIGINS)
+    ap.add_argument("--regime", default="both", choices=["aged", "early", "both"])
+    ap.add_argument("--headline", default="aged", choices=["aged", "early"], help="with --regime both: which regime is `value`")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="repeat the K-step region until this much has been timed")
+    ap.add_argument("--parity", default="auto", choices=["auto", "on", "off"], help="oracle check of two origins (auto: 1 GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--age-stride", type=int, default=1, help="timesteps between the creation of consecutive origins")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[1] / configs[2] sub-records")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tmpdir", default=os.environ.get("SDB_BENCH_TMP", "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"))
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

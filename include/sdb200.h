@@ -264,6 +264,12 @@ int sdb_voronoi_counts(const float* h_box, int32_t n, const float* d_pos, const 
 int sdb_rdf_histogram(const float* h_box, int32_t is2d, int32_t n, const float* d_pos, float rmax, float dr,
                       int32_t nbins, uint64_t* d_counts, void* stream);
 
+/* Page-lock / release a host range the caller keeps mapped (e.g. the mmap of a GSD trajectory, frame.py:162-184's
+ * arrays): frames inside it can be passed to sdb_engine_step as SDB_MEM_PINNED.  Failure (SDB_ECUDA) leaves no
+ * pending CUDA error: the caller simply keeps using SDB_MEM_HOST. */
+int sdb_host_register(void* h_ptr, size_t bytes);
+int sdb_host_unregister(void* h_ptr);
+
 const char* sdb_last_error(void);
 const char* sdb_version(void);
 /* Number of kernels launched by this library since load (used by bench.py's gpu_launches). */

@@ -89,3 +89,34 @@ extern "C" void sdb_test_wrap2d(float lx, float ly, float xy, float vx, float vy
 {
     sdb_wrap2d(lx, ly, xy, vx, vy, *ox, *oy);
 }
+
+// Page-lock a host range that the caller keeps mapped (a memory-mapped trajectory file): frames inside it are then
+// uploaded straight from the page cache.  Read-only registration first (the mapping is usually PROT_READ), then the
+// default flavour; a failure is not an error of the library (the caller falls back to staged copies) and leaves no
+// pending CUDA error behind.
+extern "C" int sdb_host_register(void* h_ptr, size_t bytes)
+{
+    if (!h_ptr || bytes == 0) return SDB_EINVAL;
+    cudaError_t err = cudaHostRegister(h_ptr, bytes, cudaHostRegisterReadOnly);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        err = cudaHostRegister(h_ptr, bytes, cudaHostRegisterDefault);
+    }
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        sdb_set_error("sdb_host_register: %s", cudaGetErrorString(err));
+        return SDB_ECUDA;
+    }
+    return SDB_OK;
+}
+
+extern "C" int sdb_host_unregister(void* h_ptr)
+{
+    if (!h_ptr) return SDB_EINVAL;
+    const cudaError_t err = cudaHostUnregister(h_ptr);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return SDB_ECUDA;
+    }
+    return SDB_OK;
+}

@@ -492,6 +492,15 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
         const int lo_t = __float_as_int(br.z), hi_t = __float_as_int(br.w);
         const uint32_t span_r = (uint32_t)(hi_r - lo_r), span_t = (uint32_t)(hi_t - lo_t);
         int n_ar = 0, n_at = 0, n_both = 0, n_cand = 0;
+        // Tracker slow path, compacted: lanes holding a molecule for which some tracker may change state
+        // (typically 1-2 % of the molecules once the origins have aged: crossings of a threshold) queue their
+        // group of 4 molecules in shared memory -- in the part of this origin's stage whose data are already in
+        // registers -- and the queue is processed after the group loop, one molecule per lane, instead of one
+        // divergent call per molecule and lane.  Entry q of group g: (lane | need << 8, flag word) in plane 0,
+        // d2[4] in plane 1, |dtheta|[4] in plane 2, each in that group's own half of the plane.
+        unsigned pushing_g[SDB_GROUPS];  // lanes that queued their group (warp-uniform)
+        unsigned char* const qbase = const_cast<unsigned char*>(st);
+        unsigned char* const q_fl = qbase + 3 * SDB_PLANE_BYTES;  // new flag byte per molecule of the tile
 
 #pragma unroll
         for (int g = 0; g < SDB_GROUPS; ++g) {
@@ -587,23 +596,33 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
                     }
                 }
             }
-            uint32_t fl4_new = fl4;
+            pushing_g[g] = 0u;
             if (track) {
                 const float m_d2 = fmaxf(fmaxf(d2[0], d2[1]), fmaxf(d2[2], d2[3]));
                 const float m_th = fmaxf(fmaxf(th[0], th[1]), fmaxf(th[2], th[3]));
                 const bool quiet = (m_d2 < min_cut_d2 && m_th < min_cut_th && (fl4 & state1_x4) == 0u) ||
                                    (fl4 == done_x4 && !literal);
+                uint32_t need = 0u;
                 if (valid && !quiet) {  // some molecule of this group is above a cut or in an intermediate state
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (TAIL && j0[g] + e >= n) break;
-                        const uint32_t fl = (fl4 >> (8 * e)) & 0xffu;
-                        const float4 q = quiet_tab[fl];
+                        const float4 q = quiet_tab[(fl4 >> (8 * e)) & 0xffu];
                         const bool quiet_e = d2[e] < q.x && d2[e] >= q.y && th[e] < q.z && th[e] >= q.w && !literal;
-                        if (quiet_e) continue;
-                        const uint32_t fl_new = sdb_track(a.p.trackers, a.p.n_trackers, fl, d2[e], th[e],
-                                                          sbase + j0[g] + e, stride, org.timediff, literal);
-                        fl4_new = (fl4_new & ~(0xffu << (8 * e))) | (fl_new << (8 * e));
+                        need |= quiet_e ? 0u : (1u << e);
+                    }
+                }
+                const unsigned pushing = __ballot_sync(0xffffffffu, need != 0u);
+                pushing_g[g] = pushing;
+                if (pushing) {  // warp-uniform
+                    __syncwarp();  // every lane holds this group's part of the stage in registers: it is free
+                    if (need) {
+                        const int qs = __popc(pushing & lanemask_lt);
+                        unsigned char* const half = qbase + g * (SDB_PLANE_BYTES / 2);
+                        *reinterpret_cast<uint2*>(half + qs * 8) = make_uint2((uint32_t)lane | (need << 8), fl4);
+                        *reinterpret_cast<float4*>(half + SDB_PLANE_BYTES + qs * 16) = make_float4(d2[0], d2[1], d2[2], d2[3]);
+                        *reinterpret_cast<float4*>(half + 2 * SDB_PLANE_BYTES + qs * 16) = make_float4(th[0], th[1], th[2], th[3]);
+                        *reinterpret_cast<uint32_t*>(q_fl + (g * 32 + lane) * 4) = fl4;
                     }
                 }
             }
@@ -611,8 +630,34 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
                 sdb_st_stream4(dbase + j0[g], make_float4(ddx[0], ddx[1], ddx[2], ddx[3]));
                 sdb_st_stream4(dbase + stride + j0[g], make_float4(ddy[0], ddy[1], ddy[2], ddy[3]));
                 sdb_st_stream4(dbase + 2 * stride + j0[g], make_float4(ddt[0], ddt[1], ddt[2], ddt[3]));
-                if (track && fl4_new != fl4) *reinterpret_cast<uint32_t*>(fbase + j0[g]) = fl4_new;
             }
+        }
+        if (track && (pushing_g[0] | pushing_g[1]) != 0u) {  // warp-uniform
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < SDB_GROUPS; ++g) {
+                const unsigned char* const half = qbase + g * (SDB_PLANE_BYTES / 2);
+                const int n_q = 4 * __popc(pushing_g[g]);
+                for (int i = lane; i < n_q; i += 32) {  // one molecule per lane: entry i / 4, element i % 4
+                    const int q = i >> 2, e = i & 3;
+                    const uint2 id = *reinterpret_cast<const uint2*>(half + q * 8);
+                    if (!((id.x >> (8 + e)) & 1u)) continue;
+                    const uint32_t local = (uint32_t)(g * 128) + (id.x & 0xffu) * 4u + (uint32_t)e;
+                    const float qd2 = *reinterpret_cast<const float*>(half + SDB_PLANE_BYTES + q * 16 + e * 4);
+                    const float qth = *reinterpret_cast<const float*>(half + 2 * SDB_PLANE_BYTES + q * 16 + e * 4);
+                    const uint32_t fl_new = sdb_track(a.p.trackers, a.p.n_trackers, (id.y >> (8 * e)) & 0xffu, qd2, qth,
+                                                      sbase + tile0 + local, stride, org.timediff, literal);
+                    q_fl[local] = (unsigned char)fl_new;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < SDB_GROUPS; ++g) {
+                if ((pushing_g[g] >> lane) & 1u)  // (a handful of lanes per tile: stored whether it changed or not)
+                    *reinterpret_cast<uint32_t*>(fbase + j0[g]) = *reinterpret_cast<const uint32_t*>(q_fl + (g * 32 + lane) * 4);
+            }
+            // generic-proxy writes to this stage precede the next bulk copy (async proxy) into it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         // Append the staged candidates to the origin's dense list: the slot reservation (one atomic per
         // warp tile) is issued here and its result is only consumed after the reduction below.

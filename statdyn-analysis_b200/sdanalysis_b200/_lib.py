@@ -61,6 +61,8 @@ EXPORTS = (
     "sdb_launch_count",
     "sdb_test_rot_increment",
     "sdb_test_wrap2d",
+    "sdb_host_register",
+    "sdb_host_unregister",
     "sdb_engine_create",
     "sdb_engine_destroy",
     "sdb_engine_set_trackers",
@@ -260,6 +262,8 @@ def load():
         "sdb_launch_count": (c_uint64, []),
         "sdb_test_rot_increment": (c_double, [c_float, c_float, c_float, c_float, POINTER(c_int32)]),
         "sdb_test_wrap2d": (None, [c_float, c_float, c_float, c_float, c_float, POINTER(c_float), POINTER(c_float)]),
+        "sdb_host_register": (c_int32, [P, c_size_t]),
+        "sdb_host_unregister": (c_int32, [P]),
         "sdb_engine_create": (c_int32, [POINTER(SdbEngineConfig), POINTER(c_void_p)]),
         "sdb_engine_destroy": (None, [P]),
         "sdb_engine_set_trackers": (c_int32, [P, POINTER(SdbTracker), c_int32]),
@@ -369,6 +373,26 @@ def device_context(device):
     except Exception:
         pass
     return t.cuda.device(device)
+
+
+# ---- page-locked host ranges registered by this package (a memory-mapped trajectory file pinned with
+# cudaHostRegister): frames inside them are uploaded without the staging copy (SDB_MEM_PINNED)
+_pinned_ranges = []
+
+
+def register_pinned(address, nbytes):
+    _pinned_ranges.append((int(address), int(address) + int(nbytes)))
+
+
+def unregister_pinned(address):
+    _pinned_ranges[:] = [r for r in _pinned_ranges if r[0] != int(address)]
+
+
+def is_pinned(address, nbytes=1):
+    for lo, hi in _pinned_ranges:
+        if lo <= address and address + nbytes <= hi:
+            return True
+    return False
 
 
 def float_array(values):

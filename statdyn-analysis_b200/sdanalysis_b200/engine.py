@@ -588,9 +588,15 @@ class DynamicsEngine:
             if orientation.dtype != F32 or not orientation.flags.c_contiguous:
                 orientation = np.ascontiguousarray(orientation, dtype=F32)
             quat_ptr = orientation.ctypes.data
+        pos_ptr = position.ctypes.data
+        if _lib._pinned_ranges and _lib.is_pinned(pos_ptr, position.nbytes) and (
+            not quat_ptr or _lib.is_pinned(quat_ptr, orientation.nbytes)
+        ):
+            # views of a page-locked file mapping (gsdio.GSDTrajectory.pin): uploaded in place
+            return pos_ptr, quat_ptr, _lib.SDB_MEM_PINNED, (position, orientation)
         # pageable host memory is copied into the engine's pinned ring inside the call: the (possibly converted)
         # arrays only have to outlive the call itself
-        return position.ctypes.data, quat_ptr, _lib.SDB_MEM_HOST, (position, orientation)
+        return pos_ptr, quat_ptr, _lib.SDB_MEM_HOST, (position, orientation)
 
     # ------------------------------------------------------------------------------------------
     def step(self, timestep, position, orientation, active, *, zero_step=False, want_sums=None, to_host=True, rows_out=0):
@@ -650,7 +656,7 @@ class DynamicsEngine:
                 raise OverflowError(message)
             raise _lib.SdbError(f"libsdb200 error {ticket}: {message}")
         self._next_ticket = ticket + 1
-        if keep is not None and self.torch is not None and isinstance(keep[0], self.torch.Tensor) and not keep[0].is_cuda:
+        if keep is not None and f.where == _lib.SDB_MEM_PINNED:
             # pinned host tensors are read by the copy stream after this call returns
             self._keepalive.append(keep)
             if len(self._keepalive) > self.ring_depth + 1:

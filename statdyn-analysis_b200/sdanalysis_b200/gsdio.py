@@ -131,7 +131,40 @@ class GSDTrajectory:
     def __len__(self):
         return self._nframes
 
+    def pin(self):
+        """Page-lock the file mapping (``cudaHostRegister``, read-only) so that frames are uploaded to the GPU
+        straight from the page cache, without a staging copy.  Returns True on success; on failure (no CUDA,
+        read-only registration unsupported, locked-memory limit) nothing changes and frames take the staged path."""
+        if getattr(self, "_pinned_addr", None):
+            return True
+        try:
+            from . import _lib
+
+            torch = _lib.torch()
+            if not torch.cuda.is_available():
+                return False
+            view = np.frombuffer(self._mm, dtype=np.uint8)
+            addr, size = view.ctypes.data, view.nbytes
+            if _lib.load().sdb_host_register(addr, size) != 0:
+                return False
+            self._pinned_addr = addr
+            _lib.register_pinned(addr, size)
+            return True
+        except Exception:
+            return False
+
+    def _unpin(self):
+        addr = getattr(self, "_pinned_addr", None)
+        if addr:
+            from . import _lib
+
+            _lib.torch().cuda.synchronize()  # uploads reading the mapping have finished
+            _lib.load().sdb_host_unregister(addr)
+            _lib.unregister_pinned(addr)
+            self._pinned_addr = None
+
     def close(self):
+        self._unpin()
         # numpy views keep the mmap alive; closing is best effort
         try:
             self._mm.close()

@@ -63,6 +63,8 @@ class WriteCache:
         self.cache_multiplier = cache_multiplier
         self.to_append = to_append
         self._cache: List[Any] = []
+        self._blocks: List[pandas.DataFrame] = []  # column blocks (one per frame) from append_table
+        self._block_rows = 0
         self._cache_default = 8192
         self._emptied_count = 0
 
@@ -76,21 +78,36 @@ class WriteCache:
             self._emptied_count += 1
         self._cache.append(item)
 
+    def append_table(self, table: Dict[str, Any]) -> None:
+        """All rows of one frame at once, as columns (what ``StepResult.table`` returns): the per-row dicts of
+        ``append`` cost more than the kernels of a 32 k-molecule frame."""
+        block = pandas.DataFrame(table)
+        if self._filename is not None and self._block_rows + len(block) > self._cache_size and (self._blocks or self._cache):
+            self.flush()
+            self._emptied_count += 1
+        self._blocks.append(block)
+        self._block_rows += len(block)
+
     def flush(self) -> None:
         assert self.filename is not None
         _write_table(self.to_dataframe(), self.filename, self.group, self.to_append)
         self.to_append = True
         self._cache.clear()
+        self._blocks.clear()
+        self._block_rows = 0
 
     @property
     def filename(self) -> Optional[Path]:
         return None if self._filename is None else Path(self._filename)
 
     def __len__(self) -> int:
-        return self._cache_size * self._emptied_count + len(self._cache)
+        return self._cache_size * self._emptied_count + len(self._cache) + self._block_rows
 
     def to_dataframe(self):
-        return pandas.DataFrame.from_records(self._cache)
+        if not self._blocks:
+            return pandas.DataFrame.from_records(self._cache)
+        parts = ([pandas.DataFrame.from_records(self._cache)] if self._cache else []) + self._blocks
+        return pandas.concat(parts, ignore_index=True)
 
 
 def process_frames(
@@ -102,13 +119,15 @@ def process_frames(
     temperature: float = np.nan,
     pressure: float = np.nan,
     sink=None,
+    table_sink=None,
     device=None,
     struct_mode: str = "reference",
     pipeline_depth: int = 3,
 ):
     """Run the hot loop of ``process_file`` (reference ``_read.py:128-168``) over any iterator of
-    ``(indexes, frame)`` pairs.  Rows are passed to ``sink(row)``; returns the engine (per-origin
-    passage times stay on the device until ``engine.summary(key)`` is called)."""
+    ``(indexes, frame)`` pairs.  Rows are passed to ``sink(row)`` one dict at a time like the reference builds
+    them, or -- ``table_sink`` -- one column block per frame (``{quantity: (A,) array}``, the fast form);
+    returns the engine (per-origin passage times stay on the device until ``engine.summary(key)`` is called)."""
     engine = None
     box_warned = False
     pending = deque()
@@ -116,6 +135,17 @@ def process_frames(
     def drain(limit):
         while len(pending) > limit:
             result = pending.popleft()
+            if table_sink is not None:
+                try:
+                    table = result.table()
+                except (ValueError, RuntimeError) as e:  # _read.py:154-156
+                    logger.warning(e)
+                    continue
+                count = len(result.keys)
+                table["temperature"] = np.full(count, temperature)
+                table["pressure"] = np.full(count, pressure)
+                table_sink(table)
+                continue
             try:
                 rows = result.rows()
             except (ValueError, RuntimeError) as e:  # _read.py:154-156
@@ -212,7 +242,7 @@ def process_file(
         scattering_function=scattering_function,
         temperature=temperature,
         pressure=pressure,
-        sink=dataframes.append,
+        table_sink=dataframes.append_table,
     )
     logger.info("Finished processing %s, took %s", infile, datetime.datetime.now() - start_time)
 

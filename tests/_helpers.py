@@ -4,6 +4,7 @@
 import numpy as np
 
 from oracle import dynamics as odyn
+from oracle.parity import near_cutoff, overlap_tie as _overlap_tie  # noqa: F401
 
 WAVE_NUMBER = 2.9
 FLOAT_KEYS = ("mean_displacement", "msd", "mfd", "mean_rotation", "msr", "rot1", "rot2")
@@ -46,35 +47,6 @@ def oracle_process(frames, wave_number=WAVE_NUMBER, ulps=1, scattering_function=
             near[index] = near_cutoff(relax, near[index], ulps)
     summaries = {index: relax.summary() for index, (_, relax) in keyframes.items()}
     return rows, summaries, near, keyframes
-
-
-def near_cutoff(relax, near=None, ulps=1):
-    """Accumulate, per tracker of the oracle ``relax``, the mask of molecules whose current distance lies
-    within ``ulps`` ulp (f32) of a cutoff of that tracker."""
-    if near is None:
-        near = {name: np.zeros(relax._num_elements, dtype=bool) for name in relax.mol_relax}
-    disp = np.linalg.norm(relax.motion.delta_translation, axis=1)
-    rot = np.linalg.norm(relax.motion.delta_rotation, axis=1)
-    for name, func in relax.mol_relax.items():
-        value = rot if func.relaxation_type == "rotation" else disp
-        cuts = [func.threshold] + ([func._irreversibility] if hasattr(func, "_irreversibility") else [])
-        for cut in cuts:
-            c = np.float32(cut)
-            near[name] |= np.abs(value - c) <= ulps * np.spacing(c)
-    return near
-
-
-def _overlap_tie(dyn):
-    """True when the top-10% cut of either key array falls inside a run of equal values (numpy's
-    choice among equal keys is implementation-defined: SURVEY trap T4)."""
-    k = int(dyn.num_particles * 0.1)
-    if k == 0:
-        return True
-    for values in (dyn.compute_displacement(), np.abs(dyn.compute_rotation())):
-        s = np.sort(values)
-        if s[-k] == s[-k - 1]:
-            return True
-    return False
 
 
 def compare_rows(gpu_rows, ref_rows, n, n_sites=3, struct_slack=2):

@@ -161,3 +161,32 @@ def test_scattering_function_column_of_process_frames():
     for want in ref_rows:
         got = order[(want["keyframe"], want["time"])]
         np.testing.assert_allclose(got["scattering_function"], want["scattering_function"], rtol=1e-6, atol=1e-9)
+
+
+def test_passage_times_when_time_moves_backwards():
+    """Relaxations.add with a timestep smaller than an earlier one (relaxations.py:215-218: a fired tracker
+    is rewritten while ``status > timediff``): the device's literal path (SDB_ORIGIN_LITERAL) against the
+    oracle, every molecule, including the frames after time moves forward again."""
+    from oracle import dynamics as odyn
+    from sdanalysis_b200 import dynamics
+    from sdanalysis_b200.molecules import Trimer
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    walk = SyntheticTrimer(6000, seed=41, sigma_r=0.12, sigma_theta=0.25)
+    pos0, quat0 = walk.frame()
+    relax = dynamics.Relaxations(0, walk.box, pos0, quat0, molecule=Trimer(), wave_number=WAVE_NUMBER)
+    ref = odyn.Relaxations(0, walk.box, pos0, quat0, "trimer", wave_number=WAVE_NUMBER)
+    near = None
+    for timestep in (10, 20, 5, 6, 30, 31, 12, 40):
+        walk.advance(4)
+        pos, quat = walk.frame()
+        relax.add(timestep, pos, quat)
+        ref.add(timestep, pos, quat)
+        near = near_cutoff(ref, near)
+    got, want = relax.summary(), ref.summary()
+    rewritten = 0
+    for name, col in want.items():
+        mask = ~near[name]
+        assert np.array_equal(got[name].to_numpy()[mask], col[mask]), name
+        rewritten += int(np.isin(col, (5, 6, 12)).sum())
+    assert rewritten > 100  # the literal rule really rewrote passage times
