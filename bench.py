@@ -50,7 +50,13 @@ N_ORIGINS = 200
 WAVE_NUMBER = 2.9
 PIPELINE = int(os.environ.get("SDB_BENCH_PIPELINE", "2"))  # frames in flight before the oldest result is read
 SIGMA_R, SIGMA_T = 0.01, 0.02
-POOL = int(os.environ.get("SDB_BENCH_POOL", "16"))  # distinct frames of the measured steps (walked back and forth)
+# Distinct consecutive frames of the measured steps.  The device-resident loop gets as many as it can use (no frame
+# is seen twice in a run of the default length); if the memory budgets below cap the pool, it is walked back and
+# forth (every step is still one genuine walk step; a reversal makes the top-10 % thresholds of young origins jump,
+# which costs their `overlap` selection one exact pass).
+POOL = int(os.environ.get("SDB_BENCH_POOL", "1300"))
+POOL_DEVICE_BYTES = float(os.environ.get("SDB_BENCH_POOL_GB", "36")) * 1e9
+POOL_FILE_BYTES = float(os.environ.get("SDB_BENCH_FILE_GB", "4")) * 1e9
 AGE_STRIDE = {"aged": 10, "early": 1}
 WORKLOAD = (
     "configs[3]: synthetic 2D Trimer liquid, 1M molecules, 200 time-origins, dense linear schedule "
@@ -248,7 +254,8 @@ def run_gpu(args):
     all_keys = list(range(n_origins))
     local_keys = partition(all_keys, rank, world)
     peak, peak_kind = _peaks()
-    pool_size = max(2, min(POOL, 4096))
+    pool_size = max(2, min(POOL, int(POOL_DEVICE_BYTES // (28 * n))))
+    file_frames = max(2, min(pool_size, int(POOL_FILE_BYTES // (28 * n))))
     prof_steps = max(2, min(steps, 8))
     want_parity = args.parity == "on" or (args.parity == "auto" and world == 1 and not args.no_cpu_baseline)
     if n_origins < 3:
@@ -329,9 +336,9 @@ def run_gpu(args):
                 pool_dev.append((pos.clone(), quat.clone()))
             else:
                 pool_dev.append((None, None))
-            if rank == 0 and (writer is not None or (with_parity and j <= warmup)):
+            if rank == 0 and ((writer is not None and j < file_frames) or (with_parity and j <= warmup)):
                 hp, hq = pos.cpu().numpy(), quat.cpu().numpy()
-                if writer is not None:
+                if writer is not None and j < file_frames:
                     writer.append(t_first + j, box, hp, hq, dimensions=2)
                 if with_parity and j <= warmup:
                     pool_host.append((hp, hq))
@@ -349,7 +356,7 @@ def run_gpu(args):
 
         def frame_of(source, i):
             if source == "gsd":
-                snap = trj["gsd"][pingpong(i, pool_size)]
+                snap = trj["gsd"][pingpong(i, file_frames)]
                 return snap.position, snap.orientation
             return pool_dev[pingpong(i, pool_size)]
 
@@ -468,7 +475,8 @@ def run_gpu(args):
             e2e_times, e2e_host, _ = timed("gsd", args.min_seconds)
             h2d = engine.h2d_bytes if world == 1 else 28 * n
             d2h = engine.d2h_bytes if world == 1 else n_origins * 16 * 8
-            e2e = {"times": e2e_times, "host_ms": statistics.median(e2e_host), "h2d": h2d, "d2h": d2h, "pinned_file": pinned_file}
+            e2e = {"times": e2e_times, "host_ms": statistics.median(e2e_host), "h2d": h2d, "d2h": d2h, "pinned_file": pinned_file,
+                   "pin_error": getattr(trj["gsd"], "pin_error", None)}
             posted.clear()
             torch.cuda.synchronize()
             barrier()
@@ -574,6 +582,7 @@ def run_gpu(args):
                 "source": "GSD trajectory file read through sdanalysis_b200.gsdio (mmap) inside the timed region"
                           + (", file mapping page-locked (cudaHostRegister)" if m["e2e"]["pinned_file"] else
                              ", frames copied to the engine's pinned ring by its host threads"),
+                "file_frames": file_frames, "pin_error": m["e2e"]["pin_error"],
             }
         return rec
 
@@ -629,7 +638,8 @@ def run_gpu(args):
             "l2": "inputs larger than L2 (>= 25 MB of state per origin and step)",
             "timing": f"{steps}-step region (barrier + synchronize on both sides) repeated {head_rec['regions']['regions']} times "
                       f"= {head_rec['regions']['timed_seconds']:.2f} s; value = median region",
-            "frames": f"pool of {pool_size} consecutive frames walked back and forth",
+            "frames": f"{pool_size} consecutive frames resident in HBM (walked back and forth when a run needs more); "
+                      f"e2e: a GSD file of {file_frames} frames",
         },
         "e2e": head_rec.get("e2e"),
         "gpu_launches": head["launches"],

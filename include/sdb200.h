@@ -238,6 +238,12 @@ int sdb_neighbours(const float* h_box, int32_t n, const float* d_pos, const floa
                    float rmax, int32_t k, uint32_t* d_nlist, float* d_rsq, uint32_t* d_counts,
                    double* d_order, void* d_scratch, size_t scratch_bytes, void* stream);
 size_t sdb_neighbours_scratch_bytes(const float* h_box, int32_t n, float rmax);
+/* The same search with capacity k (d_counts saturates at k, like num_neighbours' k = 9, order.py:279-281) and rows
+ * of width k_list <= k in d_nlist / d_rsq / the order parameter: ONE build serves compute_neighbours (k_list = 8),
+ * orientational_order (8) and num_neighbours (k = 9) of a frame, where the reference builds three times. */
+int sdb_neighbours_ex(const float* h_box, int32_t n, const float* d_pos, const float* d_quat, float rmax, int32_t k,
+                      int32_t k_list, uint32_t* d_nlist, float* d_rsq, uint32_t* d_counts, double* d_order,
+                      void* d_scratch, size_t scratch_bytes, void* stream);
 /* order._orientational_order (order.py:68-86) and order._neighbour_relative_angle (order.py:28-65)
  * on a caller-provided neighbour list: d_order double[n] and/or d_angles double[n][k]. */
 int sdb_orientational_order(const uint32_t* d_nlist, int32_t n, int32_t k, const float* d_quat,

@@ -66,9 +66,9 @@ public:
 private:
     CopyPool()
     {
-        int want = 4;
-        if (const char* e = getenv("SDB_COPY_THREADS")) want = atoi(e);
         const int hw = (int)std::thread::hardware_concurrency();
+        int want = hw >= 16 ? 7 : 3;
+        if (const char* e = getenv("SDB_COPY_THREADS")) want = atoi(e);
         if (hw > 0) want = std::min(want, std::max(hw - 1, 0));
         for (int i = 0; i < want; ++i) workers_.emplace_back([this] { run(); });
     }
@@ -536,9 +536,13 @@ struct SdbEngine {
         seg_rows.clear();
         const long target_blocks = 148L * 16;
         const long blocks_per_segment = (n_parts + 3) / 4;
+        // a segment of fewer origins amortises a CTA's set-up (tracker table, pipeline fill, phase 1) over fewer
+        // iterations, but small systems need more than (tiles / 4) x (origins / 8) CTAs to fill 148 SMs
+        static const long seg_floor_env = [] { const char* e = getenv("SDB_SEG_MIN"); return e ? atol(e) : 0L; }();
+        const long seg_floor = seg_floor_env > 0 ? seg_floor_env : (blocks_per_segment >= 592 ? 8L : (blocks_per_segment >= 148 ? 4L : 2L));
         auto split = [&](const std::vector<Origin*>& members, const float* prev, uint32_t flags) {
             const long len = (long)members.size();
-            long size = cfg.chunk > 0 ? cfg.chunk : std::max(8L, (len * blocks_per_segment + target_blocks - 1) / target_blocks);
+            long size = cfg.chunk > 0 ? cfg.chunk : std::max(seg_floor, (len * blocks_per_segment + target_blocks - 1) / target_blocks);
             const long pieces = (len + size - 1) / size;
             size = (len + pieces - 1) / pieces;  // equal shares
             for (long first = 0; first < len; first += size) {

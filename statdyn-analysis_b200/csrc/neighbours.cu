@@ -26,7 +26,8 @@ struct NbArgs {
     int ncx, ncy;
     float rmaxsq;
     float inv_lx, inv_ly, filt;  // two-phase search: cheap minimum image and its acceptance bound (rmax + eps)^2
-    int k;
+    int k;      // capacity of the search: the count saturates at k
+    int k_out;  // width of the list / r^2 rows and number of neighbours in the order parameter (<= k)
     uint32_t* cell_of;     // [n]
     uint32_t* cell_count;  // [ncells + 1] -> after scan: cell_start
     uint32_t* cell_fill;   // [ncells]
@@ -109,6 +110,43 @@ __global__ void __launch_bounds__(1024) nb_scan_blocks(uint32_t* block_sums, int
     }
 }
 
+// Exclusive scan of up to 64 k counters by ONE block (the cell counts of a 32 k-molecule frame are ~13 k
+// numbers: three launches of the two-level scan cost more than the work).
+__global__ void __launch_bounds__(1024) nb_scan_single(uint32_t* data, int n)
+{
+    __shared__ uint32_t warp_sums[32];
+    const int per = (n + 1023) / 1024;
+    const int begin = min(threadIdx.x * per, n), end = min(begin + per, n);
+    uint32_t local = 0;
+    for (int i = begin; i < end; ++i) local += data[i];
+    // inclusive scan of the per-thread sums across the block
+    uint32_t v = local;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    if (lane == 31) warp_sums[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += o;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t run = v - local + (warp ? warp_sums[warp - 1] : 0u);  // exclusive prefix of this thread's range
+    for (int i = begin; i < end; ++i) {
+        const uint32_t c = data[i];
+        data[i] = run;
+        run += c;
+    }
+}
+
 __global__ void nb_scan_add(uint32_t* data, int n, const uint32_t* block_sums)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,7 +218,7 @@ __global__ void __launch_bounds__(128) nb_search_kernel(const NbArgs a)
         }
     }
 
-    const int kk = a.k;  // K is the compiled capacity, kk <= K the requested width
+    const int kk = a.k_out;  // K is the compiled capacity, kk <= a.k <= K the requested width
     if (a.nlist) {
 #pragma unroll
         for (int s = 0; s < K; ++s)
@@ -191,7 +229,7 @@ __global__ void __launch_bounds__(128) nb_search_kernel(const NbArgs a)
         for (int s = 0; s < K; ++s)
             if (s < kk) a.rsq[(long)i * kk + s] = best_i[s] == 0xFFFFFFFFu ? -1.0f : best_r[s];
     }
-    if (a.counts) a.counts[i] = (uint32_t)min(found, kk);
+    if (a.counts) a.counts[i] = (uint32_t)min(found, a.k);
     if (a.order && a.quat) {
         const float4 q = sdb_ldg4(a.quat + 4L * i);
         double acc = 0.0;
@@ -262,7 +300,7 @@ template <int K>
 __device__ __forceinline__ void nb_write_results(const NbArgs& a, const uint32_t i, const float (&best_r)[K],
                                                  const uint32_t (&best_i)[K], const int found)
 {
-    const int kk = a.k;  // K is the compiled capacity, kk <= K the requested width
+    const int kk = a.k_out;  // K is the compiled capacity, kk <= a.k <= K the requested width
     if (a.nlist) {
 #pragma unroll
         for (int s = 0; s < K; ++s)
@@ -273,7 +311,7 @@ __device__ __forceinline__ void nb_write_results(const NbArgs& a, const uint32_t
         for (int s = 0; s < K; ++s)
             if (s < kk) a.rsq[(long)i * kk + s] = best_i[s] == 0xFFFFFFFFu ? -1.0f : best_r[s];
     }
-    if (a.counts) a.counts[i] = (uint32_t)min(found, kk);
+    if (a.counts) a.counts[i] = (uint32_t)min(found, a.k);
     if (a.order && a.quat) {
         const float4 q = sdb_ldg4(a.quat + 4L * i);
         double acc = 0.0;
@@ -440,8 +478,17 @@ extern "C" int sdb_neighbours(const float* h_box, int32_t n, const float* d_pos,
                               uint32_t* d_nlist, float* d_rsq, uint32_t* d_counts, double* d_order, void* d_scratch,
                               size_t scratch_bytes, void* stream)
 {
+    return sdb_neighbours_ex(h_box, n, d_pos, d_quat, rmax, k, k, d_nlist, d_rsq, d_counts, d_order, d_scratch, scratch_bytes,
+                             stream);
+}
+
+extern "C" int sdb_neighbours_ex(const float* h_box, int32_t n, const float* d_pos, const float* d_quat, float rmax, int32_t k,
+                                 int32_t k_list, uint32_t* d_nlist, float* d_rsq, uint32_t* d_counts, double* d_order,
+                                 void* d_scratch, size_t scratch_bytes, void* stream)
+{
     NbLayout L;
-    if (!h_box || !d_pos || !d_scratch || n <= 0 || k <= 0 || k > SDB_MAX_K || !nb_layout(h_box, n, rmax, L)) {
+    if (!h_box || !d_pos || !d_scratch || n <= 0 || k <= 0 || k > SDB_MAX_K || k_list <= 0 || k_list > k ||
+        !nb_layout(h_box, n, rmax, L)) {
         sdb_set_error("sdb_neighbours: bad argument (n=%d k=%d)", n, k);
         return SDB_EINVAL;
     }
@@ -466,6 +513,7 @@ extern "C" int sdb_neighbours(const float* h_box, int32_t n, const float* d_pos,
     a.ncy = L.ncy;
     a.rmaxsq = rmax * rmax;
     a.k = k;
+    a.k_out = k_list;
     a.cell_of = reinterpret_cast<uint32_t*>(base + L.off_cell_of);
     a.cell_count = reinterpret_cast<uint32_t*>(base + L.off_count);
     a.cell_fill = reinterpret_cast<uint32_t*>(base + L.off_fill);
@@ -481,9 +529,14 @@ extern "C" int sdb_neighbours(const float* h_box, int32_t n, const float* d_pos,
     const int nblk = (n + 255) / 256;
     nb_bin_kernel<<<nblk, 256, 0, s>>>(a);
     SDB_CHECK_LAUNCH("nb_bin_kernel");
-    nb_scan_local<<<L.scan_blocks, 256, 0, s>>>(a.cell_count, L.ncells + 1, a.block_sums);
-    SDB_CHECK_LAUNCH("nb_scan_local");
-    if (L.scan_blocks > 1) {
+    if (L.ncells + 1 <= 65536) {
+        nb_scan_single<<<1, 1024, 0, s>>>(a.cell_count, L.ncells + 1);
+        SDB_CHECK_LAUNCH("nb_scan_single");
+    } else {
+        nb_scan_local<<<L.scan_blocks, 256, 0, s>>>(a.cell_count, L.ncells + 1, a.block_sums);
+        SDB_CHECK_LAUNCH("nb_scan_local");
+    }
+    if (L.ncells + 1 > 65536 && L.scan_blocks > 1) {
         nb_scan_blocks<<<1, 1024, 0, s>>>(a.block_sums, L.scan_blocks);
         SDB_CHECK_LAUNCH("nb_scan_blocks");
         nb_scan_add<<<(L.ncells + 1 + 255) / 256, 256, 0, s>>>(a.cell_count, L.ncells + 1, a.block_sums);

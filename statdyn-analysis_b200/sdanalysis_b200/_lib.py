@@ -54,6 +54,7 @@ EXPORTS = (
     "sdb_sums_general",
     "sdb_sums_general_parts",
     "sdb_neighbours",
+    "sdb_neighbours_ex",
     "sdb_neighbours_scratch_bytes",
     "sdb_orientational_order",
     "sdb_last_error",
@@ -255,6 +256,7 @@ def load():
         "sdb_sums_general": (c_int32, [c_int32, P, P, c_float, P, P, P, P, P]),
         "sdb_sums_general_parts": (c_int32, [c_int32]),
         "sdb_neighbours": (c_int32, [POINTER(c_float), c_int32, P, P, c_float, c_int32, P, P, P, P, P, c_size_t, P]),
+        "sdb_neighbours_ex": (c_int32, [POINTER(c_float), c_int32, P, P, c_float, c_int32, c_int32, P, P, P, P, P, c_size_t, P]),
         "sdb_neighbours_scratch_bytes": (c_size_t, [POINTER(c_float), c_int32, c_float]),
         "sdb_orientational_order": (c_int32, [P, c_int32, c_int32, P, P, P, P]),
         "sdb_last_error": (ctypes.c_char_p, []),

@@ -146,11 +146,13 @@ class GSDTrajectory:
             view = np.frombuffer(self._mm, dtype=np.uint8)
             addr, size = view.ctypes.data, view.nbytes
             if _lib.load().sdb_host_register(addr, size) != 0:
+                self.pin_error = _lib.load().sdb_last_error().decode()
                 return False
             self._pinned_addr = addr
             _lib.register_pinned(addr, size)
             return True
-        except Exception:
+        except Exception as exc:
+            self.pin_error = repr(exc)
             return False
 
     def _unpin(self):

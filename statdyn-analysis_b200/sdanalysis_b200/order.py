@@ -34,18 +34,70 @@ def _to_device(array, width, torch, device):
     return torch.from_numpy(array).to(device)
 
 
+# ---- one cell-list build per frame, shared by the public functions -------------------------------------------
+# The reference rebuilds freud's neighbour structure in compute_neighbours, orientational_order and
+# num_neighbours (order.py:207,258-261,279-281): a frame that wants all three pays three builds.  Here the
+# functions share ONE search of capacity 9 (its first 8 columns are the k = 8 list; the count saturates at 9 like
+# num_neighbours') as long as they are called with the same frame.  "The same frame" must be cheap and safe to
+# recognise: a torch tensor (same storage, shape and in-place version counter) or a read-only numpy array (same
+# address and shape, e.g. a view of a memory-mapped trajectory).  Writable numpy arrays are never cached.
+_workspaces = {}
+_analysis_cache = {"key": None, "value": None}
+
+
+def _immutable(array):
+    """A numpy array nobody can write through: read-only, and so is every array it is a view of."""
+    while isinstance(array, np.ndarray):
+        if array.flags.writeable:
+            return False
+        array = array.base
+    return True
+
+
+def _identity(array, torch):
+    """Hashable identity of a frame array's *contents*, or None when they cannot be recognised cheaply.  Valid
+    only while the cache holds a reference to the array (its memory cannot be reused for something else)."""
+    if isinstance(array, torch.Tensor):
+        return ("t", array.data_ptr(), tuple(array.shape), array.dtype, array._version, str(array.device))
+    if isinstance(array, np.ndarray) and _immutable(array):
+        return ("n", array.ctypes.data, array.shape, array.dtype.str, array.strides)
+    return None
+
+
+def _workspace(lib, torch, device, box6, n, max_radius):
+    key = (device, n, box6.tobytes(), float(max_radius))
+    ws = _workspaces.get(key)
+    if ws is None:
+        box_c = _lib.float_array(box6)
+        nbytes = int(lib.sdb_neighbours_scratch_bytes(box_c, n, float(max_radius)))
+        if nbytes == 0:
+            raise ValueError("invalid box or radius")
+        if len(_workspaces) > 8:
+            _workspaces.clear()
+        ws = _workspaces[key] = (box_c, torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes)
+    return ws
+
+
 def neighbour_analysis(
-    box, position, orientation=None, max_radius=3.5, max_neighbours=8, *, want=("nlist",), device=None, to_host=True
+    box, position, orientation=None, max_radius=3.5, max_neighbours=8, *, want=("nlist",), device=None, to_host=None,
+    count_capacity=None,
 ):
     """One cell-list build, any of ``nlist`` (N,k) uint32, ``rsq`` (N,k) f32, ``counts`` (N,) uint32,
-    ``order`` (N,) f64.  Missing neighbours are 2**32-1 in ``nlist`` and -1 in ``rsq``."""
+    ``order`` (N,) f64.  Missing neighbours are 2**32-1 in ``nlist`` and -1 in ``rsq``; ``counts`` saturates at
+    ``count_capacity`` (default: ``max_neighbours``).  Results are device tensors (int32 views of the uint32
+    data) when the frame was given as torch tensors or ``to_host=False``, numpy arrays otherwise."""
     torch = _lib.torch()
     device = _lib.require_cuda(device)
     lib = _lib.load()
     k = int(max_neighbours)
     if not 0 < k <= _lib.SDB_MAX_K:
         raise ValueError(f"max_neighbours must be in 1..{_lib.SDB_MAX_K}")
-    with torch.cuda.device(device):
+    cap = k if count_capacity is None else max(int(count_capacity), k)
+    if cap > _lib.SDB_MAX_K:
+        raise ValueError(f"count capacity must be <= {_lib.SDB_MAX_K}")
+    if to_host is None:
+        to_host = not isinstance(position, torch.Tensor)
+    with _lib.device_context(device):
         pos = _to_device(position, 3, torch, device)
         n = pos.shape[0]
         if n == 0:
@@ -55,11 +107,7 @@ def neighbour_analysis(
             if orientation is None:
                 raise ValueError("orientational order needs orientations")
             quat = _to_device(orientation, 4, torch, device)
-        box_c = _lib.float_array(_box6(box))
-        nbytes = int(lib.sdb_neighbours_scratch_bytes(box_c, n, float(max_radius)))
-        if nbytes == 0:
-            raise ValueError("invalid box or radius")
-        scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        box_c, scratch, nbytes = _workspace(lib, torch, device, _box6(box), n, max_radius)
         out = {}
         if "nlist" in want:
             out["nlist"] = torch.empty((n, k), dtype=torch.int32, device=device)
@@ -70,8 +118,8 @@ def neighbour_analysis(
         if "order" in want:
             out["order"] = torch.empty(n, dtype=torch.float64, device=device)
         _lib.check(
-            lib.sdb_neighbours(
-                box_c, n, pos.data_ptr(), _lib.ptr(quat), float(max_radius), k,
+            lib.sdb_neighbours_ex(
+                box_c, n, pos.data_ptr(), _lib.ptr(quat), float(max_radius), cap, k,
                 _lib.ptr(out.get("nlist")), _lib.ptr(out.get("rsq")), _lib.ptr(out.get("counts")),
                 _lib.ptr(out.get("order")), scratch.data_ptr(), nbytes, _lib.stream_ptr(device),
             )
@@ -82,6 +130,66 @@ def neighbour_analysis(
     for key in ("nlist", "counts"):
         if key in host:
             host[key] = host[key].view(np.uint32)
+    return host
+
+
+def _frame_analysis(box, position, orientation, max_radius, max_neighbours, need):
+    """The shared build: list / r^2 of width ``max_neighbours``, counts saturating at max(9, max_neighbours),
+    order parameter when orientations are known (computed from the cached list when they arrive later).
+    Cached for the frame it was computed for (see above)."""
+    torch = _lib.torch()
+    lib = _lib.load()
+    k = int(max_neighbours)
+    cap = max(k, 9)
+    ident = _identity(position, torch)
+    key = None if ident is None else (ident, _box6(box).tobytes(), float(max_radius), cap, k)
+    cached = _analysis_cache["value"] if (key is not None and _analysis_cache["key"] == key) else None
+    if cached is not None:
+        if need != "order":
+            return cached
+        quat_ident = _identity(orientation, torch)
+        if "order" in cached and quat_ident is not None and cached["quat_ident"] == quat_ident:
+            return cached
+        if orientation is None:
+            raise ValueError("orientational order needs orientations")
+        # the list of this frame is known: the order parameter is one more small kernel, not another build
+        device = cached["nlist"].device
+        with _lib.device_context(device):
+            quat = _to_device(orientation, 4, torch, device)
+            n = cached["nlist"].shape[0]
+            if quat.shape[0] != n:
+                raise ValueError("orientation and position have different lengths")
+            order = torch.empty(n, dtype=torch.float64, device=device)
+            _lib.check(lib.sdb_orientational_order(cached["nlist"].data_ptr(), n, k, quat.data_ptr(), order.data_ptr(), 0,
+                                                   _lib.stream_ptr(device)))
+        cached["order"] = order
+        cached["quat_ident"] = quat_ident
+        cached["refs"] = (cached["refs"][0], orientation)
+        cached["host"].pop("order", None)
+        return cached
+    if need == "order" and orientation is None:
+        raise ValueError("orientational order needs orientations")
+    want = ("nlist", "rsq", "counts") + (("order",) if orientation is not None else ())
+    result = neighbour_analysis(box, position, orientation, max_radius, k, want=want, to_host=False, count_capacity=cap)
+    result["quat_ident"] = _identity(orientation, torch) if orientation is not None else None
+    result["host"] = {}
+    result["refs"] = (position, orientation)  # keeps the memory the identities refer to from being reused
+    if key is not None:
+        _analysis_cache["key"], _analysis_cache["value"] = key, result
+    return result
+
+
+def _deliver(result, name, position):
+    """Device tensor for torch callers, numpy array (cached per frame) for numpy callers."""
+    torch = _lib.torch()
+    if isinstance(position, torch.Tensor):
+        return result[name]
+    host = result["host"].get(name)
+    if host is None:
+        host = result[name].cpu().numpy()
+        if name in ("nlist", "counts"):
+            host = host.view(np.uint32)
+        result["host"][name] = host
     return host
 
 
@@ -114,14 +222,15 @@ def setup_neighbours(box, position, max_radius: float = 3.5, max_neighbours: int
     if not is_2D:
         raise NotImplementedError("the cell-list kernel covers the reference's 2D boxes only")
     return NeighbourQuery(
-        neighbour_analysis(box, position, None, max_radius, max_neighbours, want=("nlist", "rsq", "counts"))
+        neighbour_analysis(box, position, None, max_radius, max_neighbours, want=("nlist", "rsq", "counts"), to_host=True)
     )
 
 
 def compute_neighbours(box, position, max_radius: float = 3.5, max_neighbours: int = 8) -> np.ndarray:
     """Indices of the nearest neighbours of each molecule, (N, max_neighbours) uint32, sorted by
-    distance, ``2**32 - 1`` marking a missing neighbour (reference ``order.py:186-207``)."""
-    return neighbour_analysis(box, position, None, max_radius, max_neighbours, want=("nlist",))["nlist"]
+    distance, ``2**32 - 1`` marking a missing neighbour (reference ``order.py:186-207``).  Torch tensors in:
+    an int32 device tensor (the same bits) out, without synchronising."""
+    return _deliver(_frame_analysis(box, position, None, max_radius, max_neighbours, "nlist"), "nlist", position)
 
 
 def _list_on_device(neighbourlist, orientation, torch, device):
@@ -179,18 +288,23 @@ def relative_orientations(box, position, orientation, max_radius: float = 3.5, m
 
 def orientational_order(box, position, orientation, max_radius: float = 3.5, max_neighbours: int = 8) -> np.ndarray:
     """Orientational order parameter of every molecule (reference ``order.py:234-262``)."""
-    return neighbour_analysis(box, position, orientation, max_radius, max_neighbours, want=("order",))["order"]
+    return _deliver(_frame_analysis(box, position, orientation, max_radius, max_neighbours, "order"), "order", position)
 
 
 def num_neighbours(box, position, max_radius: float = 3.5) -> np.ndarray:
-    """Number of neighbours within ``max_radius``; k = 9, so it saturates at 9 like the reference
-    (``order.py:265-281``, SURVEY trap T8)."""
-    return neighbour_analysis(box, position, None, max_radius, 9, want=("counts",))["counts"]
+    """Number of neighbours within ``max_radius``; the search has capacity 9, so it saturates at 9 like the
+    reference (``order.py:265-281``, SURVEY trap T8)."""
+    torch = _lib.torch()
+    ident = _identity(position, torch)
+    key, cached = _analysis_cache["key"], _analysis_cache["value"]
+    if ident is not None and key is not None and key[:4] == (ident, _box6(box).tobytes(), float(max_radius), 9):
+        return _deliver(cached, "counts", position)  # any list width <= 9 of this frame has the count
+    return _deliver(_frame_analysis(box, position, None, max_radius, 8, "counts"), "counts", position)
 
 
 def relative_distances(box, position, max_radius: float = 3.5, max_neighbours: int = 8) -> np.ndarray:
     """Distance to each neighbour, 0 where missing (reference ``order.py:284-309``)."""
-    rsq = neighbour_analysis(box, position, None, max_radius, max_neighbours, want=("rsq",))["rsq"]
+    rsq = neighbour_analysis(box, position, None, max_radius, max_neighbours, want=("rsq",), to_host=True)["rsq"]
     distances = rsq.astype(np.float64)
     distances[distances < 0] = 0
     return np.sqrt(distances)
@@ -217,7 +331,7 @@ def compute_voronoi_neighs(box, position) -> np.ndarray:
         k = _lib.SDB_MAX_K
         spacing = float(np.sqrt(float(box6[0]) * float(box6[1]) / n))
         rmax = min(4.0 * spacing, 0.49 * float(min(box6[0], box6[1])))
-        found = neighbour_analysis(box6, pos, None, rmax, k, want=("nlist",), device=device, to_host=False)
+        found = neighbour_analysis(box6, pos, None, rmax, k, want=("nlist",), device=device, to_host=False)  # (own build: k = 16)
         counts = torch.empty(n, dtype=torch.int32, device=device)
         scratch = torch.empty(n + 1, dtype=torch.int32, device=device)
         _lib.check(

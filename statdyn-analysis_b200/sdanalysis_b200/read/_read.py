@@ -63,7 +63,7 @@ class WriteCache:
         self.cache_multiplier = cache_multiplier
         self.to_append = to_append
         self._cache: List[Any] = []
-        self._blocks: List[pandas.DataFrame] = []  # column blocks (one per frame) from append_table
+        self._blocks: List[Dict[str, Any]] = []  # column blocks (one per frame) from append_table
         self._block_rows = 0
         self._cache_default = 8192
         self._emptied_count = 0
@@ -81,12 +81,12 @@ class WriteCache:
     def append_table(self, table: Dict[str, Any]) -> None:
         """All rows of one frame at once, as columns (what ``StepResult.table`` returns): the per-row dicts of
         ``append`` cost more than the kernels of a 32 k-molecule frame."""
-        block = pandas.DataFrame(table)
-        if self._filename is not None and self._block_rows + len(block) > self._cache_size and (self._blocks or self._cache):
+        count = len(table["keyframe"])
+        if self._filename is not None and self._block_rows + count > self._cache_size and (self._blocks or self._cache):
             self.flush()
             self._emptied_count += 1
-        self._blocks.append(block)
-        self._block_rows += len(block)
+        self._blocks.append(table)  # (a DataFrame per frame would cost more than the frame's kernels)
+        self._block_rows += count
 
     def flush(self) -> None:
         assert self.filename is not None
@@ -106,8 +106,14 @@ class WriteCache:
     def to_dataframe(self):
         if not self._blocks:
             return pandas.DataFrame.from_records(self._cache)
-        parts = ([pandas.DataFrame.from_records(self._cache)] if self._cache else []) + self._blocks
-        return pandas.concat(parts, ignore_index=True)
+        columns = list(self._blocks[0].keys())
+        merged = pandas.DataFrame({
+            name: np.concatenate([np.broadcast_to(np.asarray(b[name]), (len(b["keyframe"]),)) for b in self._blocks])
+            for name in columns
+        })
+        if self._cache:
+            merged = pandas.concat([pandas.DataFrame.from_records(self._cache), merged], ignore_index=True)
+        return merged
 
 
 def process_frames(

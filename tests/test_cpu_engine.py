@@ -32,7 +32,9 @@ def _frame(n, seed=0, quat=True):
 
 def _expected_segment_sizes(count, n, chunk=None):
     n_parts = (n + 255) // 256
-    size = chunk or max(8, math.ceil(count * ((n_parts + 3) // 4) / (148 * 16)))
+    blocks = (n_parts + 3) // 4
+    floor = 8 if blocks >= 592 else (4 if blocks >= 148 else 2)  # small systems: more, shorter segments
+    size = chunk or max(floor, math.ceil(count * blocks / (148 * 16)))
     size = math.ceil(count / math.ceil(count / size))
     return [min(size, count - first) for first in range(0, count, size)]
 
