@@ -240,3 +240,24 @@ def run_all(device, peak, cpu_baseline=True, tmpdir=None):
     except Exception as exc:
         out["2_order"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+
+    REPO = Path(__file__).resolve().parent
+    for _p in (REPO, REPO / "statdyn-analysis_b200"):
+        if str(_p) not in sys.path:
+            sys.path.insert(0, str(_p))
+    import torch
+
+    import __graft_entry__
+
+    __graft_entry__.build()
+    peak = 6551.7
+    try:
+        peak = float(json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+    except (OSError, KeyError, ValueError):
+        pass
+    print(json.dumps(run_all(torch.device("cuda", 0), peak, cpu_baseline="--no-cpu-baseline" not in sys.argv)))
