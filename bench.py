@@ -50,11 +50,11 @@ N_ORIGINS = 200
 WAVE_NUMBER = 2.9
 PIPELINE = int(os.environ.get("SDB_BENCH_PIPELINE", "2"))  # frames in flight before the oldest result is read
 SIGMA_R, SIGMA_T = 0.01, 0.02
-# Distinct consecutive frames of the measured steps.  The device-resident loop gets as many as it can use (no frame
-# is seen twice in a run of the default length); if the memory budgets below cap the pool, it is walked back and
-# forth (every step is still one genuine walk step; a reversal makes the top-10 % thresholds of young origins jump,
-# which costs their `overlap` selection one exact pass).
-POOL = int(os.environ.get("SDB_BENCH_POOL", "1300"))
+# Distinct consecutive frames of the measured steps, walked back and forth: every step is one genuine walk step, and
+# the regime stays what it is called -- with fresh frames throughout, the `early` origins would be `aged` before a
+# second of timed regions is over.  (A reversal makes the top-10 % thresholds of young origins jump, which costs
+# their `overlap` selection one exact pass per 63 steps.)
+POOL = int(os.environ.get("SDB_BENCH_POOL", "64"))
 POOL_DEVICE_BYTES = float(os.environ.get("SDB_BENCH_POOL_GB", "36")) * 1e9
 POOL_FILE_BYTES = float(os.environ.get("SDB_BENCH_FILE_GB", "4")) * 1e9
 AGE_STRIDE = {"aged": 10, "early": 1}

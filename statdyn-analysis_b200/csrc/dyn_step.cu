@@ -24,6 +24,8 @@ struct StepArgs {
     const SdbOrigin* origins;
     const SdbSegment* segments;
     double* partials;    // double[n_origins][n_parts][SDB_NSUM]
+    double* sums;        // double[n_origins][SDB_NSUM] or nullptr: the warp of tile 0 clears the `struct` slot of every
+                         // origin it passes (the struct kernel then needs no separate clear)
     const double (*atan_tab)[2];
     int n_parts;
     int full_parts;  // number of complete 256-molecule tiles (a partial last tile may follow)
@@ -442,6 +444,7 @@ __device__ __forceinline__ void dyn_step_tile(const StepArgs& a, StepWarpShared&
         uint8_t* fbase = org.d_flags;
         uint32_t* sbase = org.d_status;
         double* out = a.partials + ((long)o * a.n_parts + part) * SDB_NSUM;
+        if (SUMS && part == 0 && lane == 0 && a.sums) a.sums[(long)o * SDB_NSUM + SDB_S_STRUCT] = 0.0;
         const unsigned char* st = sh.stage[slot];
         sdb_mbar_wait(&sh.bar[slot], parity);
         slot = slot + 1 == SDB_STAGES ? 0 : slot + 1;
@@ -961,6 +964,7 @@ int sdb_dyn_step_launch(const SdbDynParams* h_params, const float* d_pos, const 
     a.origins = d_origins;
     a.segments = d_segments;
     a.partials = d_partials;
+    a.sums = p.do_sums ? d_sums : nullptr;
     a.atan_tab = sdb_device_atan_table();
     a.n_parts = sdb_dyn_num_parts(p.n);
     if (!a.atan_tab) return SDB_ECUDA;

@@ -206,6 +206,34 @@ struct SdbEngine {
     std::vector<SegRow> seg_rows;
 
     // ---- memory -----------------------------------------------------------------------------------------
+    // Per-origin blocks and previous-sample frames come out of large slabs: a run with hundreds of origins then
+    // costs a handful of cudaMalloc / cudaFree calls instead of hundreds (cudaFree synchronises the device, a few
+    // ms each at the end of every process_file).  Blocks are recycled through free lists, never returned.
+    struct Slab {
+        char* base;
+        size_t size, used;
+    };
+    std::vector<Slab> slabs;
+    int arena_alloc(void** p, size_t bytes)
+    {
+        bytes = (bytes + 255) & ~size_t(255);
+        if (slabs.empty() || slabs.back().used + bytes > slabs.back().size) {
+            size_t want = std::min<size_t>(std::max<size_t>(16 * bytes, size_t(64) << 20), size_t(1) << 30);
+            want = std::max(want, bytes);
+            Slab sl{nullptr, want, 0};
+            int rc = dev_alloc(reinterpret_cast<void**>(&sl.base), want);
+            if (rc && want > bytes) {  // not enough memory for a whole slab: exactly what is needed
+                sl.size = bytes;
+                rc = dev_alloc(reinterpret_cast<void**>(&sl.base), bytes);
+            }
+            if (rc) return rc;
+            slabs.push_back(sl);
+        }
+        *p = slabs.back().base + slabs.back().used;
+        slabs.back().used += bytes;
+        return SDB_OK;
+    }
+
     int dev_alloc(void** p, size_t bytes)
     {
         if (bytes == 0) bytes = 16;
@@ -270,7 +298,7 @@ struct SdbEngine {
             o = new Origin{};
             size_t off_status, off_flags;
             const size_t bytes = origin_block_layout(&off_status, &off_flags);
-            *rc = dev_alloc(reinterpret_cast<void**>(&o->block), bytes);
+            *rc = arena_alloc(reinterpret_cast<void**>(&o->block), bytes);
             if (*rc) {
                 delete o;
                 return nullptr;
@@ -301,7 +329,7 @@ struct SdbEngine {
             return f;
         }
         PoolFrame* f = new PoolFrame{};
-        *rc = dev_alloc(reinterpret_cast<void**>(&f->planes), sizeof(float) * 4 * (size_t)stride);
+        *rc = arena_alloc(reinterpret_cast<void**>(&f->planes), sizeof(float) * 4 * (size_t)stride);
         if (*rc) {
             delete f;
             return nullptr;
@@ -771,18 +799,10 @@ struct SdbEngine {
         dev_free(d_partials);
         dev_free(d_ov_ws);
         dev_free(d_inc_ws);
-        for (auto& kv : origins) {
-            dev_free(kv.second->block);
-            delete kv.second;
-        }
-        for (Origin* o : free_origins) {
-            dev_free(o->block);
-            delete o;
-        }
-        for (PoolFrame* f : pool) {
-            dev_free(f->planes);
-            delete f;
-        }
+        for (auto& kv : origins) delete kv.second;
+        for (Origin* o : free_origins) delete o;
+        for (PoolFrame* f : pool) delete f;
+        for (Slab& sl : slabs) dev_free(sl.base);
     }
 };
 

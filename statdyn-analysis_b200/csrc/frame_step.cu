@@ -158,7 +158,10 @@ int sdb_frame_step_impl(const SdbDynParams* h_params, const float* d_pos, const 
         prof_copy = *prof;  // the vector may grow under another thread; the handles stay valid
         cudaEventRecord(prof_copy.ev[0], s);
     }
-    SideStream* side = sums ? side_stream() : nullptr;
+    // small systems: every kernel of the frame takes a few microseconds and the six event calls of the fork / join
+    // cost the host more than the overlap gains (SDB_SIDE_MIN_N overrides the threshold)
+    static const int side_min_n = [] { const char* e = getenv("SDB_SIDE_MIN_N"); return e ? atoi(e) : 0; }();
+    SideStream* side = (sums && h_params->n >= side_min_n) ? side_stream() : nullptr;
     if (use_ov) {
         // overlap prepare needs only the descriptors (and, for sampled brackets, the state before the update)
         void* ps = stream;
@@ -265,8 +268,9 @@ int sdb_frame_step_impl(const SdbDynParams* h_params, const float* d_pos, const 
     if (do_struct) {
         for (int g = 0; g < n_groups; ++g) {
             if (g > 0) cudaStreamWaitEvent(s, side->group_done[g - 1], 0);
-            rc = sdb_struct(d_origins + org_lo[g], org_lo[g + 1] - org_lo[g], h_params->n, h_params->stride, h_sites_xy,
-                            n_sites, struct_dist, struct_mode, d_sums + (size_t)org_lo[g] * SDB_NSUM, stream);
+            // (dyn_step_kernel has cleared the struct slots of every origin of the frame)
+            rc = sdb_struct_launch(d_origins + org_lo[g], org_lo[g + 1] - org_lo[g], h_params->n, h_params->stride, h_sites_xy,
+                                   n_sites, struct_dist, struct_mode, d_sums + (size_t)org_lo[g] * SDB_NSUM, 0, stream);
             if (rc) return rc;
         }
     }

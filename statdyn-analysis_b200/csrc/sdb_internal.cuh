@@ -33,6 +33,10 @@ int sdb_dyn_step_launch(const SdbDynParams* h_params, const float* d_pos, const 
                         int32_t inc_sets, int32_t finalize, void* stream);
 int sdb_dyn_finalize(const double* d_partials, int32_t n, double* d_sums, int32_t n_origins, int32_t with_ov, void* stream);
 
+// sdb_struct with the clear of the SDB_S_STRUCT slots optional: csrc/struct.cu
+int sdb_struct_launch(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride, const float* h_sites_xy,
+                      int32_t n_sites, double dist, int32_t mode, double* d_sums, int32_t clear, void* stream);
+
 // row sums + overlap selection + intersection in one launch: csrc/overlap.cu
 int sdb_overlap_resolve_fused(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride, int32_t k, void* d_ws,
                               int32_t ws_origins, const double* d_partials, double* d_sums, void* stream);

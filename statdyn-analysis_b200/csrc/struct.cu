@@ -279,6 +279,14 @@ extern "C" int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t
                           const float* h_sites_xy, int32_t n_sites, double dist, int32_t mode, double* d_sums,
                           void* stream)
 {
+    return sdb_struct_launch(d_origins, n_origins, n, stride, h_sites_xy, n_sites, dist, mode, d_sums, 1, stream);
+}
+
+// clear == 0: the SDB_S_STRUCT slots have been zeroed on this stream already (dyn_step_kernel does it in
+// sdb_frame_step: one launch less per frame)
+int sdb_struct_launch(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride, const float* h_sites_xy,
+                      int32_t n_sites, double dist, int32_t mode, double* d_sums, int32_t clear, void* stream)
+{
     if (!d_origins || !h_sites_xy || !d_sums || n <= 0 || n_sites <= 0 || n_sites > 8 || mode < 0 || mode > 1 ||
         (long long)n * n_sites >= 0xffffffffLL) {
         sdb_set_error("sdb_struct: bad argument");
@@ -302,10 +310,12 @@ extern "C" int sdb_struct(const SdbOrigin* d_origins, int32_t n_origins, int32_t
         a.sx[i] = h_sites_xy[2 * i];
         a.sy[i] = h_sites_xy[2 * i + 1];
     }
-    int rc = sdb_check_cuda(cudaMemset2DAsync(d_sums + SDB_S_STRUCT, SDB_NSUM * sizeof(double), 0, sizeof(double),
-                                              (size_t)n_origins, s),
-                            "sdb_struct: clear");
-    if (rc) return rc;
+    if (clear) {
+        int rc = sdb_check_cuda(cudaMemset2DAsync(d_sums + SDB_S_STRUCT, SDB_NSUM * sizeof(double), 0, sizeof(double),
+                                                  (size_t)n_origins, s),
+                                "sdb_struct: clear");
+        if (rc) return rc;
+    }
     // grid.x blocks per origin, each striding over the 1024-molecule tiles; sized so that the grid is a
     // whole number of waves (148 SMs x 5 resident blocks of 256 threads at 48 registers)
     // (struct3_kernel: one block iteration covers 256 groups of each of the three sites = 3072 molecules)

@@ -18,6 +18,7 @@ File layout (GSD file-layer v1.0 / v2.0):
 """
 
 import mmap
+import os
 import struct
 from pathlib import Path
 
@@ -143,11 +144,34 @@ class GSDTrajectory:
             torch = _lib.torch()
             if not torch.cuda.is_available():
                 return False
+            lib = _lib.load()
             view = np.frombuffer(self._mm, dtype=np.uint8)
             addr, size = view.ctypes.data, view.nbytes
-            if _lib.load().sdb_host_register(addr, size) != 0:
-                self.pin_error = _lib.load().sdb_last_error().decode()
+            if size > int(float(os.environ.get("SDB_PIN_MAX_GB", "16")) * 2 ** 30):
+                self.pin_error = "file larger than SDB_PIN_MAX_GB"
                 return False
+            if lib.sdb_host_register(addr, size) != 0:
+                self.pin_error = lib.sdb_last_error().decode()
+                # the driver pins pages through a writable mapping only: map the file read-write when its
+                # permissions allow (nothing is ever written through it; the views handed out stay read-only)
+                del view
+                try:
+                    fh = open(self.filename, "r+b")
+                    mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_WRITE)
+                except (OSError, ValueError) as exc:
+                    self.pin_error += f"; no writable mapping: {exc}"
+                    return False
+                view = np.frombuffer(mm, dtype=np.uint8)
+                addr, size = view.ctypes.data, view.nbytes
+                if lib.sdb_host_register(addr, size) != 0:
+                    self.pin_error += "; writable mapping: " + lib.sdb_last_error().decode()
+                    del view
+                    mm.close()
+                    fh.close()
+                    return False
+                self._fh_ro, self._mm_ro = self._fh, self._mm  # views handed out earlier keep the old mapping alive
+                self._fh, self._mm = fh, mm
+                self.pin_error = None
             self._pinned_addr = addr
             _lib.register_pinned(addr, size)
             return True
@@ -190,6 +214,8 @@ class GSDTrajectory:
                 if dtype is None or loc + n * m * dtype.itemsize > len(self._mm):
                     raise RuntimeError(f"corrupt chunk {name} in frame {frame}")
                 arr = np.frombuffer(self._mm, dtype=dtype, count=n * m, offset=loc)
+                if arr.flags.writeable:  # (mapping made writable for pinning: the views stay read-only)
+                    arr.flags.writeable = False
                 return arr.reshape(n, m) if m > 1 else arr
         return None
 

@@ -8,6 +8,7 @@ trajectory and the step schedule disagree and the ``keyframe_max + 1`` origins o
 """
 
 import logging
+import os
 from pathlib import Path
 from typing import Iterator, List, Optional, Tuple
 
@@ -23,7 +24,10 @@ _LAST_FRAME_ATTEMPTS = 10
 
 def iter_trajectory(trajectory: GSDTrajectory) -> Iterator[HoomdFrame]:
     """Readable frames in file order; a frame that fails to decode is logged and left out
-    (reference ``_gsd.py:31-52``)."""
+    (reference ``_gsd.py:31-52``).  The file mapping is page-locked when the driver allows, so that frames are
+    uploaded straight from the page cache (otherwise they are staged through the engine's pinned ring)."""
+    if os.environ.get("SDB_PIN_TRAJECTORY", "1") == "1":
+        trajectory.pin()
     for position in range(len(trajectory)):
         try:
             snapshot = trajectory[position]

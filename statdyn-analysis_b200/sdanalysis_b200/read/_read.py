@@ -27,29 +27,86 @@ from ._lammps import parse_lammpstrj, read_lammps_trajectory
 logger = logging.getLogger(__name__)
 
 
-def _write_table(df: pandas.DataFrame, filename: Path, group: str, append: bool) -> None:
-    """HDF5 like the reference when PyTables is present (``_read.py:57-61``: one file, one group per
-    table); otherwise parquet / CSV: the ``dynamics`` table goes to ``filename`` itself, any other
-    table to ``<stem>.<group><suffix>`` next to it."""
+# Open parquet writers of this process, by target path: a parquet file is appended to one row group at a time
+# through a writer that stays open until the tables of the run are closed (`close_tables`).
+_parquet_writers: Dict[str, Any] = {}
+
+
+def _table_target(filename: Path, group: str):
+    """(kind, path) of the file a table goes to: HDF5 like the reference when PyTables is present
+    (``_read.py:57-61``: one file, one group per table); otherwise parquet / CSV -- the ``dynamics`` table goes to
+    ``filename`` itself, any other table to ``<stem>.<group><suffix>`` next to it."""
     filename = Path(filename)
     if filename.suffix in (".h5", ".hdf5", ".hdf"):
         try:
             import tables  # noqa: F401
 
-            df.to_hdf(filename, key=group, format="table", append=append)
-            return
+            return "hdf", filename
         except ImportError:
             logger.warning("PyTables is not installed: writing %s as parquet instead of HDF5", group)
             filename = filename.with_suffix(".parquet")
     if filename.suffix not in (".parquet", ".csv"):
         filename = filename.with_suffix(".parquet")
     target = filename if group == "dynamics" else filename.with_suffix(f".{group}{filename.suffix}")
-    if target.suffix == ".csv":
+    return ("csv" if target.suffix == ".csv" else "parquet"), target
+
+
+def _write_table(df: pandas.DataFrame, filename: Path, group: str, append: bool) -> None:
+    """Write (``append=False``: start) or extend a table.  Appending never re-reads what is already on disk:
+    HDF5 tables and CSV files are extended in place, parquet files one row group per call."""
+    kind, target = _table_target(filename, group)
+    if kind == "hdf":
+        df.to_hdf(target, key=group, format="table", append=append)
+        return
+    if kind == "csv":
         df.to_csv(target, mode="a" if append else "w", header=not append, index=False)
         return
-    if append and target.exists():
-        df = pandas.concat([pandas.read_parquet(target), df], ignore_index=True)
-    df.to_parquet(target, index=False)
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    key = str(target)
+    table = pa.Table.from_pandas(df, preserve_index=False)
+    writer = _parquet_writers.get(key)
+    if writer is not None and not append:
+        writer.close()
+        writer = None
+    if writer is None:
+        if append and target.exists():
+            # the file was closed by an earlier run: its rows move into the new writer once, then row groups follow
+            old = pq.read_table(target)
+            writer = pq.ParquetWriter(target, old.schema)
+            writer.write_table(old)
+        else:
+            writer = pq.ParquetWriter(target, table.schema)
+        _parquet_writers[key] = writer
+    if table.schema != writer.schema:
+        table = table.cast(writer.schema)
+    writer.write_table(table)
+
+
+def close_tables(filename: Optional[Path] = None) -> None:
+    """Finish the parquet files written through :func:`_write_table` (all of them, or those of ``filename``)."""
+    prefix = None if filename is None else str(Path(filename).with_suffix(""))
+    for key in list(_parquet_writers):
+        if prefix is None or key.startswith(prefix):
+            _parquet_writers.pop(key).close()
+
+
+def write_molecular_relaxations(engine, outfile: Path, temperature: float, pressure: float, keys=None) -> int:
+    """The ``molecular_relaxations`` table (reference ``_read.py:177-190``: one row per (keyframe, molecule) with
+    the passage time of every tracker), streamed one origin at a time: origins x N rows never exist at once (1 M
+    molecules x 200 origins would be 2e8 rows).  Returns the number of rows written."""
+    keys = list(engine.origins.keys()) if keys is None else list(keys)
+    rows = 0
+    molecule = np.arange(engine.n, dtype=np.int64)
+    for i, key in enumerate(keys):
+        columns = {"keyframe": np.full(engine.n, key), "molecule": molecule}
+        columns.update(engine.summary(key))
+        columns["temperature"] = np.full(engine.n, temperature, dtype=np.float64)
+        columns["pressure"] = np.full(engine.n, pressure, dtype=np.float64)
+        _write_table(pandas.DataFrame(columns), Path(outfile), "molecular_relaxations", append=i > 0)
+        rows += engine.n
+    return rows
 
 
 class WriteCache:
@@ -96,6 +153,11 @@ class WriteCache:
         self._blocks.clear()
         self._block_rows = 0
 
+    def close(self) -> None:
+        """Finish the output file (a parquet file becomes readable when its writer is closed; HDF5 / CSV need nothing)."""
+        if self._filename is not None:
+            close_tables(self.filename)
+
     @property
     def filename(self) -> Optional[Path]:
         return None if self._filename is None else Path(self._filename)
@@ -108,8 +170,7 @@ class WriteCache:
             return pandas.DataFrame.from_records(self._cache)
         columns = list(self._blocks[0].keys())
         merged = pandas.DataFrame({
-            name: np.concatenate([np.broadcast_to(np.asarray(b[name]), (len(b["keyframe"]),)) for b in self._blocks])
-            for name in columns
+            name: np.concatenate([np.asarray(b[name]) for b in self._blocks]) for name in columns
         })
         if self._cache:
             merged = pandas.concat([pandas.DataFrame.from_records(self._cache), merged], ignore_index=True)
@@ -138,19 +199,55 @@ def process_frames(
     box_warned = False
     pending = deque()
 
+    # table_sink: results are finalised in batches -- the closed forms of compute_all are ~15 numpy expressions,
+    # which cost as much per call for one frame as for a hundred
+    batch = []  # (keys, timediffs, sums, isf or None)
+    batch_rows = 0
+
+    def flush_batch():
+        nonlocal batch_rows
+        if not batch:
+            return
+        items, batch_rows = list(batch), 0
+        batch.clear()
+
+        def emit(part):
+            sums = np.concatenate([it[2] for it in part])
+            timediffs = np.concatenate([np.asarray(it[1], dtype=np.int64) for it in part])
+            table = engine.finalize_table(sums, timediffs)  # ValueError: a row with non-unit quaternions
+            if part[0][3] is not None:
+                table["scattering_function"] = np.concatenate([it[3] for it in part]) / engine.n
+            keys = [k for it in part for k in it[0]]
+            table["keyframe"] = np.asarray(keys) if all(isinstance(k, (int, np.integer)) for k in keys) else keys
+            table["temperature"] = np.full(len(keys), temperature)
+            table["pressure"] = np.full(len(keys), pressure)
+            table_sink(table)
+
+        try:
+            emit(items)
+        except (ValueError, RuntimeError):
+            for it in items:  # find the offending frame(s); the others keep their rows (_read.py:154-156)
+                try:
+                    emit([it])
+                except (ValueError, RuntimeError) as e:
+                    logger.warning(e)
+
     def drain(limit):
+        nonlocal batch_rows
         while len(pending) > limit:
             result = pending.popleft()
             if table_sink is not None:
+                if not result.keys:
+                    continue
                 try:
-                    table = result.table()
+                    sums = result.sums()
                 except (ValueError, RuntimeError) as e:  # _read.py:154-156
                     logger.warning(e)
                     continue
-                count = len(result.keys)
-                table["temperature"] = np.full(count, temperature)
-                table["pressure"] = np.full(count, pressure)
-                table_sink(table)
+                batch.append((result.keys, result.timediffs, sums, result._isf))
+                batch_rows += len(result.keys)
+                if len(batch) >= 256 or batch_rows >= 8192:
+                    flush_batch()
                 continue
             try:
                 rows = result.rows()
@@ -198,6 +295,7 @@ def process_frames(
             continue
         drain(pipeline_depth - 1)
     drain(0)
+    flush_batch()
     return engine
 
 
@@ -255,13 +353,8 @@ def process_file(
     if outfile is not None:
         dataframes.flush()
         if engine is not None and engine.trackers:
-            keys = list(engine.origins.keys())
-            mol_relax = pandas.concat((pandas.DataFrame(engine.summary(k)) for k in keys), keys=keys)
-            mol_relax["temperature"] = temperature
-            mol_relax["pressure"] = pressure
-            mol_relax.index.names = ["keyframe", "molecule"]
-            mol_relax = mol_relax.reset_index()
-            _write_table(mol_relax, Path(outfile), "molecular_relaxations", False)
+            write_molecular_relaxations(engine, Path(outfile), temperature, pressure)
+        close_tables(Path(outfile))
         return None
 
     df = dataframes.to_dataframe()

@@ -144,9 +144,38 @@ def test_write_cache(tmp_path):
     assert len(cache._cache) == 9000 - 8192 and len(cache) == 9000
     cache.flush()
     assert len(cache._cache) == 0 and out.is_file()
+    cache.close()  # parquet: the row groups written by the flushes become a readable file
     import pandas
 
     assert len(pandas.read_parquet(out)) == 9000
+    # appending never re-reads the file while the run is open: one row group per flush
+    import pyarrow.parquet as pq
+
+    assert pq.ParquetFile(out).num_row_groups == 2
+
+
+def test_write_cache_column_blocks_and_append_after_close(tmp_path):
+    """Column blocks (one per frame, what process_file feeds) end up as rows in order; a table closed by an
+    earlier run is extended by a later one."""
+    import pandas
+
+    from sdanalysis_b200.read._read import _write_table, close_tables
+
+    out = tmp_path / "blocks.parquet"
+    cache = WriteCache(out)
+    for frame in range(30):
+        count = 1 + frame % 4
+        cache.append_table({"time": np.full(count, frame), "msd": np.arange(count, dtype=float), "keyframe": np.arange(count)})
+    assert len(cache) == sum(1 + f % 4 for f in range(30))
+    df = cache.to_dataframe()
+    assert df["time"].tolist() == [f for f in range(30) for _ in range(1 + f % 4)]
+    cache.flush()
+    cache.close()
+    first = pandas.read_parquet(out)
+    assert first.equals(df)
+    _write_table(df.iloc[:5], out, "dynamics", append=True)
+    close_tables(out)
+    assert len(pandas.read_parquet(out)) == len(df) + 5
 
 
 def test_filename_variables():
