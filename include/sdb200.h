@@ -276,6 +276,9 @@ int sdb_rdf_histogram(const float* h_box, int32_t is2d, int32_t n, const float* 
 int sdb_host_register(void* h_ptr, size_t bytes);
 int sdb_host_unregister(void* h_ptr);
 
+/* Diagnostics: the engine's multi-threaded host copy (SDB_MEM_HOST staging) on caller buffers. */
+void sdb_test_host_copy(void* h_dst, const void* h_src, size_t bytes);
+
 const char* sdb_last_error(void);
 const char* sdb_version(void);
 /* Number of kernels launched by this library since load (used by bench.py's gpu_launches). */

@@ -1064,3 +1064,6 @@ extern "C" int32_t sdb_engine_last_descriptors(SdbEngine* e, void* h_out, int32_
     if (h_out && bytes > 0) memcpy(h_out, e->last_desc.data(), (size_t)bytes);
     return bytes;
 }
+
+// Test / diagnostics hook: the engine's multi-threaded host copy (pageable -> pinned staging) on caller buffers.
+extern "C" void sdb_test_host_copy(void* dst, const void* src, size_t bytes) { CopyPool::instance().copy(dst, src, bytes); }
