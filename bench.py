@@ -349,6 +349,7 @@ def run_gpu(args):
         barrier()
 
         # ---- stepping ---------------------------------------------------------------------------------------
+        hostprof = {} if os.environ.get("SDB_BENCH_HOSTPROF") == "1" else None  # diagnostics: where the host loop waits
         state = {"i": 0}  # index of the next measured step
         results, tables, posted = [], [], {}
         keep_tables = warmup + 1 if with_parity else 0
@@ -379,6 +380,21 @@ def run_gpu(args):
                     posted[i] = post(*frame_of(source, i))
                 posted[i + 1] = post(*frame_of(source, i + 1))
                 sharded.step(ts, all_keys, posted.pop(i), gather="batch")
+                return
+            if hostprof is not None:
+                h0 = time.perf_counter()
+                pos, quat = frame_of(source, i)
+                h1 = time.perf_counter()
+                results.append((i, engine.step(ts, pos, quat, all_keys)))
+                h2 = time.perf_counter()
+                if len(results) > PIPELINE:
+                    collect(results.pop(0))
+                h3 = time.perf_counter()
+                rec = hostprof.setdefault(source, [0.0, 0.0, 0.0, 0])
+                rec[0] += h1 - h0
+                rec[1] += h2 - h1
+                rec[2] += h3 - h2
+                rec[3] += 1
                 return
             pos, quat = frame_of(source, i)
             results.append((i, engine.step(ts, pos, quat, all_keys)))
@@ -515,6 +531,10 @@ def run_gpu(args):
                         state_np.update(part)
             if rank == 0:
                 parity, cpu = _oracle_parity(np, n, box, oracle_frames, pool_host, t_first, warmup, tables, state_np, sorted(sparse))
+        if hostprof:
+            for source, (t_frame, t_step, t_collect, count) in hostprof.items():
+                print(f"[hostprof {regime} {source}] per step: frame lookup {1e3*t_frame/count:.3f} ms, engine.step {1e3*t_step/count:.3f} ms, "
+                      f"collect (wait for step i-{PIPELINE}) {1e3*t_collect/count:.3f} ms over {count} steps", file=sys.stderr, flush=True)
         exchange = None if sharded is None else sharded.exchange
         exchange_note = "" if sharded is None else sharded.exchange_note
         del engine, sharded
