@@ -91,7 +91,7 @@ def main():
             m_rows = order(table)
             assert set(m_rows) == set(s_rows), "row sets differ"
             identical = all(
-                all((m_rows[k][q] == s_rows[k][q]) or (np.isnan(m_rows[k][q]) and np.isnan(s_rows[k][q])) for q in s_rows[k])
+                all((m_rows[k][q] == s_rows[k][q]) or (np.isnan(m_rows[k][q]) and np.isnan(s_rows[k][q])) for q in m_rows[k])
                 for k in s_rows
             )
             compare_rows([m_rows[(r["keyframe"], r["time"])] for r in ref_rows], ref_rows, n)
