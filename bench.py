@@ -290,9 +290,10 @@ def run_gpu(args):
             def step_fn(ts, pos, quat, keys, rows_out=0):
                 return engine.step(ts, pos, quat, keys, to_host=False, rows_out=rows_out)
 
+            # (max_local must be the same on every rank: symmetric buffers are sized with it)
             sharded = ShardedDynamics(
-                n, step_fn, max_local=len(local_keys) + 1, device=device, batch=max(steps, warmup, prof_steps, 25 * steps) + 1,
-                direct_rows=True,
+                n, step_fn, max_local=(n_origins + world - 1) // world + 1, device=device, batch=max(steps, warmup, prof_steps) + 1,
+                direct_rows=os.environ.get("SDB_BENCH_DIRECT_ROWS", "1") == "1",
             )
         # every rank runs the same seeded walk on its own device (the frames of the device-resident phase are
         # held sharded by rows when there are several ranks)
@@ -531,6 +532,16 @@ def run_gpu(args):
                         state_np.update(part)
             if rank == 0:
                 parity, cpu = _oracle_parity(np, n, box, oracle_frames, pool_host, t_first, warmup, tables, state_np, sorted(sparse))
+        if sharded is not None and sharded.stalls:
+            # diagnostics (SDB_SHARD_PROFILE=1): how long the compute stream waited for a frame, and how long the
+            # exchange of a frame took on the side stream
+            torch.cuda.synchronize()
+            stalls = [a.elapsed_time(b) for a, b in sharded.stalls]
+            xch = [a.elapsed_time(b) for a, b in sharded.exchange_times]
+            half = len(stalls) // 2
+            print(f"[rank {rank} {regime}] frame-wait stall per step: device phase mean {sum(stalls[:half]) / max(half, 1):.3f} ms, "
+                  f"e2e phase mean {sum(stalls[half:]) / max(len(stalls) - half, 1):.3f} ms (max {max(stalls):.3f}); exchange on the side "
+                  f"stream mean {sum(xch) / max(len(xch), 1):.3f} ms (max {max(xch):.3f}) over {len(stalls)} steps", file=sys.stderr, flush=True)
         if hostprof:
             for source, (t_frame, t_step, t_collect, count) in hostprof.items():
                 print(f"[hostprof {regime} {source}] per step: frame lookup {1e3*t_frame/count:.3f} ms, engine.step {1e3*t_step/count:.3f} ms, "

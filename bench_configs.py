@@ -202,13 +202,16 @@ def _order_config(device, peak, cpu_baseline):
                   "missing_in_list": int((as_np(nlist).astype(np.int64) & 0xFFFFFFFF == 0xFFFFFFFF).sum())},
     }
     host_frames = [(p.cpu().numpy(), q.cpu().numpy()) for p, q in frames[:100]]
+    for p, q in host_frames:  # read-only like the views of a memory-mapped trajectory: the three calls share one build
+        p.flags.writeable = False
+        q.flags.writeable = False
     one_pass(host_frames[:10], True)
     e2e_times = [one_pass(host_frames, True)[0] for _ in range(3)]
     e2e_sec = statistics.median(e2e_times)
     record["e2e"] = {
         "value": n * len(host_frames) / e2e_sec, "unit": "molecule*frames/s", "ms_per_frame": 1e3 * e2e_sec / len(host_frames),
         "h2d_bytes_per_frame": 28 * n, "d2h_bytes_per_frame": (8 * 4 + 8 + 4) * n,
-        "source": "numpy frames in, numpy results out (three public calls per frame)",
+        "source": "read-only numpy frames in (like gsdio's mmap views), numpy results out (three public calls per frame, one build)",
     }
     if cpu_baseline:
         from oracle import order as oorder

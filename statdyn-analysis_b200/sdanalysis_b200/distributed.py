@@ -78,6 +78,12 @@ class ShardedDynamics:
         # rank 0's row buffer, enqueued by the same native call as the kernels
         self.direct_rows = bool(direct_rows)
         self.max_local = int(max_local)
+        if self.world > 1:
+            # symmetric buffers and the batched gather are sized with max_local: every rank must use the same value
+            # (ranks own ceil or floor(K / R) origins): agree on the largest one
+            t = torch.tensor([self.max_local], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            self.max_local = int(t.item())
         self.depth = int(depth)
         self.qoff = (3 * self.n + 3) // 4 * 4
         self.slot_floats = (frame_floats(self.n) + 3) // 4 * 4  # 16-byte multiple
