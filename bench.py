@@ -14,7 +14,8 @@ Two regimes of that workload are timed (``regimes`` in the JSON line; ``--headli
 * ``aged``   (headline) origins created 10 timesteps apart, i.e. aged 0 ... 2000 steps like in the last
              frames of the 2000-frame run: |dr| is of the order of the relaxation distance, `struct` ~ 0.5,
              passage trackers fire continuously.
-* ``early``  origins aged 1 ... 225 steps (round 1's only regime): almost nothing is near a threshold.
+* ``early``  origins aged 1 ... 225 steps (round 1's only regime): almost nothing is near a threshold.  Its frames
+             are 0.1 timestep apart so that the origins stay young while >= 1 s of regions is timed.
 
 * ``value``  frames already resident in HBM when the timed region starts.  The K-step region (barrier +
              synchronize on both sides) is repeated until >= 1 s has been timed; ``value`` is the median.
@@ -50,11 +51,15 @@ N_ORIGINS = 200
 WAVE_NUMBER = 2.9
 PIPELINE = int(os.environ.get("SDB_BENCH_PIPELINE", "2"))  # frames in flight before the oldest result is read
 SIGMA_R, SIGMA_T = 0.01, 0.02
-# Distinct consecutive frames of the measured steps, walked back and forth: every step is one genuine walk step, and
-# the regime stays what it is called -- with fresh frames throughout, the `early` origins would be `aged` before a
-# second of timed regions is over.  (A reversal makes the top-10 % thresholds of young origins jump, which costs
-# their `overlap` selection one exact pass per 63 steps.)
-POOL = int(os.environ.get("SDB_BENCH_POOL", "64"))
+# Distinct consecutive frames of the measured steps: as many as a default run uses, so that no frame is seen twice
+# (a trajectory never runs backwards: walking a short pool back and forth was tried and makes the top-10 %
+# thresholds of young origins jump at every reversal, which sends their `overlap` selection to the exact kernel
+# for a few frames -- at 25 origins per GPU that doubled the step time of one region in three).  If the memory
+# budgets below cap the pool it is walked back and forth after all (4 M-molecule runs, the e2e file).
+# The frames of the `early` regime are 0.1 timestep apart, so that its origins stay young for the >= 1 s of timed
+# regions (650 frames = 65 timesteps); the `aged` regime ages by one timestep per frame like the real run.
+POOL = int(os.environ.get("SDB_BENCH_POOL", "1300"))
+FRAME_DT = {"aged": 1.0, "early": 0.1}
 POOL_DEVICE_BYTES = float(os.environ.get("SDB_BENCH_POOL_GB", "36")) * 1e9
 POOL_FILE_BYTES = float(os.environ.get("SDB_BENCH_FILE_GB", "4")) * 1e9
 AGE_STRIDE = {"aged": 10, "early": 1}
@@ -343,7 +348,7 @@ def run_gpu(args):
                     writer.append(t_first + j, box, hp, hq, dimensions=2)
                 if with_parity and j <= warmup:
                     pool_host.append((hp, hq))
-            walk.advance(1)
+            walk.advance(FRAME_DT[regime])
         if writer is not None:
             writer.close()
         torch.cuda.synchronize()
@@ -669,8 +674,8 @@ def run_gpu(args):
             "l2": "inputs larger than L2 (>= 25 MB of state per origin and step)",
             "timing": f"{steps}-step region (barrier + synchronize on both sides) repeated {head_rec['regions']['regions']} times "
                       f"= {head_rec['regions']['timed_seconds']:.2f} s; value = median region",
-            "frames": f"{pool_size} consecutive frames resident in HBM (walked back and forth when a run needs more); "
-                      f"e2e: a GSD file of {file_frames} frames",
+            "frames": f"{pool_size} consecutive frames resident in HBM (walked back and forth only if a run needs more), "
+                      f"{FRAME_DT[regimes[0]]} timestep apart; e2e: a GSD file of the first {file_frames} of them",
         },
         "e2e": head_rec.get("e2e"),
         "gpu_launches": head["launches"],
