@@ -345,17 +345,21 @@ struct SdbEngine {
     }
 
     // ---- rings sized for `cap` origins ------------------------------------------------------------------
-    int ensure_capacity(int n_active)
+    // Small per-origin buffers (descriptors, rows) are sized for `small_cap` origins once -- they are a few hundred
+    // KB even for 1024 origins, and re-allocating page-locked memory in the middle of a run costs anything from a
+    // millisecond to hundreds of them.  The two workspaces that scale with origins x molecules (per-tile partial
+    // sums, overlap candidates) grow by factors of four.
+    int small_cap = 0;
+    int ensure_small(int n_active)
     {
-        if (n_active <= cap) return SDB_OK;
-        int want = 16;
+        if (n_active <= small_cap) return SDB_OK;
+        int want = 1024;
         while (want < n_active) want <<= 1;
-        if (!dry && cap > 0) {
-            // results of earlier steps still in the rings: keep their rows, then let the device drain
+        if (!dry && small_cap > 0) {
             int rc = sdb_check_cuda(cudaDeviceSynchronize(), "sdb_engine: synchronize before growing");
             if (rc) return rc;
         }
-        for (auto& sl : slots) {
+        for (auto& sl : slots) {  // results of earlier steps still in the rings keep their rows
             if (sl.ticket >= 0 && sl.host_rows && sl.has_sums && sl.stash.empty() && sl.h_sums)
                 sl.stash.assign(sl.h_sums, sl.h_sums + (size_t)sl.n_rows * SDB_NSUM);
             sl.pending = false;
@@ -384,18 +388,33 @@ struct SdbEngine {
                 if (rc) return rc;
             }
         }
+        small_cap = want;
+        desc_bytes_cap = n_desc;
+        return SDB_OK;
+    }
+
+    int ensure_capacity(int n_active)
+    {
+        int rc = ensure_small(n_active);
+        if (rc) return rc;
+        if (n_active <= cap) return SDB_OK;
+        int want = 16;
+        while (want < n_active) want <<= 2;
+        if (!dry && cap > 0) {
+            rc = sdb_check_cuda(cudaDeviceSynchronize(), "sdb_engine: synchronize before growing");
+            if (rc) return rc;
+        }
         dev_free(d_partials);
         dev_free(d_ov_ws);
         d_partials = nullptr;
         d_ov_ws = nullptr;
-        int rc = dev_alloc(reinterpret_cast<void**>(&d_partials), sizeof(double) * SDB_NSUM * (size_t)n_parts * want);
+        rc = dev_alloc(reinterpret_cast<void**>(&d_partials), sizeof(double) * SDB_NSUM * (size_t)n_parts * want);
         if (rc) return rc;
         if (cfg.compute_sums && cfg.overlap_k > 0) {
             rc = dev_alloc(&d_ov_ws, sdb_overlap_ws_bytes(want, n));
             if (rc) return rc;
         }
         cap = want;
-        desc_bytes_cap = n_desc;
         return SDB_OK;
     }
 

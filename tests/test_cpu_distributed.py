@@ -51,7 +51,10 @@ def _worker(rank, world, port, out):
             calls.append((timestep, list(keys)))
             return list(keys), [0 for _ in keys], sums
 
-        sharded = ShardedDynamics(N_MOLS, step_fn, max_local=8, device="cpu")
+        # ranks may own ceil or floor(K / R) origins and pass max_local accordingly: they agree on the largest
+        # (buffers shared between ranks are sized with it)
+        sharded = ShardedDynamics(N_MOLS, step_fn, max_local=8 - rank, device="cpu")
+        assert sharded.max_local == 8
         rng = np.random.default_rng(5)
         results = []
         handle = None
