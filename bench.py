@@ -260,7 +260,27 @@ def run_gpu(args):
     local_keys = partition(all_keys, rank, world)
     peak, peak_kind = _peaks()
     pool_size = max(2, min(POOL, int(POOL_DEVICE_BYTES // (28 * n))))
-    file_frames = max(2, min(pool_size, int(POOL_FILE_BYTES // (28 * n))))
+    # the e2e trajectory file: a RAM-backed directory when it has room (every rank maps the file), else /tmp, and
+    # never more than a third of what is free there
+    import shutil
+
+    tmpdir, file_budget = args.tmpdir, POOL_FILE_BYTES
+    for candidate in ([args.tmpdir] if args.tmpdir else []) + ["/dev/shm", "/tmp"]:
+        try:
+            free = shutil.disk_usage(candidate).free
+        except OSError:
+            continue
+        if free >= 3 * min(POOL_FILE_BYTES, 64 * 28 * n):
+            tmpdir, file_budget = candidate, min(POOL_FILE_BYTES, free / 3)
+            break
+    else:
+        tmpdir = args.tmpdir or "/tmp"
+        file_budget = min(POOL_FILE_BYTES, shutil.disk_usage(tmpdir).free / 3)
+    file_frames = max(2, min(pool_size, int(file_budget // (28 * n))))
+    if world > 1:  # rank 0 decides where the file goes and how long it is
+        decided = [tmpdir, file_frames]
+        dist.broadcast_object_list(decided, src=0)
+        tmpdir, file_frames = decided
     prof_steps = max(2, min(steps, 8))
     want_parity = args.parity == "on" or (args.parity == "auto" and world == 1 and not args.no_cpu_baseline)
     if n_origins < 3:
@@ -332,7 +352,7 @@ def run_gpu(args):
         lo, hi = sharded.slice_bounds() if sharded is not None else (0, n)
         pool_dev, pool_host = [], []
         tag = os.environ.get("MASTER_PORT", str(os.getpid())) if world > 1 else str(os.getpid())
-        gsd_path = Path(args.tmpdir) / f"sdb_bench_{tag}_{regime}.gsd"
+        gsd_path = Path(tmpdir) / f"sdb_bench_{tag}_{regime}.gsd"
         writer = GSDWriter(gsd_path) if (rank == 0 and not args.no_e2e) else None
         for j in range(pool_size):
             pos, quat = walk.frame()
@@ -783,7 +803,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[1] / configs[2] sub-records")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--tmpdir", default=os.environ.get("SDB_BENCH_TMP", "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"))
+    ap.add_argument("--tmpdir", default=os.environ.get("SDB_BENCH_TMP"), help="directory of the e2e trajectory file (default: /dev/shm or /tmp, whichever has room)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -276,6 +276,9 @@ int sdb_rdf_histogram(const float* h_box, int32_t is2d, int32_t n, const float* 
 int sdb_host_register(void* h_ptr, size_t bytes);
 int sdb_host_unregister(void* h_ptr);
 
+/* cudaMemcpyAsync(host -> device) on `stream`: the upload of a frame slice by a host that keeps its own device
+ * buffers (the multi-GPU sliced exchange) without going through a tensor library's synchronising copy. */
+int sdb_upload_async(void* d_dst, const void* h_src, size_t bytes, void* stream);
 /* Diagnostics: the engine's multi-threaded host copy (SDB_MEM_HOST staging) on caller buffers. */
 void sdb_test_host_copy(void* h_dst, const void* h_src, size_t bytes);
 

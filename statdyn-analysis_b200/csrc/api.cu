@@ -120,3 +120,16 @@ extern "C" int sdb_host_unregister(void* h_ptr)
     }
     return SDB_OK;
 }
+
+// Asynchronous host-to-device copy on `stream` (page-locked source: truly asynchronous; pageable source: the
+// runtime stages it, blocking the host but not synchronising the stream's earlier work away from the caller).
+extern "C" int sdb_upload_async(void* d_dst, const void* h_src, size_t bytes, void* stream)
+{
+    if (!d_dst || !h_src) {
+        sdb_set_error("sdb_upload_async: null argument");
+        return SDB_EINVAL;
+    }
+    if (bytes == 0) return SDB_OK;
+    return sdb_check_cuda(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)),
+                          "sdb_upload_async");
+}

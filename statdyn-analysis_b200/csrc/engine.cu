@@ -218,7 +218,11 @@ struct SdbEngine {
     {
         bytes = (bytes + 255) & ~size_t(255);
         if (slabs.empty() || slabs.back().used + bytes > slabs.back().size) {
-            size_t want = std::min<size_t>(std::max<size_t>(16 * bytes, size_t(64) << 20), size_t(1) << 30);
+            // geometric growth: an engine with one origin (the per-object Dynamics / Relaxations API creates one
+            // engine per object) stays at two blocks' worth; a run with hundreds of origins gets ~log2 slabs
+            size_t total = 0;
+            for (const Slab& sl : slabs) total += sl.size;
+            size_t want = std::min<size_t>(std::max<size_t>(2 * bytes, total), size_t(1) << 30);
             want = std::max(want, bytes);
             Slab sl{nullptr, want, 0};
             int rc = dev_alloc(reinterpret_cast<void**>(&sl.base), want);
@@ -345,16 +349,17 @@ struct SdbEngine {
     }
 
     // ---- rings sized for `cap` origins ------------------------------------------------------------------
-    // Small per-origin buffers (descriptors, rows) are sized for `small_cap` origins once -- they are a few hundred
-    // KB even for 1024 origins, and re-allocating page-locked memory in the middle of a run costs anything from a
-    // millisecond to hundreds of them.  The two workspaces that scale with origins x molecules (per-tile partial
-    // sums, overlap candidates) grow by factors of four.
+    // Small per-origin buffers (descriptors, rows; a few hundred KB for 1024 origins) grow by factors of eight:
+    // re-allocating page-locked memory in the middle of a run costs anything from a millisecond to hundreds of
+    // them, so it happens at most twice on the way to 1000 origins, while an engine with a single origin (the
+    // per-object API) stays small.  The two workspaces that scale with origins x molecules (per-tile partial sums,
+    // overlap candidates) grow by factors of four.
     int small_cap = 0;
     int ensure_small(int n_active)
     {
         if (n_active <= small_cap) return SDB_OK;
-        int want = 1024;
-        while (want < n_active) want <<= 1;
+        int want = 16;
+        while (want < n_active) want <<= 3;  // 16 -> 128 -> 1024 -> ...: at most two re-allocations for 1000 origins
         if (!dry && small_cap > 0) {
             int rc = sdb_check_cuda(cudaDeviceSynchronize(), "sdb_engine: synchronize before growing");
             if (rc) return rc;

@@ -12,6 +12,9 @@
 // safety margin of the cutoff, in which case the exact f64 sequence of rowan.rotate is evaluated.
 #include <cstdlib>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "sdb_internal.cuh"
 
 namespace {
@@ -324,7 +327,10 @@ int sdb_struct_launch(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, 
     const int base = tiles < 48 ? tiles : 48;
     const long wave = 148L * 5;
     const long waves = ((long)base * n_origins + wave - 1) / wave;
-    long gx = waves * wave / n_origins;
+    // with few origins a grid of two waves leaves a long tail (blocks of 5 and of 6 iterations): SDB_STRUCT_MIN_WAVES
+    // asks for more, shorter blocks (default: as computed above)
+    static const long min_waves = [] { const char* e = getenv("SDB_STRUCT_MIN_WAVES"); return e ? atol(e) : 0L; }();
+    long gx = std::max(waves, min_waves) * wave / n_origins;
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
     dim3 grid((unsigned)gx, n_origins);

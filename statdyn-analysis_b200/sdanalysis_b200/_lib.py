@@ -63,6 +63,7 @@ EXPORTS = (
     "sdb_test_rot_increment",
     "sdb_test_wrap2d",
     "sdb_test_host_copy",
+    "sdb_upload_async",
     "sdb_host_register",
     "sdb_host_unregister",
     "sdb_engine_create",
@@ -266,6 +267,7 @@ def load():
         "sdb_test_rot_increment": (c_double, [c_float, c_float, c_float, c_float, POINTER(c_int32)]),
         "sdb_test_wrap2d": (None, [c_float, c_float, c_float, c_float, c_float, POINTER(c_float), POINTER(c_float)]),
         "sdb_test_host_copy": (None, [P, P, c_size_t]),
+        "sdb_upload_async": (c_int32, [P, P, c_size_t, P]),
         "sdb_host_register": (c_int32, [P, c_size_t]),
         "sdb_host_unregister": (c_int32, [P]),
         "sdb_engine_create": (c_int32, [POINTER(SdbEngineConfig), POINTER(c_void_p)]),

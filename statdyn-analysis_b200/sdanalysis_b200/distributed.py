@@ -264,8 +264,7 @@ class ShardedDynamics:
                     spos[: hi - lo].copy_(pos_t, non_blocking=True)
                     squat[: hi - lo].copy_(quat_t, non_blocking=True)
                 else:
-                    spos[: hi - lo].copy_(pos_t[lo:hi], non_blocking=True)
-                    squat[: hi - lo].copy_(quat_t[lo:hi], non_blocking=True)
+                    self._upload_rows(lib, spos, squat, pos_t, quat_t, lo, hi)
             pos_bytes = (12 * (hi - lo) + 15) // 16 * 16  # <= 4 * qoff - 12 * lo: stays inside the position part
             _lib.check(lib.sdb_multicast_copy(spos.data_ptr(), base + 12 * lo, pos_bytes, self._mc_blocks, self._side.cuda_stream))
             _lib.check(lib.sdb_multicast_copy(squat.data_ptr(), base + 4 * self.qoff + 16 * lo, 16 * (hi - lo), self._mc_blocks, self._side.cuda_stream))
@@ -278,6 +277,44 @@ class ShardedDynamics:
                 self.exchange_times.append((x0, ready))
         self.h2d_bytes = 0 if direct else 28 * (hi - lo)
         return (slot, None, ready)
+
+    def _upload_rows(self, lib, spos, squat, pos_t, quat_t, lo, hi):
+        """Rows ``[lo, hi)`` of a host frame into this rank's device staging buffers, on the side stream, without
+        ever synchronising it: page-locked sources (pinned tensors, a registered trajectory mapping) are
+        uploaded in place with one asynchronous copy each; pageable ones go through a page-locked staging pair
+        first (a host copy by the library's copy threads).  torch's own ``copy_`` is not used here: for a source
+        it does not recognise as pinned it synchronises the stream, which stops the host from running ahead of
+        the device (measured: +0.2 ms per step at 2 GPUs)."""
+        torch = self.torch
+        stream = self._side.cuda_stream
+        count = hi - lo
+        if pos_t.dtype != torch.float32 or quat_t.dtype != torch.float32 or not pos_t.is_contiguous() or not quat_t.is_contiguous():
+            pos_t, quat_t = pos_t.to(torch.float32).contiguous(), quat_t.to(torch.float32).contiguous()
+        src_pos = pos_t.data_ptr() + 12 * lo
+        src_quat = quat_t.data_ptr() + 16 * lo
+        pinned = (pos_t.is_pinned() and quat_t.is_pinned()) or (
+            _lib.is_pinned(src_pos, 12 * count) and _lib.is_pinned(src_quat, 16 * count)
+        )
+        if not pinned:
+            if getattr(self, "_slice_pinned", None) is None:
+                self._slice_pinned = [
+                    (torch.empty((spos.shape[0], 3), dtype=torch.float32).pin_memory(),
+                     torch.empty((squat.shape[0], 4), dtype=torch.float32).pin_memory())
+                    for _ in range(2)
+                ]
+                self._slice_pinned_done = [None, None]
+            hpos, hquat = self._slice_pinned[self._slice_i]
+            done = self._slice_pinned_done[self._slice_i]
+            if done is not None:
+                done.synchronize()  # the upload that last read this staging pair (two frames ago)
+            lib.sdb_test_host_copy(hpos.data_ptr(), src_pos, 12 * count)
+            lib.sdb_test_host_copy(hquat.data_ptr(), src_quat, 16 * count)
+            src_pos, src_quat = hpos.data_ptr(), hquat.data_ptr()
+        _lib.check(lib.sdb_upload_async(spos.data_ptr(), src_pos, 12 * count, stream))
+        _lib.check(lib.sdb_upload_async(squat.data_ptr(), src_quat, 16 * count, stream))
+        if not pinned:
+            self._slice_pinned_done[self._slice_i] = self._side.record_event()
+        self._upload_keep = (pos_t, quat_t)  # the source stays referenced until the next upload replaces it
 
     def post_frame(self, position=None, orientation=None):
         """Start the exchange of the next frame (rank 0 supplies it; others pass nothing).
