@@ -327,9 +327,10 @@ int sdb_struct_launch(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, 
     const int base = tiles < 48 ? tiles : 48;
     const long wave = 148L * 5;
     const long waves = ((long)base * n_origins + wave - 1) / wave;
-    // with few origins a grid of two waves leaves a long tail (blocks of 5 and of 6 iterations): SDB_STRUCT_MIN_WAVES
-    // asks for more, shorter blocks (default: as computed above)
-    static const long min_waves = [] { const char* e = getenv("SDB_STRUCT_MIN_WAVES"); return e ? atol(e) : 0L; }();
+    // with few origins a grid of two waves leaves a long tail (blocks of 5 and of 6 iterations): at least
+    // SDB_STRUCT_MIN_WAVES (default 8) waves of shorter blocks
+    // (measured at 25 origins x 1 M molecules: 0.096 ms with 2 waves, 0.086 with 6, 0.084 with 12)
+    static const long min_waves = [] { const char* e = getenv("SDB_STRUCT_MIN_WAVES"); return e ? atol(e) : 8L; }();
     long gx = std::max(waves, min_waves) * wave / n_origins;
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
