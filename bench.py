@@ -399,15 +399,13 @@ def run_gpu(args):
             state["i"] = i + 1
             ts = t_first + i
             if world > 1:
-                # software pipeline: the exchange of frame i + 1 runs on the side stream next to the kernels of frame i.
-                # It is enqueued AFTER step i: the upload of frame i + 1 and the (tiny) descriptor upload of step i
-                # share the host-to-device copy engine, and a step whose descriptors queue behind a 14 MB frame slice
-                # starts 0.2 ms late (measured at 2 GPUs with the order reversed: e2e 17 % below `value`)
+                # software pipeline: the exchange of frame i + 1 is enqueued (side stream) before the kernels of
+                # frame i, so it overlaps them
                 post = sharded.post_frame_sliced if (source == "gsd" or sharded_resident) else sharded.post_frame
                 if i not in posted:
                     posted[i] = post(*frame_of(source, i))
-                sharded.step(ts, all_keys, posted.pop(i), gather="batch")
                 posted[i + 1] = post(*frame_of(source, i + 1))
+                sharded.step(ts, all_keys, posted.pop(i), gather="batch")
                 return
             if hostprof is not None:
                 h0 = time.perf_counter()

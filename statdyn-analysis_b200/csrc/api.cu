@@ -1,6 +1,7 @@
 // api.cu -- library-wide plumbing of libsdb200.so: error reporting, launch counter, the atan table,
 // host-side test hooks.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -132,4 +133,37 @@ extern "C" int sdb_upload_async(void* d_dst, const void* h_src, size_t bytes, vo
     if (bytes == 0) return SDB_OK;
     return sdb_check_cuda(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)),
                           "sdb_upload_async");
+}
+
+// ---- small copies on the SMs ------------------------------------------------------------------------------------
+// The per-frame descriptor upload (a few KB, host -> device) and the per-frame row write into another GPU's memory
+// (a few KB, peer) are normally cudaMemcpyAsync calls, i.e. they are served by the copy engines in submission order.
+// When a frame slice of tens of MB is being uploaded at the same time (multi-GPU end-to-end runs: every rank
+// uploads its slice on a side stream), those tiny copies queue behind it and the compute stream starts its next
+// frame up to a slice-upload late.  SDB_SMALL_COPIES=kernel moves them onto the SMs: one block copies 16-byte words
+// (the source may be mapped pinned host memory, the destination peer memory).
+namespace {
+__global__ void __launch_bounds__(256) small_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, int n_vec)
+{
+    for (int i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+bool sdb_small_copies_on_sm()
+{
+    static const bool on = [] {
+        const char* e = getenv("SDB_SMALL_COPIES");
+        return e && e[0] == 'k';
+    }();
+    return on;
+}
+
+// bytes is rounded up to 16: both buffers must have that much room
+int sdb_small_copy(void* dst, const void* src, size_t bytes, void* stream)
+{
+    if (bytes == 0) return SDB_OK;
+    const int n_vec = (int)((bytes + 15) / 16);
+    small_copy_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), n_vec);
+    SDB_CHECK_LAUNCH("small_copy_kernel");
+    return SDB_OK;
 }

@@ -262,7 +262,7 @@ struct SdbEngine {
             *p = calloc(1, bytes);
             return *p ? SDB_OK : SDB_EINVAL;
         }
-        return sdb_check_cuda(cudaHostAlloc(p, bytes, cudaHostAllocDefault), "sdb_engine: cudaHostAlloc");
+        return sdb_check_cuda(cudaHostAlloc(p, bytes, cudaHostAllocMapped | cudaHostAllocPortable), "sdb_engine: cudaHostAlloc");
     }
     void pin_free(void* p)
     {
@@ -722,7 +722,9 @@ struct SdbEngine {
                 sl.has_isf = true;
             }
             if (do_sums && f.d_rows_out) {  // rows in caller order straight to their destination (peer memory allowed)
-                if (sl.identity) {
+                if (sl.identity && sdb_small_copies_on_sm()) {
+                    rc = sdb_small_copy(f.d_rows_out, sl.d_sums, sizeof(double) * SDB_NSUM * (size_t)n_active, s);
+                } else if (sl.identity) {
                     rc = sdb_check_cuda(cudaMemcpyAsync(f.d_rows_out, sl.d_sums, sizeof(double) * SDB_NSUM * (size_t)n_active,
                                                         cudaMemcpyDeviceToDevice, s),
                                         "sdb_engine: row copy");

@@ -144,8 +144,13 @@ int sdb_frame_step_impl(const SdbDynParams* h_params, const float* d_pos, const 
         return SDB_EINVAL;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = sdb_check_cuda(cudaMemcpyAsync(d_desc, h_desc, (size_t)desc_bytes, cudaMemcpyHostToDevice, s),
+    int rc;
+    if (sdb_small_copies_on_sm()) {  // (h_desc must then be mapped pinned memory with 16 bytes of slack: the engine's is)
+        rc = sdb_small_copy(d_desc, h_desc, (size_t)desc_bytes, stream);
+    } else {
+        rc = sdb_check_cuda(cudaMemcpyAsync(d_desc, h_desc, (size_t)desc_bytes, cudaMemcpyHostToDevice, s),
                             "sdb_frame_step: descriptor upload");
+    }
     if (rc) return rc;
     const SdbOrigin* d_origins = static_cast<const SdbOrigin*>(d_desc);
     const SdbSegment* d_segments =

@@ -33,6 +33,10 @@ int sdb_dyn_step_launch(const SdbDynParams* h_params, const float* d_pos, const 
                         int32_t inc_sets, int32_t finalize, void* stream);
 int sdb_dyn_finalize(const double* d_partials, int32_t n, double* d_sums, int32_t n_origins, int32_t with_ov, void* stream);
 
+// tiny copies on the SMs instead of the copy engines (SDB_SMALL_COPIES=kernel): csrc/api.cu
+bool sdb_small_copies_on_sm();
+int sdb_small_copy(void* dst, const void* src, size_t bytes, void* stream);
+
 // sdb_struct with the clear of the SDB_S_STRUCT slots optional: csrc/struct.cu
 int sdb_struct_launch(const SdbOrigin* d_origins, int32_t n_origins, int32_t n, int32_t stride, const float* h_sites_xy,
                       int32_t n_sites, double dist, int32_t mode, double* d_sums, int32_t clear, void* stream);
