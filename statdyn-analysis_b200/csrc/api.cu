@@ -140,8 +140,9 @@ extern "C" int sdb_upload_async(void* d_dst, const void* h_src, size_t bytes, vo
 // (a few KB, peer) are normally cudaMemcpyAsync calls, i.e. they are served by the copy engines in submission order.
 // When a frame slice of tens of MB is being uploaded at the same time (multi-GPU end-to-end runs: every rank
 // uploads its slice on a side stream), those tiny copies queue behind it and the compute stream starts its next
-// frame up to a slice-upload late.  SDB_SMALL_COPIES=kernel moves them onto the SMs: one block copies 16-byte words
-// (the source may be mapped pinned host memory, the destination peer memory).
+// frame up to a slice-upload late (measured on 2 GPUs: e2e 11 % below `value`; with the copies on the SMs 3 %).
+// The native engine therefore moves them with one block of 16-byte word copies (the source may be mapped pinned
+// host memory, the destination peer memory); SDB_SMALL_COPIES=engine goes back to cudaMemcpyAsync.
 namespace {
 __global__ void __launch_bounds__(256) small_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, int n_vec)
 {
@@ -153,7 +154,7 @@ bool sdb_small_copies_on_sm()
 {
     static const bool on = [] {
         const char* e = getenv("SDB_SMALL_COPIES");
-        return e && e[0] == 'k';
+        return !(e && e[0] == 'e');  // "engine": back to cudaMemcpyAsync
     }();
     return on;
 }

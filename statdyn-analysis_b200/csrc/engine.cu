@@ -23,7 +23,7 @@ int sdb_frame_step_impl(const SdbDynParams* h_params, const float* d_pos, const 
                         int32_t n_segments, int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
                         void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy, int32_t n_sites,
                         double struct_dist, int32_t struct_mode, const void* const* h_inc_prev, const uint32_t* h_inc_flags,
-                        int32_t inc_sets, void* d_inc_ws, int32_t step_flags, void* stream);
+                        int32_t inc_sets, void* d_inc_ws, int32_t step_flags, int32_t desc_on_sm, void* stream);
 
 namespace {
 
@@ -708,7 +708,7 @@ struct SdbEngine {
                                      seg_off, n_active, n_segments, seg_count_max, d_partials, sl.d_sums,
                                      sl.host_rows ? sl.h_sums : nullptr, use_ov ? d_ov_ws : nullptr, cap, use_ov ? cfg.overlap_k : 0,
                                      do_struct ? cfg.sites_xy : nullptr, do_struct ? cfg.n_sites : 0, distance, cfg.struct_mode,
-                                     inc_sets ? inc_prev : nullptr, inc_sets ? inc_flags : nullptr, inc_sets, d_inc_ws, step_flags, s);
+                                     inc_sets ? inc_prev : nullptr, inc_sets ? inc_flags : nullptr, inc_sets, d_inc_ws, step_flags, 1, s);
             if (rc) return rc;
             if (do_sums && cfg.compute_isf && cfg.wave_number > 0) {
                 rc = sdb_isf_origins(reinterpret_cast<const SdbOrigin*>(sl.d_desc), n_active, n, stride, cfg.wave_number,

@@ -115,7 +115,7 @@ int sdb_frame_step_impl(const SdbDynParams* h_params, const float* d_pos, const 
                         int32_t n_segments, int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
                         void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy, int32_t n_sites,
                         double struct_dist, int32_t struct_mode, const void* const* h_inc_prev, const uint32_t* h_inc_flags,
-                        int32_t inc_sets, void* d_inc_ws, int32_t step_flags, void* stream);
+                        int32_t inc_sets, void* d_inc_ws, int32_t step_flags, int32_t desc_on_sm, void* stream);
 
 extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, const float* d_quat,
                               float* d_cur_compact, const void* h_desc, void* d_desc, int32_t desc_bytes,
@@ -128,7 +128,7 @@ extern "C" int sdb_frame_step(const SdbDynParams* h_params, const float* d_pos, 
     return sdb_frame_step_impl(h_params, d_pos, d_quat, d_cur_compact, h_desc, d_desc, desc_bytes, segments_offset, n_origins,
                                n_segments, max_segment_count, d_partials, d_sums, h_sums, d_ov_ws, ov_ws_origins, overlap_k,
                                h_sites_xy, n_sites, struct_dist, struct_mode, h_inc_prev, h_inc_flags, inc_sets, d_inc_ws,
-                               step_flags, stream);
+                               step_flags, 0, stream);
 }
 
 // (the native engine of csrc/engine.cu calls this directly)
@@ -137,7 +137,7 @@ int sdb_frame_step_impl(const SdbDynParams* h_params, const float* d_pos, const 
                         int32_t n_segments, int32_t max_segment_count, double* d_partials, double* d_sums, double* h_sums,
                         void* d_ov_ws, int32_t ov_ws_origins, int32_t overlap_k, const float* h_sites_xy, int32_t n_sites,
                         double struct_dist, int32_t struct_mode, const void* const* h_inc_prev, const uint32_t* h_inc_flags,
-                        int32_t inc_sets, void* d_inc_ws, int32_t step_flags, void* stream)
+                        int32_t inc_sets, void* d_inc_ws, int32_t step_flags, int32_t desc_on_sm, void* stream)
 {
     if (!h_params || !h_desc || !d_desc || desc_bytes <= 0 || segments_offset <= 0 || segments_offset >= desc_bytes) {
         sdb_set_error("sdb_frame_step: bad descriptor arguments");
@@ -145,7 +145,7 @@ int sdb_frame_step_impl(const SdbDynParams* h_params, const float* d_pos, const 
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc;
-    if (sdb_small_copies_on_sm()) {  // (h_desc must then be mapped pinned memory with 16 bytes of slack: the engine's is)
+    if (desc_on_sm && sdb_small_copies_on_sm()) {  // (h_desc is then mapped pinned memory with 16 bytes of slack: the engine's)
         rc = sdb_small_copy(d_desc, h_desc, (size_t)desc_bytes, stream);
     } else {
         rc = sdb_check_cuda(cudaMemcpyAsync(d_desc, h_desc, (size_t)desc_bytes, cudaMemcpyHostToDevice, s),
