@@ -37,3 +37,80 @@ def test_gpu_arm_fails_loudly_without_a_device():
     )
     assert out.returncode != 0
     assert "CUDA" in (out.stderr + out.stdout)
+
+
+def test_reference_arm_honours_steps_and_warmup():
+    out = subprocess.run(
+        [sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--molecules", "2000", "--steps", "3", "--warmup", "2"],
+        capture_output=True, text=True, timeout=600, cwd=str(REPO),
+    )
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["steps"] == 3 and line["warmup"] == 2 and "3 timed frames" in line["cpu_baseline"]["sample"]
+
+
+def test_frame_pool_index_walks_back_and_forth_one_step_at_a_time():
+    sys.path.insert(0, str(REPO))
+    import bench
+
+    seq = [bench.pingpong(i, 5) for i in range(20)]
+    assert seq[:9] == [0, 1, 2, 3, 4, 3, 2, 1, 0]
+    assert all(abs(a - b) == 1 for a, b in zip(seq, seq[1:]))  # consecutive frames are one walk step apart
+    assert [bench.pingpong(i, 1300) for i in (0, 1, 1299)] == [0, 1, 1299] and bench.pingpong(7, 1) == 0
+
+
+def test_bench_parity_report_accepts_the_oracle_and_rejects_a_wrong_row():
+    """The parity leg of bench.py (``_oracle_parity``) with the oracle standing in for the device: identical rows and
+    state pass; one perturbed quantity or one wrong passage time fails the run.  (On the GPU box the tables and the
+    state come from the CUDA path; this keeps the bookkeeping -- which measured step a row belongs to, which
+    origins were followed -- from rotting.)"""
+    sys.path.insert(0, str(REPO))
+    sys.path.insert(0, str(REPO / "statdyn-analysis_b200"))
+    import numpy as np
+
+    import bench
+    from oracle import parity as opar
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    n, warmup, followed = 600, 3, [0, 1]
+    walk = SyntheticTrimer(n, seed=3, sigma_r=0.15, sigma_theta=0.3)
+    box = walk.box
+    # creation: origin 0 at t = 0, origin 1 at t = 10, both at the last creation frame t = 50
+    oracle_frames = []
+    for ts, keys in ((0, [0]), (10, [1]), (50, [0, 1])):
+        walk.advance(ts - walk.timestep)
+        pos, quat = walk.frame()
+        oracle_frames.append((ts, pos, quat, keys))
+    t_first = 60
+    pool_host = []
+    for i in range(warmup + 1):
+        walk.advance(t_first + i - walk.timestep)
+        pool_host.append(walk.frame())
+    # the "device": a second oracle over the same frames, rows as column tables per measured step, state after warm-up
+    dev = opar.OracleRun(bench.WAVE_NUMBER)
+    for ts, pos, quat, keys in oracle_frames:
+        dev.frame(ts, box, pos, quat, keys)
+    tables, state = [], {}
+    for i, (pos, quat) in enumerate(pool_host):
+        first_row = len(dev.rows)
+        dev.frame(t_first + i, box, pos, quat, [0, 1, ])
+        rows = dev.rows[first_row:]
+        table = {q: np.array([r[q] for r in rows]) for q in rows[0] if q not in ("keyframe", "_tie")}
+        table["keyframe"] = [r["keyframe"] for r in rows]
+        tables.append((i, table))
+        if i == warmup - 1:
+            for key in followed:
+                dyn, relax = dev.keyframes[key]
+                state[key] = (dyn.delta_translation.copy(), dyn.delta_rotation.copy(), {k: v.copy() for k, v in relax.summary().items()})
+    report, cpu = bench._oracle_parity(np, n, box, oracle_frames, pool_host, t_first, warmup, tables, state, followed)
+    assert report["ok"] and report["checked_rows"] == 2 * (warmup + 1) and report["state_checked"] == [0, 1]
+    assert cpu["kind"] == "port" and cpu["cores"] == 1 and cpu["value"] > 0
+    # a wrong quantity in one row
+    tables[1][1]["msd"] = tables[1][1]["msd"] * (1 + 1e-3)
+    bad, _ = bench._oracle_parity(np, n, box, oracle_frames, pool_host, t_first, warmup, tables, state, followed)
+    assert not bad["ok"] and bad["failed_rows"] and "msd" in bad["failed_rows"][0]["quantities"]
+    tables[1][1]["msd"] = tables[1][1]["msd"] / (1 + 1e-3)
+    # a wrong passage time of one molecule
+    state[1][2]["tau_F"][17] += 1
+    bad, _ = bench._oracle_parity(np, n, box, oracle_frames, pool_host, t_first, warmup, tables, state, followed)
+    assert not bad["ok"] and bad["passage_mismatch"] == 1

@@ -280,3 +280,43 @@ def test_lammps_trajectory(tmp_path):
     bad.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF MOLECULES\n3\n")
     with pytest.raises(RuntimeError):
         list(parse_lammpstrj(bad))
+
+
+def test_order_frame_cache_recognises_only_frames_nobody_can_write():
+    """order.compute_neighbours / orientational_order / num_neighbours share one build per frame (the reference
+    builds three times); the frame is recognised by identity, which is only safe for arrays that cannot change:
+    torch tensors (version counter) and numpy arrays that are read-only all the way down (mmap views)."""
+    import torch
+
+    from sdanalysis_b200 import order
+
+    a = np.zeros((10, 3), dtype=np.float32)
+    assert order._identity(a, torch) is None  # writable: never cached
+    view = a.view()
+    view.flags.writeable = False
+    assert not order._immutable(view) and order._identity(view, torch) is None  # its base can still be written
+    frozen = np.frombuffer(bytes(120), dtype=np.float32).reshape(10, 3)  # read-only buffer, like an mmap view
+    assert order._immutable(frozen) and order._identity(frozen, torch) == order._identity(frozen[:], torch)
+    assert order._identity(frozen, torch) != order._identity(frozen[1:], torch)
+    t = torch.zeros((10, 3))
+    before = order._identity(t, torch)
+    assert before == order._identity(t, torch)
+    t.add_(1.0)  # an in-place write bumps the version: a different frame
+    assert order._identity(t, torch) != before
+
+
+def test_gsd_views_are_read_only_and_pinning_degrades_gracefully(tmp_path):
+    """Frames are read-only views of the file mapping; without a CUDA device pin() reports failure and nothing changes."""
+    import torch
+
+    path = tmp_path / "t.gsd"
+    pos = np.arange(30, dtype=np.float32).reshape(10, 3)
+    with GSDWriter(path) as w:
+        for step in range(3):
+            w.append(step, [5, 5, 1, 0, 0, 0], pos + step)
+    with open_gsd(path) as trj:
+        snap = trj[1]
+        assert not snap.position.flags.writeable and np.array_equal(snap.position, pos + 1)
+        if not torch.cuda.is_available():
+            assert trj.pin() is False
+        assert np.array_equal(trj[2].position, pos + 2)
