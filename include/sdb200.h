@@ -413,7 +413,8 @@ int64_t sdb_engine_step(SdbEngine* engine, const SdbFrame* frame, void* stream);
  * (NULL for steps without host rows), h_timediffs int64[n_keys], h_isf double[n_keys] (any may be NULL).
  * A ticket stays valid for ring_depth - 1 further steps (SDB_EINVAL afterwards). */
 int sdb_engine_wait(SdbEngine* engine, int64_t ticket, double* h_rows, int64_t* h_timediffs, double* h_isf);
-/* Device copy of the rows of a step (valid like the ticket), in the engine's internal origin order;
+/* Device copy of the rows of a step (valid like the ticket, and until a step with more active origins than ever
+ * before re-sizes the rings), in the engine's internal origin order;
  * h_perm int32[n_keys] (may be NULL): position of keys[i] in that order. */
 int sdb_engine_device_rows(SdbEngine* engine, int64_t ticket, double** d_rows, int32_t* h_perm);
 /* A whole batch of frames in one call (the frame loop itself in native code): steps frames[0..n_frames) in

@@ -44,6 +44,7 @@ public:
             memcpy(dst, src, bytes);
             return;
         }
+        std::lock_guard<std::mutex> one_caller(callers_);  // (engines of different host threads share the pool)
         std::unique_lock<std::mutex> lock(mutex_);
         const int parts = (int)std::min<size_t>(workers_.size() + 1, bytes / min_chunk);
         const size_t chunk = ((bytes + parts - 1) / parts + 63) & ~size_t(63);
@@ -103,7 +104,7 @@ private:
         }
     }
     std::vector<std::thread> workers_;
-    std::mutex mutex_;
+    std::mutex mutex_, callers_;
     std::condition_variable wake_, finished_;
     char* dst_ = nullptr;
     const char* src_ = nullptr;
@@ -695,11 +696,16 @@ struct SdbEngine {
             if (!new_prev) return rc ? rc : SDB_EINVAL;
             new_prev->has_orientation = has_quat;
         }
+        // a step that fails from here on hands its (still unreferenced) pool frame back
+        auto give_back = [&](int code) {
+            if (new_prev) pool_free.push_back(new_prev);
+            return code;
+        };
         int step_flags = 0;
         if (all_history) step_flags |= SDB_STEP_PREDICTED;
         if (inc_sets > 0 && !d_inc_ws) {
             rc = dev_alloc(&d_inc_ws, sdb_dyn_increments_bytes(n, stride, SDB_MAX_INC_SETS));
-            if (rc) return rc;
+            if (rc) return give_back(rc);
         }
         params.do_sums = do_sums ? 1 : 0;
         const bool do_struct = do_sums && cfg.n_sites > 0 && cfg.wave_number > 0;
@@ -709,15 +715,15 @@ struct SdbEngine {
                                      sl.host_rows ? sl.h_sums : nullptr, use_ov ? d_ov_ws : nullptr, cap, use_ov ? cfg.overlap_k : 0,
                                      do_struct ? cfg.sites_xy : nullptr, do_struct ? cfg.n_sites : 0, distance, cfg.struct_mode,
                                      inc_sets ? inc_prev : nullptr, inc_sets ? inc_flags : nullptr, inc_sets, d_inc_ws, step_flags, 1, s);
-            if (rc) return rc;
+            if (rc) return give_back(rc);
             if (do_sums && cfg.compute_isf && cfg.wave_number > 0) {
                 rc = sdb_isf_origins(reinterpret_cast<const SdbOrigin*>(sl.d_desc), n_active, n, stride, cfg.wave_number,
                                      cfg.angular_resolution, sl.d_isf, s);
-                if (rc) return rc;
+                if (rc) return give_back(rc);
                 if (sl.host_rows) {
                     rc = sdb_check_cuda(cudaMemcpyAsync(sl.h_isf, sl.d_isf, sizeof(double) * (size_t)n_active, cudaMemcpyDeviceToHost, s),
                                         "sdb_engine: isf download");
-                    if (rc) return rc;
+                    if (rc) return give_back(rc);
                 }
                 sl.has_isf = true;
             }
@@ -734,7 +740,7 @@ struct SdbEngine {
                                                             sizeof(double) * SDB_NSUM, cudaMemcpyDeviceToDevice, s),
                                             "sdb_engine: row copy");
                 }
-                if (rc) return rc;
+                if (rc) return give_back(rc);
             }
             if (staged) {
                 cudaEventRecord(staged->consumed, s);

@@ -244,3 +244,24 @@ def test_set_trackers_changes_the_descriptor_pointers_only_when_trackers_exist()
     assert origins["d_flags"][0] != 0 and origins["d_status"][0] != 0
     with pytest.raises(ValueError):
         eng.set_trackers([{"name": "bad", "threshold": -1.0}])
+
+
+def test_host_copy_pool_copies_exactly_what_memcpy_would():
+    """The engine's multi-threaded staging copy (pageable -> pinned) on caller buffers: every byte, for sizes below
+    and above the threshold at which the worker threads take part, with unaligned ends."""
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for nbytes in (0, 1, 4096, 4 * 2 ** 20 - 3, 28_000_000 + 7):
+        src = rng.integers(0, 255, nbytes + 64, dtype=np.uint8)
+        dst = np.zeros(nbytes + 64, dtype=np.uint8)
+        lib.sdb_test_host_copy(dst.ctypes.data + 3, src.ctypes.data + 5, nbytes)
+        assert np.array_equal(dst[3 : 3 + nbytes], src[5 : 5 + nbytes]) and not dst[:3].any() and not dst[3 + nbytes :].any()
+
+
+def test_large_host_frames_go_through_the_threaded_staging_copy():
+    n = 400_000  # 4.8 MB of positions, 6.4 MB of quaternions: above the threshold of the copy pool
+    eng = _engine(n)
+    pos, quat = _frame(n)
+    for t in range(4):
+        res = eng.step(t, pos, quat, [0, 1])
+    assert res.timediffs == [3, 3] and eng.stats().h2d_bytes == 28 * n
