@@ -120,3 +120,50 @@ def test_sharded_step_broadcasts_frames_and_gathers_rows():
     for (keys, timediffs, sums, _, _), (bkeys, btd, bsums) in zip(got[0][1], got[0][2]):
         assert keys == bkeys and timediffs == btd
         assert np.array_equal(np.array(sums), np.array(bsums))
+
+
+def _order_worker(rank, world, port, infile, outfile, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sdanalysis_b200 import run_analysis
+
+        seen = []
+
+        def order_fn(box, position, orientation):  # stub of order.orientational_order: a value per particle
+            seen.append(float(position[0, 0]))
+            return np.where(np.arange(len(position)) < position[0, 0], 1.0, 0.0)
+
+        run_analysis.order(infile, outfile, order_fn=order_fn)
+        out.put((rank, seen))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_order_path_shards_frames_as_replicas(tmp_path):
+    """run_analysis.order under torch.distributed: every rank analyses its own frames (no collective on the data
+    path), rank 0 writes all rows in frame order."""
+    from sdanalysis_b200.gsdio import GSDWriter
+
+    infile, outfile = tmp_path / "t.gsd", tmp_path / "order.csv"
+    with GSDWriter(infile) as w:
+        for frame in range(7):
+            pos = np.zeros((10, 3), dtype=np.float32)
+            pos[0, 0] = frame  # the stub orders `frame` of the 10 particles
+            w.append(100 * frame, [5, 5, 1, 0, 0, 0], pos, np.tile(np.array([1, 0, 0, 0], np.float32), (10, 1)))
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_order_worker, args=(r, world, port, str(infile), str(outfile), out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    seen = dict(out.get(timeout=100) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert seen[0] == [0.0, 2.0, 4.0, 6.0] and seen[1] == [1.0, 3.0, 5.0]  # frames r, r + R, ...
+    lines = outfile.read_text().strip().splitlines()
+    assert lines[0] == "Timestep, OrientOrder"
+    assert [line.split() for line in lines[1:]] == [[str(100 * f), ",", str(f / 10)] for f in range(7)]
