@@ -152,37 +152,63 @@ __global__ void __launch_bounds__(128) voronoi_kernel(const VorArgs a)
 // polygons small -- clipping by a far-away row of molecules first would give a cell with one edge per
 // molecule of the row.  After a shell of outer radius R everything closer than R has been seen, so the cell
 // is final once its farthest vertex is within R / 2.
-__global__ void __launch_bounds__(64) voronoi_brute_kernel(const VorArgs a)
+// One WARP per unresolved molecule (round 1: one thread, which made a 32 k-molecule frame with a void strip three
+// times slower than a 1 M-molecule one without): the lanes test 32 candidates at a time, the few that pass are
+// clipped in candidate order by lane 0 on a polygon in shared memory -- the same sequence of clips as a serial scan.
+constexpr int VOR_BRUTE_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * VOR_BRUTE_WARPS) voronoi_brute_kernel(const VorArgs a)
 {
-    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= a.unresolved[0]) return;
-    const int i = (int)a.unresolved[1 + u];
-    PolyT<VOR_MAXV_BRUTE> buf[2];
-    int cur = 0;
+    __shared__ PolyT<VOR_MAXV_BRUTE> polys[VOR_BRUTE_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_unresolved = a.unresolved[0];
     const double b = 0.5 * fmin(a.lx, a.ly);  // beyond this a cell would meet its own periodic images
-    poly_square(buf[0], b);
-    double r2 = 2.0 * b * b;
-    bool ok = true;
-    double rin2 = 0.0, rout = a.rmax;
-    while (ok) {
-        const double rout2 = rout * rout;
-        for (int j = 0; j < a.n && ok; ++j) {
-            if (j == i) continue;
-            double dx, dy;
-            min_image(a, i, j, dx, dy);
-            const double d2 = dx * dx + dy * dy;
-            if (d2 < rin2 || d2 >= rout2 || d2 >= 4.0 * r2) continue;
-            ok = poly_clip(buf[cur], buf[cur ^ 1], dx, dy, j);
-            cur ^= 1;
-            r2 = poly_radius2(buf[cur]);
+    for (uint32_t u = blockIdx.x * VOR_BRUTE_WARPS + warp; u < n_unresolved; u += gridDim.x * VOR_BRUTE_WARPS) {
+        const int i = (int)a.unresolved[1 + u];
+        PolyT<VOR_MAXV_BRUTE>* buf = polys[warp];
+        int cur = 0;
+        if (lane == 0) poly_square(buf[0], b);
+        __syncwarp();
+        double r2 = 2.0 * b * b;
+        bool ok = true;
+        double rin2 = 0.0, rout = a.rmax;
+        while (ok) {
+            const double rout2 = rout * rout;
+            for (int base = 0; base < a.n && ok; base += 32) {
+                const int j = base + lane;
+                double dx = 0.0, dy = 0.0, d2 = INFINITY;
+                if (j < a.n && j != i) {
+                    min_image(a, i, j, dx, dy);
+                    d2 = dx * dx + dy * dy;
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, d2 >= rin2 && d2 < rout2 && d2 < 4.0 * r2);
+                while (mask && ok) {  // (warp-uniform)
+                    const int l = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const double cx = __shfl_sync(0xffffffffu, dx, l), cy = __shfl_sync(0xffffffffu, dy, l);
+                    if (cx * cx + cy * cy >= 4.0 * r2) continue;  // the cell has shrunk since the test above
+                    int clipped = 1;
+                    double nr2 = r2;
+                    if (lane == 0) {
+                        clipped = poly_clip(buf[cur], buf[cur ^ 1], cx, cy, base + l) ? 1 : 0;
+                        if (clipped) nr2 = poly_radius2(buf[cur ^ 1]);
+                    }
+                    clipped = __shfl_sync(0xffffffffu, clipped, 0);
+                    nr2 = __shfl_sync(0xffffffffu, nr2, 0);
+                    ok = clipped != 0;
+                    cur ^= 1;
+                    r2 = nr2;
+                }
+            }
+            if (4.0 * r2 <= rout2 || rout2 >= 2.0 * b * b) break;
+            rin2 = rout2;
+            rout *= 2.0;
         }
-        if (4.0 * r2 <= rout2 || rout2 >= 2.0 * b * b) break;
-        rin2 = rout2;
-        rout *= 2.0;
+        // a cell that still touches the starting square is bounded by the molecule's own periodic images:
+        // not representable here (freud's buffer would not cover it either); reported as VOR_MISSING
+        if (lane == 0) a.counts[i] = ok && poly_closed(buf[cur]) ? (uint32_t)buf[cur].nv : VOR_MISSING;
+        __syncwarp();
     }
-    // a cell that still touches the starting square is bounded by the molecule's own periodic images:
-    // not representable here (freud's buffer would not cover it either); reported as VOR_MISSING
-    a.counts[i] = ok && poly_closed(buf[cur]) ? (uint32_t)buf[cur].nv : VOR_MISSING;
 }
 
 }  // namespace
@@ -216,9 +242,8 @@ extern "C" int sdb_voronoi_counts(const float* h_box, int32_t n, const float* d_
     if (rc) return rc;
     voronoi_kernel<<<(n + 127) / 128, 128, 0, s>>>(a);
     SDB_CHECK_LAUNCH("voronoi_kernel");
-    // the second kernel sizes itself from the device-side count: launch enough threads for every molecule,
-    // in blocks that exit at once when there is nothing to do
-    voronoi_brute_kernel<<<(n + 63) / 64, 64, 0, s>>>(a);
+    // the second kernel sizes itself from the device-side count: a fixed grid of warps strides over the list
+    voronoi_brute_kernel<<<148 * 4, 32 * VOR_BRUTE_WARPS, 0, s>>>(a);
     SDB_CHECK_LAUNCH("voronoi_brute_kernel");
     return SDB_OK;
 }
