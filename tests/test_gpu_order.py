@@ -99,3 +99,57 @@ def test_setup_neighbours_query_object(golden_dir):
     rsq = query.nlist.r_sq_list
     assert np.allclose(np.sqrt(np.where(rsq < 0, 0, rsq)), order.relative_distances(g["box"], g["position"], 3.5, 8))
     assert np.array_equal(np.minimum(query.nlist.neighbor_counts, 8), (query.getNeighborList() != 2 ** 32 - 1).sum(axis=1))
+
+
+def test_config2_size_the_three_public_functions_share_one_build():
+    """BASELINE configs[2] size (32 768 molecules): compute_neighbours + orientational_order + num_neighbours on
+    one frame -- read-only numpy arrays as a GSD mapping hands them out, and torch device tensors -- against the
+    oracle, which (like the reference, order.py:207,258-261,279-281) builds its neighbour structure three times.
+    The k = 8 list must be the first 8 columns of the shared k = 9 search, the count must saturate at 9."""
+    import torch
+
+    from sdanalysis_b200 import _lib, order
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    n = 32768
+    walk = SyntheticTrimer(n, seed=5)
+    walk.advance(400)
+    pos, quat = walk.frame()
+    nn = oorder.setup_neighbours(walk.box, pos, 3.5, 8)
+    want_list, want_rsq = nn.getNeighborList(), nn.r_sq_list
+    want_counts = oorder.num_neighbours(walk.box, pos, 3.5)
+    want_order = oorder._orientational_order(want_list, quat)
+    rows = _no_ties(want_rsq)
+    assert rows.mean() > 0.99
+
+    def check(nlist, oo, counts):
+        assert np.array_equal(nlist[rows], want_list[rows])
+        np.testing.assert_allclose(oo[rows], want_order[rows], rtol=1e-5, atol=1e-7)
+        assert np.array_equal(counts, want_counts) and counts.max() <= 9
+
+    # read-only numpy frames (what gsdio's mapping hands out): the three calls share one build
+    ro_pos = np.frombuffer(pos.tobytes(), dtype=np.float32).reshape(n, 3)
+    ro_quat = np.frombuffer(quat.tobytes(), dtype=np.float32).reshape(n, 4)
+    launches = _lib.launch_count()
+    got = (order.compute_neighbours(walk.box, ro_pos, 3.5, 8), order.orientational_order(walk.box, ro_pos, ro_quat, 3.5, 8),
+           order.num_neighbours(walk.box, ro_pos, 3.5))
+    assert _lib.launch_count() - launches <= 6
+    check(*got)
+    # writable numpy arrays are never recognised as "the same frame": three builds, same answers
+    launches = _lib.launch_count()
+    check(order.compute_neighbours(walk.box, pos, 3.5, 8), order.orientational_order(walk.box, pos, quat, 3.5, 8),
+          order.num_neighbours(walk.box, pos, 3.5))
+    assert _lib.launch_count() - launches >= 12
+    # device tensors in, device tensors out, one build for the three calls
+    d_pos, d_quat = torch.from_numpy(pos).cuda(), torch.from_numpy(quat).cuda()
+    launches = _lib.launch_count()
+    nlist = order.compute_neighbours(walk.box, d_pos, 3.5, 8)
+    oo = order.orientational_order(walk.box, d_pos, d_quat, 3.5, 8)
+    counts = order.num_neighbours(walk.box, d_pos, 3.5)
+    assert _lib.launch_count() - launches <= 6  # bin, scan, scatter, search (+ order from the cached list)
+    assert nlist.is_cuda and oo.is_cuda and counts.is_cuda
+    check(nlist.cpu().numpy().view(np.uint32), oo.cpu().numpy(), counts.cpu().numpy().view(np.uint32))
+    d_pos.add_(0.0)  # an in-place write makes it a different frame: a new build
+    launches = _lib.launch_count()
+    order.num_neighbours(walk.box, d_pos, 3.5)
+    assert _lib.launch_count() - launches >= 4
