@@ -428,7 +428,7 @@ int sdb_engine_drop(SdbEngine* engine, int64_t key);
 
 typedef struct {
     int64_t timestep;         /* of the origin's first frame */
-    int64_t updates;          /* samples added since (0: just created) */
+    int64_t updates;          /* frames the origin has been stepped with, the one that created it included */
     int64_t max_timediff;
     float* d_delta;           /* float[3][stride] (+ SDB_HISTORY_WORDS words) */
     uint8_t* d_flags;         /* uint8[stride] or NULL */

@@ -130,3 +130,72 @@ def test_tracker_validation_errors():
         [{"name": "a", "threshold": 1.0}, {"name": "b", "threshold": 0.5, "last_passage": True}, {"name": "c", "threshold": 1, "type": "rotation"}]
     )
     assert [s.bit for s in specs] == [0, 1, 3] and specs[1].cutoff == 1.5
+
+
+# ---- the boundary seen from plain C ---------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c_client(lib, tmp_path_factory):
+    """tests/cabi_client.c compiled as strict C99 against include/sdb200.h and linked with the shared library."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    from sdanalysis_b200 import _lib
+
+    libdir = _lib.LIB_PATH.parent
+    exe = tmp_path_factory.mktemp("cabi") / "client"
+    subprocess.run(
+        ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{REPO / 'include'}",
+         str(REPO / "tests" / "cabi_client.c"), "-o", str(exe), f"-L{libdir}", "-lsdb200", f"-Wl,-rpath,{libdir}"],
+        check=True, capture_output=True, text=True)
+
+    def run(mode):
+        return subprocess.run([str(exe), mode], check=True, capture_output=True, text=True, timeout=60).stdout.splitlines()
+
+    return run
+
+
+def test_header_is_plain_c_and_layouts_match_the_ctypes_mirrors(c_client):
+    from sdanalysis_b200 import _lib
+
+    sizes, fields, consts = {}, {}, {}
+    for line in c_client("layout"):
+        kind, *rest = line.split()
+        if kind == "size":
+            sizes[rest[0]] = int(rest[1])
+        elif kind == "field":
+            fields.setdefault(rest[0], {})[rest[1]] = int(rest[2])
+        else:
+            consts[rest[0]] = int(rest[1])
+    assert set(sizes) == {"SdbTracker", "SdbDynParams", "SdbOrigin", "SdbSegment", "SdbEngineConfig", "SdbFrame",
+                          "SdbOriginInfo", "SdbEngineStats"}
+    for name, size in sizes.items():
+        mirror = getattr(_lib, name)
+        assert ctypes.sizeof(mirror) == size, name
+        assert {f: getattr(mirror, f).offset for f, *_ in mirror._fields_} == fields[name], name
+    assert np.dtype(_lib.ORIGIN_DTYPE).itemsize == sizes["SdbOrigin"]
+    assert {f: np.dtype(_lib.ORIGIN_DTYPE).fields[f][1] for f in np.dtype(_lib.ORIGIN_DTYPE).names} == fields["SdbOrigin"]
+    assert {f: np.dtype(_lib.SEGMENT_DTYPE).fields[f][1] for f in np.dtype(_lib.SEGMENT_DTYPE).names} == fields["SdbSegment"]
+    assert consts["SDB_NSUM"] == _lib.SDB_NSUM and consts["SDB_MAX_TRACKERS"] == _lib.SDB_MAX_TRACKERS
+    assert (consts["SDB_MEM_HOST"], consts["SDB_MEM_PINNED"]) == (_lib.SDB_MEM_HOST, _lib.SDB_MEM_PINNED)
+    assert consts["SDB_ENGINE_DRY"] == _lib.SDB_ENGINE_DRY and consts["SDB_FRAME_NO_SUMS"] == _lib.SDB_FRAME_NO_SUMS
+    assert (consts["SDB_OK"], consts["SDB_EINVAL"], consts["SDB_ECUDA"]) == (0, -1, -2)
+
+
+def test_c_client_drives_the_frame_loop_through_the_header_alone(c_client):
+    """The loop of read/_read.py:128-168 for a linear schedule (new origin every 3 frames, 3 alive), written
+    against the header in C: every frame reports ``timestep - origin timestep`` per active origin, oldest first."""
+    out = c_client("dry")
+    assert out[0].startswith("version sdb200") and "sm_100a" in out[0]
+    frames = [line.split() for line in out if line.startswith("frame")]
+    assert len(frames) == 12
+    first = 0
+    for f, words in enumerate(frames):
+        newest = f // 3
+        first = max(first, newest - 2)
+        assert int(words[1]) == f and int(words[3]) == newest - first + 1
+        assert [int(w) for w in words[5:]] == [f - 3 * k for k in range(first, newest + 1)]
+    assert out[13] == "oldest key 1 timestep 3 updates 9 max_timediff 8 stride 1000"
+    assert out[14] == "unknown key rc -1"
+    assert out[15] == "stats frames 12 updates 27000 origins 3"
