@@ -508,6 +508,23 @@ struct SdbEngine {
             sdb_set_error("sdb_engine_step: no position array");
             return SDB_EINVAL;
         }
+        // refuse before anything is created or re-sized: a failed step leaves the engine as it was
+        for (int i = 0; i < n_active; ++i) {
+            auto it = origins.find(f.keys[i]);
+            if (it == origins.end()) {
+                if (zero_step) {
+                    sdb_set_error("sdb_engine_step: zero step on an origin that does not exist");
+                    return SDB_EINVAL;
+                }
+                continue;
+            }
+            const int64_t td = it->second->updates == 0 ? 0 : f.timestep - it->second->t0;
+            if (td < 0 || td >= (int64_t)SDB_NO_STATUS) {
+                sdb_set_error("sdb_engine_step: time difference %lld outside [0, 2**32-1): passage times are 32-bit on the device",
+                              (long long)td);
+                return SDB_EINVAL;
+            }
+        }
         int rc = ensure_capacity(std::max(n_active, 1));
         if (rc) return rc;
         const int64_t ticket = tickets;
@@ -554,7 +571,8 @@ struct SdbEngine {
             } else {
                 Origin* o = it->second;
                 by_key[(size_t)i] = o;
-                if (o->updates == 0) {  // created by a step that failed before its launch: still new
+                if (o->updates == 0) {  // created by a step that failed before its launch: still new, and it starts now
+                    o->t0 = f.timestep;
                     fresh.push_back(o);
                     continue;
                 }

@@ -546,11 +546,18 @@ class DynamicsEngine:
         return arr
 
     def _forget_failed_keys(self, active):
-        """After a failed step: keys the native engine did not create lose their Python-side record."""
+        """After a failed step nothing of it stays: keys the native engine did not create lose their Python-side
+        record, origins it created without ever stepping them are dropped."""
         info = _lib.SdbOriginInfo()
         for key in active:
             ident = self._ids.get(key)
-            if ident is not None and self.lib.sdb_engine_origin(self._handle, ident, ctypes.byref(info)) != 0:
+            if ident is None:
+                continue
+            known = self.lib.sdb_engine_origin(self._handle, ident, ctypes.byref(info)) == 0
+            if known and info.updates == 0:
+                self.lib.sdb_engine_drop(self._handle, ident)
+                known = False
+            if not known:
                 self._ids.pop(key, None)
                 self._keys_by_id.pop(ident, None)
                 self._t0.pop(key, None)
@@ -618,20 +625,20 @@ class DynamicsEngine:
             for key in active:
                 if key not in self._ids:
                     raise RuntimeError("zero_step on an origin that does not exist")
-        ids = self._key_ids(active, timestep)
         f = self._frame
-        f.timestep = timestep
-        f.keys = ctypes.addressof(ids)
-        f.n_keys = n_active
         flags = 0
         keep = None
         if zero_step:
             flags |= _lib.SDB_FRAME_ZERO_STEP
             f.pos = f.quat = None
             f.where = _lib.SDB_MEM_DEVICE
-        else:
+        else:  # (a frame that is refused must not leave records of the keys it would have created)
             pos_ptr, quat_ptr, kind, keep = self._frame_pointers(position, orientation)
             f.pos, f.quat, f.where = pos_ptr, quat_ptr or None, kind
+        ids = self._key_ids(active, timestep)
+        f.timestep = timestep
+        f.keys = ctypes.addressof(ids)
+        f.n_keys = n_active
         if not do_sums:
             flags |= _lib.SDB_FRAME_NO_SUMS
         if not to_host:
@@ -691,8 +698,13 @@ class DynamicsEngine:
         total = 0
         for i, (timestep, position, orientation, active) in enumerate(frames):
             active = list(active)
+            try:
+                pos_ptr, quat_ptr, kind, alive = self._frame_pointers(position, orientation)
+            except Exception:
+                for seen in actives:  # nothing has reached the native engine yet
+                    self._forget_failed_keys(seen)
+                raise
             ids = self._key_ids(active, int(timestep))
-            pos_ptr, quat_ptr, kind, alive = self._frame_pointers(position, orientation)
             keep.append((alive, position, orientation))
             key_arrays.append(ids)
             actives.append(active)

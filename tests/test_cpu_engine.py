@@ -265,3 +265,186 @@ def test_large_host_frames_go_through_the_threaded_staging_copy():
     for t in range(4):
         res = eng.step(t, pos, quat, [0, 1])
     assert res.timediffs == [3, 3] and eng.stats().h2d_bytes == 28 * n
+
+
+# ---- randomised runs against a model of the reference's loop ---------------------------------------------
+class _LoopModel:
+    """What read/_read.py:128-168 keeps per keyframe, restated for arbitrary call sequences: the origin's first
+    timestep, the frame it saw last (``TrackedMotion.previous_*``, _util.py:155-156), its largest time difference so
+    far (decides the literal passage-time rule of relaxations.py:215-218) and how many frames it has seen."""
+
+    def __init__(self):
+        self.t0, self.last_frame, self.max_td, self.updates, self.order = {}, {}, {}, {}, []
+        self.frames = 0
+
+    def step(self, frame_id, timestep, keys, zero_step=False):
+        out = []
+        for k in keys:
+            new = k not in self.t0
+            if new:
+                self.t0[k], self.max_td[k], self.updates[k] = timestep, -1, 0
+                self.order.append(k)
+            td = timestep - self.t0[k]
+            out.append((k, td, new, (not new) and td < self.max_td[k], self.last_frame.get(k)))
+        if not zero_step:  # a zero step (rows of the current state once more) leaves the origin's history alone
+            for k in keys:
+                self.max_td[k] = max(self.max_td[k], timestep - self.t0[k])
+                self.updates[k] += 1
+                self.last_frame[k] = frame_id
+            self.frames += 1
+        return out
+
+    def drop(self, k):
+        for d in (self.t0, self.last_frame, self.max_td, self.updates):
+            d.pop(k, None)
+        self.order.remove(k)
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("SDB_TEST_SEEDS", "6"))))
+def test_random_call_sequences_follow_the_loop_model(seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.choice([37, 260, 1500]))
+    eng = _engine(n, ring_depth=int(rng.integers(2, 5)), chunk=int(rng.choice([0, 0, 3])))
+    model = _LoopModel()
+    pos, quat = _frame(n, seed)
+    timestep, next_key, frame_id = 0, 0, 0
+    state_ptrs = {}
+    for op in range(150):
+        live = list(model.t0)
+        roll = rng.random()
+        if live and roll < 0.08:
+            k = live[int(rng.integers(len(live)))]
+            eng.drop_origin(k)
+            model.drop(k)
+            state_ptrs.pop(k, None)
+            continue
+        if live and roll < 0.12:  # a call the engine must refuse without side effects
+            with pytest.raises(RuntimeError):
+                eng.step(timestep, pos[:-1], quat, live[:1] + [next_key + 1000])
+            assert next_key + 1000 not in eng.origins and len(eng.origins) == len(live)
+            continue
+        if roll < 0.15:  # Relaxations.set_mol_relax mid-run: passage state afresh, the bookkeeping untouched
+            count = int(rng.integers(0, 4))
+            eng.set_trackers([{"name": f"tau_{i}", "threshold": 0.1 * (i + 1), "last_passage": bool(i % 2)} for i in range(count)])
+            for k in live:
+                view = eng.origins[k]
+                assert (view.timestep, view.updates, view.max_timediff) == (model.t0[k], model.updates[k], model.max_td[k])
+            continue
+        if live and roll < 0.20:  # a batch of frames in one native call
+            batch = []
+            timestep = max(timestep, max(model.t0.values()))  # (no frame before an origin's first one)
+            for _ in range(int(rng.integers(2, 5))):
+                timestep += int(rng.choice([1, 3, 8]))
+                keys = [int(k) for k in model.t0 if rng.random() < 0.7] + [next_key]
+                next_key += 1
+                frame_id += 1
+                batch.append((timestep, keys, model.step(frame_id, timestep, keys)))
+            got = eng.run([(t, pos, quat, keys) for t, keys, _ in batch])
+            for res, (t, keys, want) in zip(got, batch):
+                assert res.keys == keys and res.timediffs == [td for _, td, *_ in want]
+            st = eng.stats()
+            assert st.frames == model.frames and st.pool_frames - st.pool_free == len(set(model.last_frame.values()))
+            assert eng.origins.keys() == model.order
+            continue
+        zero_step = bool(live) and roll < 0.24
+        keys = [k for k in live if rng.random() < 0.6]
+        if not zero_step:
+            for _ in range(int(rng.integers(0, 3)) if live else 1):
+                keys.append(next_key)
+                next_key += 1
+        if not keys:
+            continue
+        rng.shuffle(keys)
+        keys = [int(k) for k in keys]
+        if not zero_step:
+            timestep = max(0, timestep + int(rng.choice([1, 1, 2, 5, 17, -3])))
+            frame_id += 1
+        if any(k in model.t0 and timestep < model.t0[k] for k in keys):
+            # before an origin's first frame: refused (passage times are unsigned), nothing created, nothing stepped
+            fresh = [k for k in keys if k not in model.t0]
+            before = eng.stats()
+            with pytest.raises(OverflowError):
+                eng.step(timestep, pos, quat, keys, zero_step=zero_step)
+            after = eng.stats()
+            assert (after.frames, after.updates, after.pool_frames, after.pool_free) == (
+                before.frames, before.updates, before.pool_frames, before.pool_free)
+            assert not any(k in eng.origins for k in fresh) and eng.origins.keys() == model.order
+            frame_id -= 0 if zero_step else 1
+            continue
+        prev_before = {k: eng.origins[k]._info.d_prev for k in keys if k in model.t0}
+        res = eng.step(timestep, None if zero_step else pos, None if zero_step else quat, keys, zero_step=zero_step)
+        want = model.step(frame_id, timestep, keys, zero_step)
+        # rows come back in the caller's order with timediff = frame.timestep - origin.timestep
+        assert res.keys == keys and res.timediffs == [td for _, td, *_ in want]
+        origins, segments = eng.last_descriptors()
+        assert len(origins) == len(keys)
+        # the segments tile the origin records in order
+        assert segments["first"].tolist() == np.cumsum([0] + segments["count"].tolist())[:-1].tolist()
+        assert int(segments["count"].sum()) == len(keys) and np.all(segments["count"] > 0)
+        # every record can be matched to one key: same state pointer as ever, same timediff and flags as the model
+        by_ptr = {}
+        for k in keys:
+            view = eng.origins[k]
+            seen = state_ptrs.setdefault(k, list(view.ptrs))
+            for slot, ptr in enumerate(view.ptrs):  # an origin's state never moves (no trackers: no flag / status pointers)
+                seen[slot] = seen[slot] or ptr
+                assert ptr in (seen[slot], 0) and (slot > 0 or ptr)
+            by_ptr[view.ptrs[0]] = k
+        assert len(by_ptr) == len(keys)
+        seg_of = np.repeat(np.arange(len(segments)), segments["count"])
+        expect = {k: (td, new, literal, last) for k, td, new, literal, last in want}
+        for rec, s in zip(origins, seg_of):
+            k = by_ptr[int(rec["d_delta"])]
+            td, new, literal, last = expect[k]
+            assert int(rec["timediff"]) == td
+            assert bool(rec["flags"] & ORIGIN_NEW) == new and bool(rec["flags"] & ORIGIN_LITERAL) == literal, (op, k)
+            seg = segments[s]
+            if zero_step:
+                assert seg["flags"] & SEG_ZERO_STEP
+            elif new:
+                assert seg["d_prev"] == 0  # created now: previous sample == this frame
+            else:
+                assert int(seg["d_prev"]) == prev_before[k] != 0  # steps from the frame IT saw last
+        # origins grouped in one segment share their last-seen frame (the converse need not hold: long groups are split)
+        for s in range(len(segments)):
+            members = {expect[by_ptr[int(r["d_delta"])]][3] for r in origins[segments["first"][s] : segments["first"][s] + segments["count"][s]]}
+            assert len(members) == 1 or zero_step
+        # afterwards: the pool holds exactly one sample per distinct last-seen frame, shared by its origins
+        st = eng.stats()
+        assert st.pool_frames - st.pool_free == len(set(model.last_frame.values()))
+        assert st.frames == model.frames
+        prev_now = {}
+        for k in model.t0:
+            view = eng.origins[k]
+            assert (view.timestep, view.updates, view.max_timediff) == (model.t0[k], model.updates[k], model.max_td[k])
+            prev_now.setdefault(model.last_frame[k], set()).add(view._info.d_prev)
+        assert all(len(ptrs) == 1 for ptrs in prev_now.values())
+        assert len({next(iter(p)) for p in prev_now.values()}) == len(prev_now)
+        assert eng.origins.keys() == model.order
+
+
+def test_refused_frames_leave_nothing_behind():
+    n = 90
+    eng = _engine(n)
+    pos, quat = _frame(n)
+    eng.step(10, pos, quat, [0])
+    # a frame before origin 0's first one: refused by the native engine before it creates origin 1
+    with pytest.raises(OverflowError):
+        eng.step(7, pos, quat, [1, 0])
+    assert 1 not in eng.origins and eng.origins.keys() == [0] and eng.stats().frames == 1
+    # a frame of the wrong shape: refused before the key gets a record, so its later creation starts at ITS timestep
+    with pytest.raises(RuntimeError):
+        eng.step(11, pos[:-1], quat, [0, 1])
+    assert 1 not in eng.origins
+    res = eng.step(15, pos, quat, [0, 1])
+    assert res.timediffs == [5, 0] and eng.origins[1].timestep == 15
+    # a batch that fails at its third frame: the first two are applied, the keys of the refused frame are forgotten
+    with pytest.raises(OverflowError):
+        eng.run([(16, pos, quat, [0, 1]), (17, pos, quat, [0, 1, 2]), (12, pos, quat, [0, 1, 3]), (18, pos, quat, [0, 4])])
+    assert eng.origins.keys() == [0, 1, 2] and 3 not in eng.origins and 4 not in eng.origins
+    assert eng.stats().frames == 4 and eng.origins[2].timestep == 17 and eng.origins[0].updates == 4
+    res = eng.step(20, pos, quat, [3, 0])
+    assert res.timediffs == [0, 10]
+    with pytest.raises(RuntimeError):
+        eng.run([(21, pos, quat, [0, 5]), (22, pos[:-1], quat, [0, 6])])  # nothing of this batch reaches the engine
+    assert 5 not in eng.origins and 6 not in eng.origins and eng.stats().frames == 5
