@@ -282,7 +282,7 @@ def process_frames(
             # own first frame (_read.py:135-141); this engine wraps every origin with the box of the first
             # frame of the file.  On constant-volume trajectories the two are the same; on NPT files the
             # minimum-image step of later origins uses a slightly different L (results differ only for
-            # steps within |dL| of L/2).  Documented deviation (DESIGN.md section 7).
+            # steps within |dL| of L/2).  Documented deviation (DESIGN.md section 8).
             logger.warning(
                 "box changes along the trajectory (%s -> %s): all origins are wrapped with the first frame's box",
                 engine.box[:2], np.asarray(frame.box)[:2],

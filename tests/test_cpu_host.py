@@ -320,3 +320,37 @@ def test_gsd_views_are_read_only_and_pinning_degrades_gracefully(tmp_path):
         if not torch.cuda.is_available():
             assert trj.pin() is False
         assert np.array_equal(trj[2].position, pos + 2)
+
+
+def test_process_file_host_loop_without_a_gpu(gsd_trajectory, tmp_path, monkeypatch):
+    """The whole host side of ``process_file`` (_read.py:82-195) -- schedule, key lists, native frame loop,
+    batch finalisation, table writers -- with a dry engine (all bookkeeping, no CUDA): one row per (frame, active
+    keyframe) with ``time = frame.timestep - first timestep of the keyframe``, in frame order."""
+    import functools
+
+    import pandas
+
+    from sdanalysis_b200.engine import DynamicsEngine
+    from sdanalysis_b200.read import _read
+
+    monkeypatch.setattr(_read, "DynamicsEngine", functools.partial(DynamicsEngine, dry=True))
+    for kwargs in (
+        dict(steps_max=100, linear_steps=None, keyframe_interval=10, keyframe_max=5),
+        dict(steps_max=300, linear_steps=10, keyframe_interval=50, keyframe_max=4),
+    ):
+        first, want = {}, []
+        for indexes, frame in read_gsd_trajectory(gsd_trajectory, **kwargs):
+            for key in indexes:
+                want.append((key, frame.timestep - first.setdefault(key, frame.timestep)))
+        assert len(first) > 3 and len(want) > 50
+        df = _read.process_file(gsd_trajectory, wave_number=2.9, mol_relaxations=[], **kwargs)
+        assert list(zip(df["keyframe"].tolist(), df["time"].tolist())) == want
+        assert {"msd", "alpha", "struct", "overlap", "temperature", "pressure"} <= set(df.columns)
+        out = tmp_path / f"out_{kwargs['steps_max']}.h5"
+        assert _read.process_file(gsd_trajectory, wave_number=2.9, mol_relaxations=[], outfile=out, **kwargs) is None
+        written = sorted(tmp_path.glob(f"out_{kwargs['steps_max']}*"))
+        assert written, "no table written"
+        for table in written:
+            if table.suffix == ".parquet":  # (no PyTables in this image: the dynamics table is a parquet file)
+                back = pandas.read_parquet(table)
+                assert list(zip(back["keyframe"].tolist(), back["time"].tolist())) == want
