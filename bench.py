@@ -25,8 +25,10 @@ Two regimes of that workload are timed (``regimes`` in the JSON line; ``--headli
 * ``parity``        rows and per-molecule state of two aged origins of THIS run against the CPU oracle.
 * ``cpu_baseline``  the CPU oracle (a numpy restatement of the reference; the reference itself cannot
              run here: freud/rowan/gsd are not installed) on the same frames, one core.
-* ``configs``       BASELINE.json configs[1] (32 k molecules, log-spaced and linear schedules) and configs[2]
-             (neighbours + orientational order + num_neighbours per frame) as sub-records (1 GPU only).
+* ``configs``       BASELINE.json configs[0] (the bundled-liquid trajectory through ``read.process_file``, the oracle
+             on the whole run beside it, every row compared), configs[1] (32 k molecules, log-spaced and linear
+             schedules) and configs[2] (neighbours + orientational order + num_neighbours per frame) as
+             sub-records (1 GPU only).
 * ``--impl reference``  the CPU arm alone: origin-parallel oracle processes on all host cores.
 """
 

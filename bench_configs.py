@@ -1,5 +1,10 @@
 """Sub-records of bench.py for the BASELINE.json configurations other than configs[3] (one GPU):
 
+* ``0_small``  configs[0], the reference's own CPU-runnable case.  The bundled trajectory blob is missing from the
+  reference checkout, so the bundled liquid dump (1250 molecules, ``tests/golden/liquid.npz``) is
+  frame 0 of a seeded Brownian trajectory on ``GenerateStepSeries(10000, 100, 1000, 500)`` (1901 frames, 11
+  origins, 2361 pairs), written as ``trajectory-Trimer-P13.50-T3.00.gsd`` and analysed by the public
+  ``read.process_file``; the oracle runs the WHOLE trajectory beside it and every row is compared.
 * ``1_exp`` / ``1_lin``  configs[1]: 32 768 molecules, 100 origins, 1000 frames; the reference's default
   log-spaced schedule ``GenerateStepSeries(1000, 10, 10, 100)`` (2405 (frame, origin) pairs) and the dense
   linear schedule (a new origin every 10 frames, 50 500 pairs).  ``value``: whole run with the frames
@@ -231,18 +236,162 @@ def _order_config(device, peak, cpu_baseline):
     return record
 
 
-def run_all(device, peak, cpu_baseline=True, tmpdir=None):
+def small_trajectory(seed=1):
+    """configs[0]: ``(box, [(timestep, indexes, position, orientation), ...])`` on the host -- the bundled liquid frame
+    followed by independent Gaussian steps (sigma 0.01 per component and timestep, 0.02 rad about z)."""
+    from sdanalysis_b200.synthetic import exponential_schedule
+
+    golden = np.load(Path(__file__).resolve().parent / "tests" / "golden" / "liquid.npz")
+    box = np.asarray(golden["box"], dtype=np.float32)
+    xy = np.asarray(golden["position"], dtype=np.float64)[:, :2].copy()
+    quat0 = np.asarray(golden["orientation"], dtype=np.float64)
+    theta = 2.0 * np.arctan2(quat0[:, 3], quat0[:, 0])
+    n = len(xy)
+    rng = np.random.default_rng(seed)
+    span = np.asarray(box[:2], dtype=np.float64)
+    frames, now = [], 0
+    for timestep, indexes in exponential_schedule(10000, 100, 1000, 500):
+        gap = timestep - now
+        if gap > 0:
+            xy += rng.normal(0.0, SIGMA_R * np.sqrt(gap), (n, 2))
+            theta += rng.normal(0.0, SIGMA_T * np.sqrt(gap), n)
+            xy -= span * np.floor(xy / span + 0.5)  # back into [-L/2, L/2)
+            now = timestep
+        pos = np.zeros((n, 3), dtype=np.float32)
+        pos[:, :2] = xy
+        quat = np.zeros((n, 4), dtype=np.float32)
+        quat[:, 0], quat[:, 3] = np.cos(theta / 2), np.sin(theta / 2)
+        frames.append((int(timestep), list(indexes), pos, quat))
+    return box, frames
+
+
+def _small_config(device, peak, cpu_baseline, tmpdir):
+    import tempfile
+
+    import torch
+
+    from sdanalysis_b200 import _lib
+    from sdanalysis_b200.engine import DynamicsEngine
+    from sdanalysis_b200.gsdio import GSDWriter
+    from sdanalysis_b200.molecules import Trimer
+    from sdanalysis_b200.read import process_file
+
+    box, frames = small_trajectory()
+    n = len(frames[0][2])
+    pairs = sum(len(ix) for _, ix, _, _ in frames)
+    updates = pairs * n
+    algo_bytes = sum(n * (65 * len(ix) + 28) for _, ix, _, _ in frames if ix)  # SURVEY 8(d), log-spaced schedule
+    resident = [(ts, torch.from_numpy(pos).to(device), torch.from_numpy(quat).to(device), ix) for ts, ix, pos, quat in frames]
+
+    def one_run():
+        engine = DynamicsEngine(n, box, WAVE_NUMBER, mol_sites=Trimer().positions, device=device, ring_depth=4)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _lib.launch_count()
+        t0.record()
+        rows = 0
+        for first in range(0, len(resident), 256):
+            for res in engine.run(resident[first : first + 256]):
+                rows += len(res.keys)
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1), rows, _lib.launch_count() - launches0
+
+    one_run()
+    runs = [one_run() for _ in range(5)]
+    ms = statistics.median(r[0] for r in runs)
+    assert runs[0][1] == pairs
+    record = {
+        "workload": f"configs[0]: bundled liquid dump ({n} molecules) + seeded Brownian trajectory, {len(frames)} frames, "
+                    f"{pairs} (frame, origin) pairs on GenerateStepSeries(10000, 100, 1000, 500), wave number {WAVE_NUMBER}",
+        "value": updates / (ms * 1e-3), "unit": "updates/s", "ms_per_frame": ms / len(frames), "ms_per_run": ms,
+        "runs_ms": [r[0] for r in runs], "gpu_launches": runs[0][2],
+        "roofline": {"bound": "hbm", "achieved": algo_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo_bytes / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_run": algo_bytes,
+                     "note": "whole run; at 1250 molecules a frame is 35 KB of state per origin: launch latency, not bandwidth"},
+    }
+    del resident
+
+    # ---- e2e: the reference's entry point on the trajectory file ----------------------------------------------
+    with tempfile.TemporaryDirectory(dir=tmpdir) as scratch:
+        path = Path(scratch) / "trajectory-Trimer-P13.50-T3.00.gsd"
+        with GSDWriter(path) as writer:
+            for ts, _, pos, quat in frames:
+                writer.append(ts, box, pos, quat, dimensions=2)
+        kwargs = dict(steps_max=10000, linear_steps=100, keyframe_interval=1000, keyframe_max=500)
+        process_file(path, WAVE_NUMBER, **kwargs)  # warm-up
+        times = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            df = process_file(path, WAVE_NUMBER, **kwargs)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+    assert len(df) == pairs, (len(df), pairs)
+    sec = statistics.median(times)
+    record["e2e"] = {
+        "value": updates / sec, "unit": "updates/s", "ms_per_frame": 1e3 * sec / len(frames), "seconds_per_run": sec, "rows": len(df),
+        "h2d_bytes_per_frame": 28 * n, "source": "read.process_file(GSD file) -> pandas.DataFrame, wall clock",
+    }
+
+    # ---- the oracle on the whole trajectory: CPU baseline and row-by-row parity ---------------------------------
+    if cpu_baseline:
+        record.update(small_oracle_leg(box, frames, df.to_dict("records")))
+    return record
+
+
+def small_oracle_leg(box, frames, got_rows):
+    """Time the oracle over every (frame, origin) pair of configs[0] and compare ``got_rows`` (process_file's rows,
+    in the reference's order: frame by frame, origins in index order) with its rows."""
+    from oracle import parity as opar
+
+    n = len(frames[0][2])
+    run = opar.OracleRun(WAVE_NUMBER)
+    t0 = time.perf_counter()
+    for ts, ix, pos, quat in frames:
+        run.frame(ts, box, pos, quat, ix)
+    sec = time.perf_counter() - t0
+    max_rel, failed = 0.0, []
+    if len(got_rows) != len(run.rows):
+        failed.append(f"row count {len(got_rows)} != {len(run.rows)}")
+    for i, (got, want) in enumerate(zip(got_rows, run.rows)):
+        if int(got["keyframe"]) != int(want["keyframe"]):
+            failed.append(f"row {i}: keyframe {got['keyframe']} != {want['keyframe']}")
+            continue
+        rel, bad = opar.compare_row(got, want, n)
+        max_rel = max(max_rel, rel)
+        failed.extend(f"row {i} (keyframe {want['keyframe']}, time {want['time']}): {name}" for name in bad)
+    return {
+        "cpu_baseline": {
+            "value": run.pairs * n / sec, "unit": "updates/s", "cores": 1, "kind": "port", "seconds_per_run": sec,
+            "sample": f"the whole trajectory: {run.pairs} (frame, origin) pairs, 1 process",
+        },
+        "parity": {"ok": not failed, "rows_checked": min(len(got_rows), len(run.rows)), "max_rel": max_rel,
+                   "failed": failed[:10], "bar": "15 quantities of every row: rtol 1e-5, counts exact, overlap exact unless tied"},
+    }
+
+
+def run_all(device, peak, cpu_baseline=True, tmpdir=None, only=None):
     tmpdir = tmpdir or ("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp")
     out = {}
+    wanted = lambda name: not only or name in only  # noqa: E731
+    if wanted("0_small"):
+        try:
+            out["0_small"] = _small_config(device, peak, cpu_baseline, tmpdir)
+        except Exception as exc:  # a sub-record must not take the headline line down with it
+            out["0_small"] = {"error": f"{type(exc).__name__}: {exc}"}
     for name, schedule in _schedules().items():
+        if not wanted(name):
+            continue
         try:
             out[name] = _dynamics_config(name, schedule, device, peak, cpu_baseline, tmpdir)
         except Exception as exc:  # a sub-record must not take the headline line down with it
             out[name] = {"error": f"{type(exc).__name__}: {exc}"}
-    try:
-        out["2_order"] = _order_config(device, peak, cpu_baseline)
-    except Exception as exc:
-        out["2_order"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if wanted("2_order"):
+        try:
+            out["2_order"] = _order_config(device, peak, cpu_baseline)
+        except Exception as exc:
+            out["2_order"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 
@@ -264,4 +413,5 @@ if __name__ == "__main__":
         peak = float(json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
     except (OSError, KeyError, ValueError):
         pass
-    print(json.dumps(run_all(torch.device("cuda", 0), peak, cpu_baseline="--no-cpu-baseline" not in sys.argv)))
+    names = [a for a in sys.argv[1:] if not a.startswith("--")]  # e.g. `python bench_configs.py 0_small 2_order`
+    print(json.dumps(run_all(torch.device("cuda", 0), peak, cpu_baseline="--no-cpu-baseline" not in sys.argv, only=names or None)))

@@ -114,3 +114,43 @@ def test_bench_parity_report_accepts_the_oracle_and_rejects_a_wrong_row():
     state[1][2]["tau_F"][17] += 1
     bad, _ = bench._oracle_parity(np, n, box, oracle_frames, pool_host, t_first, warmup, tables, state, followed)
     assert not bad["ok"] and bad["passage_mismatch"] == 1
+
+
+def test_config0_trajectory_and_its_oracle_leg():
+    """bench_configs' configs[0] record: the trajectory is the one SURVEY 8(d) describes (bundled liquid frame, 1901
+    frames, 11 origins, 2361 pairs on GenerateStepSeries(10000, 100, 1000, 500)); the oracle leg accepts the oracle's
+    own rows and reports a perturbed one."""
+    sys.path.insert(0, str(REPO))
+    sys.path.insert(0, str(REPO / "statdyn-analysis_b200"))
+    import numpy as np
+
+    import bench_configs
+    from oracle import parity as opar
+
+    box, frames = bench_configs.small_trajectory()
+    assert len(frames) == 1901 and sum(len(ix) for _, ix, _, _ in frames) == 2361
+    assert frames[0][0] == 0 and frames[-1][0] == 10000 and frames[-1][1] == list(range(11))
+    golden = np.load(REPO / "tests" / "golden" / "liquid.npz")
+    assert np.array_equal(frames[0][2], golden["position"]) and frames[0][2].shape == (1250, 3)
+    assert np.allclose(np.abs(frames[0][3]), np.abs(golden["orientation"]), atol=1e-6)  # (q and -q are one rotation)
+    half = np.asarray(box[:2]) / 2
+    for _, _, pos, quat in frames[::97]:
+        assert np.all(np.abs(pos[:, :2]) <= half + 1e-4) and not pos[:, 2].any() and not quat[:, 1:3].any()
+        assert np.allclose(np.linalg.norm(quat, axis=1), 1, atol=1e-6)
+    # mean squared displacement grows like 2 sigma^2 t (two components), crossing d = pi / (2 k) for a tail of molecules
+    step = frames[200][2][:, :2].astype(np.float64) - frames[0][2][:, :2]
+    step -= np.asarray(box[:2]) * np.rint(step / np.asarray(box[:2]))
+    assert 0.5 < np.mean(np.sum(step ** 2, axis=1)) / (2 * 0.01 ** 2 * frames[200][0]) < 2.0
+
+    sample = frames[:150]
+    run = opar.OracleRun(bench_configs.WAVE_NUMBER)
+    for ts, ix, pos, quat in sample:
+        run.frame(ts, box, pos, quat, ix)
+    rows = [dict(r) for r in run.rows]
+    leg = bench_configs.small_oracle_leg(box, sample, rows)
+    assert leg["parity"]["ok"] and leg["parity"]["rows_checked"] == len(rows) and leg["parity"]["max_rel"] == 0.0
+    assert leg["cpu_baseline"]["kind"] == "port" and leg["cpu_baseline"]["value"] > 0
+    rows[40]["msr"] = rows[40]["msr"] * (1 + 1e-3)
+    bad = bench_configs.small_oracle_leg(box, sample, rows)
+    assert not bad["parity"]["ok"] and "msr" in bad["parity"]["failed"][0]
+    assert not bench_configs.small_oracle_leg(box, sample, rows[:-1])["parity"]["ok"]
