@@ -354,3 +354,60 @@ def test_process_file_host_loop_without_a_gpu(gsd_trajectory, tmp_path, monkeypa
             if table.suffix == ".parquet":  # (no PyTables in this image: the dynamics table is a parquet file)
                 back = pandas.read_parquet(table)
                 assert list(zip(back["keyframe"].tolist(), back["time"].tolist())) == want
+
+
+def test_closed_forms_from_the_sums_reproduce_compute_all():
+    """Host half of ``Dynamics.compute_all`` without a GPU: the SDB_S_* sums (include/sdb200.h) taken in f64 from the
+    oracle's own accumulators, pushed through ``finalize_row`` / ``finalize_table``, give the oracle's 15 quantities
+    (dynamics.py:183-303), including NaN for alpha / alpha_rot / gamma at zero motion (SURVEY trap T3)."""
+    from oracle import parity as opar
+    from sdanalysis_b200 import _lib
+    from sdanalysis_b200.engine import ALL_QUANTITIES, finalize_row, finalize_table
+    from sdanalysis_b200.synthetic import SyntheticTrimer
+
+    n, wave_number = 900, 2.9
+    distance = np.pi / (2 * wave_number)
+    walk = SyntheticTrimer(n, seed=11, sigma_r=0.08, sigma_theta=0.2)
+    run = opar.OracleRun(wave_number)
+    sums, timediffs = [], []
+    for timestep in (0, 1, 4, 20, 90):
+        walk.advance(timestep - walk.timestep)
+        pos, quat = walk.frame()
+        run.frame(timestep, walk.box, pos, quat, [0])
+        dyn, _ = run.keyframes[0]
+        want = run.rows[-1]
+        dr = np.linalg.norm(dyn.delta_translation, axis=1)  # f32, like compute_displacement
+        th = np.linalg.norm(dyn.delta_rotation, axis=1)
+        if timestep == 0:
+            # rowan's to_euler(q / q) leaves +-2e-16 in some accumulators; their f32 square underflows in the reference's
+            # own msr^2, which is how it arrives at NaN.  The device state of a new origin is exactly zero.
+            assert th.max() < 1e-15
+            th = np.zeros_like(th)
+        d2, t2 = dr.astype(np.float64) ** 2, th.astype(np.float64) ** 2
+        s = np.zeros(_lib.SDB_NSUM)
+        s[_lib.S_DISP], s[_lib.S_DISP2], s[_lib.S_DISP4] = dr.astype(np.float64).sum(), d2.sum(), (d2 * d2).sum()
+        s[_lib.S_COMSTRUCT] = np.count_nonzero(dr < distance)
+        s[_lib.S_ROT], s[_lib.S_ROT2], s[_lib.S_ROT4] = th.astype(np.float64).sum(), t2.sum(), (t2 * t2).sum()
+        c = np.cos(th.astype(np.float64))
+        s[_lib.S_COS], s[_lib.S_COS2], s[_lib.S_D2R2] = c.sum(), (2 * c * c - 1).sum(), (d2 * t2).sum()
+        s[_lib.S_STRUCT] = round(float(want["struct"]) * n * 3)
+        s[_lib.S_OVERLAP] = round(float(want["overlap"]) * int(0.1 * n))
+        row = finalize_row(s, timestep, n, distance=distance, overlap_k=int(0.1 * n), n_sites=3)
+        assert list(row) == list(ALL_QUANTITIES) and len(row) == 15
+        max_rel, failed = opar.compare_row(row, want, n)
+        assert not failed and max_rel < 2e-6, (timestep, failed, max_rel)
+        if timestep == 0:
+            assert all(np.isnan(row[k]) for k in ("alpha", "alpha_rot", "gamma")) and want["_tie"]
+        sums.append(s)
+        timediffs.append(timestep)
+    table = finalize_table(np.array(sums), timediffs, n, distance=distance, overlap_k=int(0.1 * n), n_sites=3)
+    for i, s in enumerate(sums):
+        row = finalize_row(s, timediffs[i], n, distance=distance, overlap_k=int(0.1 * n), n_sites=3)
+        for key in ALL_QUANTITIES:
+            assert (np.isnan(row[key]) and np.isnan(table[key][i])) or row[key] == table[key][i], (key, i)
+    # without a wave number / overlap / sites the dependent quantities stay NaN; N < 10 divides by zero like the reference
+    bare = finalize_row(sums[1], 1, n)
+    assert all(np.isnan(bare[k]) for k in ("com_struct", "struct", "overlap", "scattering_function"))
+    with pytest.raises(ZeroDivisionError):
+        finalize_row(sums[1], 1, 9, overlap_k=0)
+    assert np.isnan(finalize_row(sums[1], 1, 9, overlap_k=0, strict=False)["overlap"])
