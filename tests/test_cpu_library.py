@@ -199,3 +199,34 @@ def test_c_client_drives_the_frame_loop_through_the_header_alone(c_client):
     assert out[13] == "oldest key 1 timestep 3 updates 9 max_timediff 8 stride 1000"
     assert out[14] == "unknown key rc -1"
     assert out[15] == "stats frames 12 updates 27000 origins 3"
+
+
+def test_integration_md_ctypes_stub_runs_as_written(lib):
+    """The reference-side binding shown in INTEGRATION.md (level 2) is executed verbatim -- only the library path and
+    the dry flag are supplied -- so its struct layouts, signatures and loop cannot drift from the library."""
+    from types import SimpleNamespace
+
+    from sdanalysis_b200 import _lib
+
+    text = (REPO / "INTEGRATION.md").read_text()
+    start = text.index("# sdanalysis/_b200.py")
+    code = text[start : text.index("```", start)]
+    assert 'C.CDLL("libsdb200.so")' in code
+    scope = {}
+    exec(compile(code.replace('C.CDLL("libsdb200.so")', f'C.CDLL("{_lib.LIB_PATH}")'), "INTEGRATION.md", "exec"), scope)
+    for name, mirror in (("Tracker", _lib.SdbTracker), ("EngineConfig", _lib.SdbEngineConfig), ("Frame", _lib.SdbFrame)):
+        assert ctypes.sizeof(scope[name]) == ctypes.sizeof(mirror)
+        assert [(f, getattr(scope[name], f).offset) for f, _ in scope[name]._fields_] == [
+            (f, getattr(mirror, f).offset) for f, *_ in mirror._fields_]
+    n = 64
+    cfg = scope["EngineConfig"](n=n, wave_number=2.9, com_cut_lt=0.29, compute_sums=1, overlap_k=n // 10, ring_depth=4,
+                                flags=_lib.SDB_ENGINE_DRY)
+    cfg.box[0] = cfg.box[1] = 20.0
+    cfg.box[2] = 1.0
+    rng = np.random.default_rng(0)
+    quat = np.zeros((n, 4), np.float32)
+    quat[:, 0] = 1
+    frames = [([k for k in range(t // 4 + 1)], SimpleNamespace(timestep=t, position=rng.normal(size=(n, 3)), orientation=quat))
+              for t in range(10)]
+    got = [(key, int(td), sums.shape) for key, td, sums in scope["process_frames"](iter(frames), cfg)]
+    assert got == [(k, t - 4 * k, (16,)) for t in range(10) for k in range(t // 4 + 1)]
