@@ -230,3 +230,15 @@ def test_integration_md_ctypes_stub_runs_as_written(lib):
               for t in range(10)]
     got = [(key, int(td), sums.shape) for key, td, sums in scope["process_frames"](iter(frames), cfg)]
     assert got == [(k, t - 4 * k, (16,)) for t in range(10) for k in range(t // 4 + 1)]
+
+
+def test_every_export_is_documented_in_integration_md():
+    """INTEGRATION.md's table names the reference interface behind every entry point of include/sdb200.h
+    (lists such as ``sdb_engine_create / destroy / step`` share their prefix)."""
+    header = (REPO / "include" / "sdb200.h").read_text()
+    doc = (REPO / "INTEGRATION.md").read_text()
+    named = set(re.findall(r"\bsdb_[a-z0-9_]+", doc))
+    for match in re.finditer(r"`(sdb_[a-z0-9]+_)([a-z0-9_]+)((?: / [a-z0-9_]+)+)`", doc):
+        named.update(match.group(1) + tail for tail in match.group(3).split(" / ")[1:])
+    declared = set(re.findall(r"\b(sdb_[a-z0-9_]+)\s*\(", header))
+    assert not declared - named, sorted(declared - named)
