@@ -98,9 +98,21 @@ class GSDTrajectory:
     def __init__(self, filename):
         self.filename = Path(filename)
         self._fh = open(self.filename, "rb")
-        self._mm = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
-        if len(self._mm) < _HEADER.size:
-            raise RuntimeError(f"{filename}: not a GSD file (too short)")
+        try:
+            if os.fstat(self._fh.fileno()).st_size < _HEADER.size:
+                raise RuntimeError(f"{filename}: not a GSD file (too short)")
+            self._mm = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
+            try:
+                self._read_index(filename)
+            except (ValueError, IndexError, struct.error, UnicodeDecodeError) as exc:
+                # index or name list outside the file, name ids outside the name list: like the gsd package
+                # (RuntimeError for a file it cannot index), so callers catch one exception type
+                raise RuntimeError(f"{filename}: corrupt GSD file ({exc})") from exc
+        except Exception:
+            self._fh.close()
+            raise
+
+    def _read_index(self, filename):
         (magic, iloc, ialloc, nloc, nalloc, self.schema_version, self.gsd_version, app, schema) = _HEADER.unpack_from(
             self._mm, 0
         )

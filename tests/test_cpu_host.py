@@ -411,3 +411,42 @@ def test_closed_forms_from_the_sums_reproduce_compute_all():
     with pytest.raises(ZeroDivisionError):
         finalize_row(sums[1], 1, 9, overlap_k=0)
     assert np.isnan(finalize_row(sums[1], 1, 9, overlap_k=0, strict=False)["overlap"])
+
+
+def test_gsd_reader_reports_corruption_as_runtime_error(tmp_path):
+    """Like the gsd package: a file that cannot be indexed raises RuntimeError when opened, a frame whose data lie
+    outside the file raises RuntimeError when it is read -- which is what the reference's loops skip
+    (_read.py:218-224, _gsd.py:100-109)."""
+    from sdanalysis_b200 import gsdio
+    from sdanalysis_b200.gsdio import open_gsd
+
+    path = tmp_path / "ok.gsd"
+    rng = np.random.default_rng(0)
+    quat = np.tile(np.array([1, 0, 0, 0], np.float32), (50, 1))
+    with GSDWriter(path) as dst:
+        for step in range(6):
+            dst.append(step, [10, 10, 1, 0, 0, 0], rng.random((50, 3)).astype(np.float32), quat)
+    data = path.read_bytes()
+    for name, blob in (("empty", b""), ("short", data[:100]), ("zeros", bytes(400)), ("truncated", data[: len(data) - 700])):
+        bad = tmp_path / f"{name}.gsd"
+        bad.write_bytes(blob)
+        with pytest.raises(RuntimeError):
+            open_gsd(bad)
+    # one chunk of frame 3 pointing past the end of the file: that frame alone is unreadable
+    with open_gsd(path) as trj:
+        assert len(trj) == 6
+    header = gsdio._HEADER.unpack_from(data, 0)
+    index_location, allocated = header[1], header[2]
+    index = np.frombuffer(data, dtype=gsdio._ENTRY, count=allocated, offset=index_location).copy()
+    hit = np.flatnonzero((index["frame"] == 3) & (index["N"] == 50))[0]
+    index["location"][hit] = len(data) + 4096
+    patched = bytearray(data)
+    patched[index_location : index_location + index.nbytes] = index.tobytes()
+    broken = tmp_path / "broken.gsd"
+    broken.write_bytes(bytes(patched))
+    with open_gsd(broken) as trj:
+        assert len(trj) == 6 and trj[2].step == 2
+        with pytest.raises(RuntimeError):
+            trj[3]
+    assert [f.timestep for f in open_trajectory(broken)] == [0, 1, 2, 4, 5]
+    assert [f.timestep for _, f in read_gsd_trajectory(broken, steps_max=5, linear_steps=None)] == [0, 1, 2, 4, 5]
