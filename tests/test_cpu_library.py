@@ -100,6 +100,43 @@ def test_rotation_increment_helper_matches_oracle(lib):
     assert lib.sdb_test_rot_increment(0.6, 0.8, 0.6, 0.8, ctypes.byref(bad)) == 0.0 and bad.value == 0
 
 
+def test_wrap_and_rotation_increment_edge_cases(lib):
+    """The same two helpers where the rounding is delicate: coordinates within a few ulps of 0, +-L/2, +-L, +-3L/2,
+    2L and far outside the box, signed zeros and denormals; quaternion quotients next to the +-pi branch cut, after a
+    full turn, below f32 resolution, and with one operand negated (q and -q are one rotation)."""
+    ox, oy = ctypes.c_float(), ctypes.c_float()
+    for lx, ly, xy in [(62.75029, 108.68669, 0.0), (10.0, 7.0, 0.3), (2236.068, 2236.068, 0.0), (4472.136, 4472.136, 0.0)]:
+        specials = [-0.0, 1e-30, -1e-30, 1e-45, -1e-45]
+        for base in (0.0, lx / 2, -lx / 2, lx, -lx, 1.5 * lx, -1.5 * lx, 2 * lx, 1e6, -1e6, 3e7):
+            for k in range(-3, 4):
+                x = np.float32(base)
+                for _ in range(abs(k)):
+                    x = np.nextafter(x, np.float32(np.inf if k > 0 else -np.inf))
+                specials.append(float(x))
+        m = len(specials)
+        v = np.zeros((2 * m, 3), np.float32)
+        v[:m, 0], v[:m, 1] = specials, np.float32(ly) / 3
+        v[m:, 1], v[m:, 0] = specials, np.float32(lx) / 3
+        want = Box(lx, ly, xy=xy, is2D=True).wrap(v)
+        for i in range(2 * m):
+            lib.sdb_test_wrap2d(lx, ly, xy, v[i, 0], v[i, 1], ctypes.byref(ox), ctypes.byref(oy))
+            assert np.float32(ox.value) == want[i, 0] and np.float32(oy.value) == want[i, 1], (lx, v[i])
+    rng = np.random.default_rng(3)
+    n = 2000
+    th0 = rng.uniform(-np.pi, np.pi, n)
+    step = np.concatenate([np.pi + rng.normal(0, 1e-4, n // 4), -np.pi + rng.normal(0, 1e-4, n // 4),
+                           rng.normal(0, 1e-7, n // 4), 2 * np.pi + rng.normal(0, 1e-3, n - 3 * (n // 4))])
+    q0 = np.zeros((n, 4), np.float32)
+    q1 = np.zeros((n, 4), np.float32)
+    q0[:, 0], q0[:, 3] = np.cos(th0 / 2), np.sin(th0 / 2)
+    q1[:, 0], q1[:, 3] = np.cos((th0 + step) / 2), np.sin((th0 + step) / 2)
+    q1[::2] *= -1
+    want = rowan.to_euler(rowan.divide(q1, q0))[:, 0]
+    bad = ctypes.c_int32(0)
+    got = np.array([lib.sdb_test_rot_increment(q1[i, 0], q1[i, 3], q0[i, 0], q0[i, 3], ctypes.byref(bad)) for i in range(n)])
+    assert np.max(np.abs(got - want)) < 4e-15  # in particular: the same side of the branch cut as rowan's atan2
+
+
 def test_threshold_cuts_are_exact():
     """disp2 >= cut  <=>  fl32(sqrt(disp2)) > thr, checked on both sides of every cut."""
     from sdanalysis_b200.engine import _cut_direct, _cut_sqrt
